@@ -1,0 +1,139 @@
+/*
+ * rxcuda.h -- C-ABI of librxcuda.so: the B200 (sm_100a) implementation of rustworkx's
+ * all-sources unweighted BFS hot path.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one generic
+ * function of the reference's `rustworkx-core` crate, i.e. exactly what a `rustworkx-cuda` crate's
+ * `extern "C"` block would bind (see INTEGRATION.md for the Rust and ctypes stubs):
+ *
+ *   rxc_betweenness*       <- rustworkx-core/src/centrality.rs:70-132   betweenness_centrality
+ *   rxc_edge_betweenness*  <- rustworkx-core/src/centrality.rs:174-219  edge_betweenness_centrality
+ *   rxc_closeness*         <- rustworkx-core/src/centrality.rs:1166-1224 closeness_centrality
+ *   rxc_distance_matrix    <- rustworkx-core/src/shortest_path/distance_matrix.rs:71-159
+ *   rxc_rescale            <- rustworkx-core/src/centrality.rs:221-252  _rescale
+ *   rxc_graph_snapshot     <- the petgraph StableGraph borrowed as `&graph.graph` by the pyo3
+ *                             wrappers at src/centrality.rs:83-98,151-166,310-323,371-384,592-606,
+ *                             654-668 and src/shortest_path/mod.rs:1559-1573,1601-1614
+ *
+ * Plain pointers and sizes only; no torch / numpy types.  All functions return 0 on success or a
+ * negative rxc_status; rxc_last_error() gives the message for the calling thread.  There is NO CPU
+ * fallback: without a CUDA device every compute entry point fails with RXC_ERR_CUDA.
+ *
+ * Index conventions follow the reference: node-keyed outputs are dense over [0, n_bound) in ORIGINAL
+ * node indices (holes left at 0.0 -- the caller drops them, src/centrality.rs:91-97), edge-keyed
+ * outputs are dense over [0, e_bound) in original edge indices, and the distance matrix is
+ * n_live x n_live over live nodes in ascending-index (compacted) order.
+ */
+#ifndef RXCUDA_H
+#define RXCUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    RXC_OK = 0,
+    RXC_ERR_INVALID = -1, /* bad argument */
+    RXC_ERR_CUDA = -2,    /* CUDA runtime error / no device */
+    RXC_ERR_OOM = -3,     /* device or host allocation failed */
+    RXC_ERR_NCCL = -4,    /* NCCL not loadable or NCCL error */
+    RXC_ERR_LIMIT = -5    /* graph exceeds supported index width */
+} rxc_status;
+
+typedef struct rxc_graph rxc_graph;
+
+/* Work and timing counters of the last compute call on a handle. */
+typedef struct {
+    uint64_t te;          /* traversed (source, arc) pairs: sum_s sum_{v reached} deg(v)        */
+    uint64_t te_dag;      /* (source, arc) pairs on shortest-path DAGs (betweenness only)        */
+    uint64_t v;           /* (source, vertex) pairs reached                                      */
+    uint64_t sources;     /* sources processed                                                   */
+    uint64_t levels;      /* BFS level launches (sum over batches)                               */
+    uint64_t launches;    /* kernels launched by the call                                        */
+    uint64_t batches;     /* source batches                                                      */
+    double ms_total;      /* device time, first to last kernel of the call (CUDA events)         */
+    double ms_forward;    /* device time in BFS / sigma kernels                                  */
+    double ms_backward;   /* device time in dependency kernels                                   */
+    double ms_snapshot;   /* host CSR build + H2D of the snapshot (wall clock)                   */
+    double ms_d2h;        /* device-to-host result copies                                        */
+} rxc_stats;
+
+/* ---- library / device ------------------------------------------------------------------------- */
+const char *rxc_version(void);
+const char *rxc_last_error(void);
+int rxc_device_count(void);       /* 0 when no CUDA device is usable */
+int rxc_set_device(int device);   /* device used by subsequent rxc_graph_snapshot calls */
+int rxc_get_device(void);
+
+/* ---- snapshot: StableGraph -> compact int32 CSR/CSC in HBM ---------------------------------------
+ * live_nodes[n_live]: ascending original indices of live nodes (PyGraph.node_indices()).
+ * edge_src/edge_dst/edge_id[n_edges]: endpoints (original node indices) and original edge index of
+ * every live edge (PyGraph.edge_list() / edge_indices()).  Parallel edges are kept (path
+ * multiplicity, centrality.rs:433-436); self-loops are dropped (no effect on BFS).  The snapshot is
+ * a copy: the caller's graph may change afterwards. */
+int rxc_graph_snapshot(uint32_t n_bound, const uint32_t *live_nodes, uint32_t n_live,
+                       uint32_t e_bound, const uint32_t *edge_src, const uint32_t *edge_dst,
+                       const uint32_t *edge_id, uint64_t n_edges, int directed,
+                       rxc_graph **out_graph);
+void rxc_graph_free(rxc_graph *g);
+int rxc_graph_info(const rxc_graph *g, uint32_t *n_bound, uint32_t *n_live, uint32_t *e_bound,
+                   uint64_t *n_arcs, int *directed);
+
+/* ---- full calls (all live sources, final scaling applied; outputs are HOST buffers) -------------- */
+int rxc_betweenness(rxc_graph *g, int include_endpoints, int normalized,
+                    double *out /* n_bound */);
+int rxc_edge_betweenness(rxc_graph *g, int normalized, double *out /* e_bound */);
+int rxc_closeness(rxc_graph *g, int wf_improved, double *out /* n_bound */);
+int rxc_distance_matrix(rxc_graph *g, int as_undirected, double null_value,
+                        double *out /* n_live * n_live, row-major */);
+
+/* ---- partial calls: a subset of sources (ORIGINAL node indices), no final scaling.  This is the
+ * unit a rank runs when sources are sharded across GPUs; partial vectors are additive.
+ * `out` is zero-initialised by the call. ----------------------------------------------------------- */
+int rxc_betweenness_partial(rxc_graph *g, const uint32_t *sources, uint64_t n_sources,
+                            int include_endpoints, double *out /* n_bound */);
+int rxc_edge_betweenness_partial(rxc_graph *g, const uint32_t *sources, uint64_t n_sources,
+                                 double *out /* e_bound */);
+/* closeness of the listed nodes only: out[i] for sources[i] */
+int rxc_closeness_partial(rxc_graph *g, const uint32_t *sources, uint64_t n_sources,
+                          int wf_improved, double *out /* n_sources */);
+/* rows of the distance matrix for live-node ranks [row_begin, row_end) */
+int rxc_distance_matrix_rows(rxc_graph *g, int as_undirected, double null_value,
+                             uint32_t row_begin, uint32_t row_end,
+                             double *out /* (row_end-row_begin) * n_live */);
+
+/* _rescale (centrality.rs:221-252): multiply by the precomputed reciprocal, on the host. */
+void rxc_rescale(double *x, uint64_t len, uint64_t node_count, int normalized, int directed,
+                 int include_endpoints);
+
+/* ---- multi-GPU: one process per GPU, sources sharded, ONE reduce at the end ------------------------
+ * NCCL is dlopen()ed (libnccl.so.2); the 128-byte unique id travels over the caller's own
+ * rendezvous (torch.distributed / MPI / a file). */
+int rxc_comm_unique_id(uint8_t id_out[128]);
+int rxc_comm_init(int rank, int world, const uint8_t id[128]);
+int rxc_comm_reduce_sum_f64(double *host_inout, uint64_t len, int root);
+int rxc_comm_barrier(void);
+void rxc_comm_destroy(void);
+
+/* ---- instrumentation --------------------------------------------------------------------------- */
+int rxc_get_stats(const rxc_graph *g, rxc_stats *out);
+/* Tunables (0 = library default): sources per batch for the centrality kernels. */
+int rxc_set_option(const char *name, int64_t value);
+
+/* ---- benchmark inputs (host-side restatement of the reference's seeded generators;
+ *      rustworkx-core/src/generators/random_graph.rs:249-345,402-466,756-824).  Each writes at most
+ *      `cap` edges and returns the number of edges generated (or a negative rxc_status). -------------- */
+int64_t rxc_gen_gnp(uint32_t n, double p, uint64_t seed, int directed, uint32_t *src,
+                    uint32_t *dst, uint64_t cap);
+int64_t rxc_gen_gnm(uint32_t n, uint64_t m, uint64_t seed, int directed, uint32_t *src,
+                    uint32_t *dst, uint64_t cap);
+int64_t rxc_gen_barabasi_albert(uint32_t n, uint32_t m, uint64_t seed, uint32_t *src,
+                                uint32_t *dst, uint64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RXCUDA_H */

@@ -1,0 +1,228 @@
+"""rustworkx_b200 -- B200-native drop-in for rustworkx's all-sources unweighted BFS hot path.
+
+Mirrors the names and signatures of the reference for exactly this path:
+
+* universal dispatchers ``betweenness_centrality``, ``edge_betweenness_centrality``,
+  ``closeness_centrality``, ``distance_matrix`` (``rustworkx/__init__.py:138-179,1164-1263,1438-1479``)
+* typed functions ``graph_*`` / ``digraph_*`` (``src/centrality.rs:83-98,151-166,310-323,371-384,
+  592-606,654-668``; ``src/shortest_path/mod.rs:1559-1573,1601-1614``)
+* return types ``CentralityMapping`` / ``EdgeCentralityMapping`` (``src/iterators.rs:1769-1809``)
+
+All computation happens in ``librxcuda.so`` (hand-written sm_100a kernels behind the C-ABI of
+``include/rxcuda.h``).  There is no CPU fallback: a missing extension or GPU raises.
+"""
+
+from __future__ import annotations
+
+import functools
+
+import numpy as np
+
+from . import generators  # noqa: F401
+from ._lib import DeviceGraph, RxCudaError  # noqa: F401
+from .graph import (  # noqa: F401
+    EdgeIndices,
+    EdgeList,
+    InvalidNode,
+    NodeIndices,
+    NoEdgeBetweenNodes,
+    PyDAG,
+    PyDiGraph,
+    PyGraph,
+)
+from .iterators import CentralityMapping, EdgeCentralityMapping  # noqa: F401
+from .random_graph import (  # noqa: F401
+    barabasi_albert_graph,
+    directed_gnm_random_graph,
+    directed_gnp_random_graph,
+    undirected_gnm_random_graph,
+    undirected_gnp_random_graph,
+)
+
+__version__ = "0.1.0"
+
+
+# ---------------------------------------------------------------------------------------------
+# argument extraction with pyo3's error behaviour
+# ---------------------------------------------------------------------------------------------
+def _usize(x, name):
+    """pyo3 ``usize`` extraction: ints only; negative -> OverflowError."""
+    if isinstance(x, (bool, np.bool_)):
+        x = int(x)
+    if not isinstance(x, (int, np.integer)):
+        raise TypeError(
+            f"argument '{name}': '{type(x).__name__}' object cannot be interpreted as an integer"
+        )
+    if x < 0:
+        raise OverflowError("can't convert negative int to unsigned")
+    return int(x)
+
+
+def _bool(x, name):
+    """pyo3 ``bool`` extraction: real bools (or numpy bools) only."""
+    if isinstance(x, (bool, np.bool_)):
+        return bool(x)
+    raise TypeError(f"argument '{name}': '{type(x).__name__}' object cannot be converted to 'PyBool'")
+
+
+def _f64(x, name):
+    if isinstance(x, (bool, np.bool_)) or not isinstance(x, (int, float, np.integer, np.floating)):
+        raise TypeError(f"argument '{name}': must be real number, not {type(x).__name__}")
+    return float(x)
+
+
+def _graph_arg(graph, cls, name):
+    if not isinstance(graph, cls) or (cls is PyGraph and isinstance(graph, PyDiGraph)):
+        raise TypeError(
+            f"argument 'graph': '{type(graph).__name__}' object cannot be converted to '{name}'"
+        )
+    return graph
+
+
+# ---------------------------------------------------------------------------------------------
+# snapshot cache: one device CSR per graph version (mutating the graph invalidates it)
+# ---------------------------------------------------------------------------------------------
+_SNAPSHOT_CACHE = True
+
+
+def set_snapshot_cache(enabled):
+    """Enable/disable re-use of the device snapshot across calls on an unchanged graph."""
+    global _SNAPSHOT_CACHE
+    _SNAPSHOT_CACHE = bool(enabled)
+
+
+def device_snapshot(graph):
+    """StableGraph -> compact CSR/CSC in HBM (``rxc_graph_snapshot``)."""
+    version = getattr(graph, "_version", None)
+    if _SNAPSHOT_CACHE and version is not None:
+        cached = graph.__dict__.get("_rxc_snapshot")
+        if cached is not None and cached[0] == version:
+            return cached[1]
+    dg = DeviceGraph.from_graph(graph)
+    if _SNAPSHOT_CACHE and version is not None:
+        graph.__dict__["_rxc_snapshot"] = (version, dg)
+    return dg
+
+
+def _node_mapping(dg, dense):
+    # binding: enumerate().filter_map(|(i, v)| v.map(|x| (i, x))), src/centrality.rs:91-97
+    keys = dg.live_nodes.astype(np.int64)
+    return CentralityMapping._from_arrays(keys, dense[keys] if keys.size else np.zeros(0))
+
+
+def _edge_mapping(dg, dense):
+    keys = np.sort(dg.edge_id.astype(np.int64))
+    return EdgeCentralityMapping._from_arrays(keys, dense[keys] if keys.size else np.zeros(0))
+
+
+# ---------------------------------------------------------------------------------------------
+# typed functions (positional-only graph, as in the pyo3 text_signature)
+# ---------------------------------------------------------------------------------------------
+def _betweenness(graph, normalized, endpoints, parallel_threshold):
+    normalized = _bool(normalized, "normalized")
+    endpoints = _bool(endpoints, "endpoints")
+    _usize(parallel_threshold, "parallel_threshold")  # scheduling hint only; results never depend on it
+    dg = device_snapshot(graph)
+    # note the argument swap: core order is (include_endpoints, normalized), src/centrality.rs:90
+    return _node_mapping(dg, dg.betweenness(endpoints, normalized))
+
+
+def graph_betweenness_centrality(graph, /, normalized=True, endpoints=False, parallel_threshold=50):
+    """``rustworkx.graph_betweenness_centrality`` (``src/centrality.rs:83-98``)."""
+    return _betweenness(_graph_arg(graph, PyGraph, "PyGraph"), normalized, endpoints,
+                        parallel_threshold)
+
+
+def digraph_betweenness_centrality(graph, /, normalized=True, endpoints=False, parallel_threshold=50):
+    """``rustworkx.digraph_betweenness_centrality`` (``src/centrality.rs:151-166``)."""
+    return _betweenness(_graph_arg(graph, PyDiGraph, "PyDiGraph"), normalized, endpoints,
+                        parallel_threshold)
+
+
+def _edge_betweenness(graph, normalized, parallel_threshold):
+    normalized = _bool(normalized, "normalized")
+    _usize(parallel_threshold, "parallel_threshold")
+    dg = device_snapshot(graph)
+    return _edge_mapping(dg, dg.edge_betweenness(normalized))
+
+
+def graph_edge_betweenness_centrality(graph, /, normalized=True, parallel_threshold=50):
+    """``rustworkx.graph_edge_betweenness_centrality`` (``src/centrality.rs:592-606``)."""
+    return _edge_betweenness(_graph_arg(graph, PyGraph, "PyGraph"), normalized, parallel_threshold)
+
+
+def digraph_edge_betweenness_centrality(graph, /, normalized=True, parallel_threshold=50):
+    """``rustworkx.digraph_edge_betweenness_centrality`` (``src/centrality.rs:654-668``)."""
+    return _edge_betweenness(_graph_arg(graph, PyDiGraph, "PyDiGraph"), normalized,
+                             parallel_threshold)
+
+
+def _closeness(graph, wf_improved, parallel_threshold):
+    wf_improved = _bool(wf_improved, "wf_improved")
+    _usize(parallel_threshold, "parallel_threshold")
+    dg = device_snapshot(graph)
+    return _node_mapping(dg, dg.closeness(wf_improved))
+
+
+def graph_closeness_centrality(graph, wf_improved=True, parallel_threshold=50):
+    """``rustworkx.graph_closeness_centrality`` (``src/centrality.rs:310-323``)."""
+    return _closeness(_graph_arg(graph, PyGraph, "PyGraph"), wf_improved, parallel_threshold)
+
+
+def digraph_closeness_centrality(graph, wf_improved=True, parallel_threshold=50):
+    """``rustworkx.digraph_closeness_centrality`` (``src/centrality.rs:371-384``)."""
+    return _closeness(_graph_arg(graph, PyDiGraph, "PyDiGraph"), wf_improved, parallel_threshold)
+
+
+def graph_distance_matrix(graph, /, parallel_threshold=300, null_value=0.0):
+    """``rustworkx.graph_distance_matrix`` (``src/shortest_path/mod.rs:1601-1614``): no
+    ``as_undirected`` keyword; the core is called with ``as_undirected=true`` (:1610)."""
+    graph = _graph_arg(graph, PyGraph, "PyGraph")
+    _usize(parallel_threshold, "parallel_threshold")
+    null_value = _f64(null_value, "null_value")
+    return device_snapshot(graph).distance_matrix(True, null_value)
+
+
+def digraph_distance_matrix(graph, /, parallel_threshold=300, as_undirected=False, null_value=0.0):
+    """``rustworkx.digraph_distance_matrix`` (``src/shortest_path/mod.rs:1559-1573``)."""
+    graph = _graph_arg(graph, PyDiGraph, "PyDiGraph")
+    _usize(parallel_threshold, "parallel_threshold")
+    as_undirected = _bool(as_undirected, "as_undirected")
+    null_value = _f64(null_value, "null_value")
+    return device_snapshot(graph).distance_matrix(as_undirected, null_value)
+
+
+# ---------------------------------------------------------------------------------------------
+# universal dispatchers (rustworkx/__init__.py:138-147)
+# ---------------------------------------------------------------------------------------------
+def _rustworkx_dispatch(func):
+    """Dispatch a universal function to its ``graph_`` / ``digraph_`` typed variant."""
+    func_name = func.__name__
+    wrapped_func = functools.singledispatch(func)
+    wrapped_func.register(PyDiGraph, globals()[f"digraph_{func_name}"])
+    wrapped_func.register(PyGraph, globals()[f"graph_{func_name}"])
+    return wrapped_func
+
+
+@_rustworkx_dispatch
+def distance_matrix(graph, parallel_threshold=300, as_undirected=False, null_value=0.0):
+    """Get the distance matrix for a graph (``rustworkx/__init__.py:150-179``)."""
+    raise TypeError(f"Invalid Input Type {type(graph)} for graph")
+
+
+@_rustworkx_dispatch
+def betweenness_centrality(graph, normalized=True, endpoints=False, parallel_threshold=50):
+    """Betweenness centrality of each node (``rustworkx/__init__.py:1164-1208``)."""
+    raise TypeError(f"Invalid Input Type {type(graph)} for graph")
+
+
+@_rustworkx_dispatch
+def closeness_centrality(graph, wf_improved=True, parallel_threshold=50):
+    """Closeness centrality of each node (``rustworkx/__init__.py:1211-1263``)."""
+    raise TypeError(f"Invalid Input Type {type(graph)} for graph")
+
+
+@_rustworkx_dispatch
+def edge_betweenness_centrality(graph, normalized=True, parallel_threshold=50):
+    """Edge betweenness centrality of each edge (``rustworkx/__init__.py:1438-1479``)."""
+    raise TypeError(f"Invalid Input Type {type(graph)} for graph")

@@ -1,0 +1,252 @@
+"""ctypes binding of ``librxcuda.so`` (the C-ABI declared in ``include/rxcuda.h``).
+
+This is the Python-side stub a maintainer would otherwise write in Rust inside a ``rustworkx-cuda``
+crate.  The shared library is built in-tree by
+``rustworkx_b200/csrc/Makefile`` (``__graft_entry__.build()``); if it is missing, or no CUDA device
+is usable, every hot-path call raises -- there is NO CPU fallback.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librxcuda.so")
+
+RXC_OK = 0
+RXC_ERR_INVALID = -1
+RXC_ERR_CUDA = -2
+RXC_ERR_OOM = -3
+RXC_ERR_NCCL = -4
+RXC_ERR_LIMIT = -5
+
+
+class RxCudaError(RuntimeError):
+    """Raised when librxcuda reports a CUDA / NCCL / argument error."""
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("te", C.c_uint64),
+        ("te_dag", C.c_uint64),
+        ("v", C.c_uint64),
+        ("sources", C.c_uint64),
+        ("levels", C.c_uint64),
+        ("launches", C.c_uint64),
+        ("batches", C.c_uint64),
+        ("ms_total", C.c_double),
+        ("ms_forward", C.c_double),
+        ("ms_backward", C.c_double),
+        ("ms_snapshot", C.c_double),
+        ("ms_d2h", C.c_double),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/rxcuda.h declares: name -> (restype, argtypes)
+_u8p = C.POINTER(C.c_uint8)
+_u32p = C.POINTER(C.c_uint32)
+_f64p = C.POINTER(C.c_double)
+_vp = C.c_void_p
+SYMBOLS = {
+    "rxc_version": (C.c_char_p, []),
+    "rxc_last_error": (C.c_char_p, []),
+    "rxc_device_count": (C.c_int, []),
+    "rxc_set_device": (C.c_int, [C.c_int]),
+    "rxc_get_device": (C.c_int, []),
+    "rxc_graph_snapshot": (C.c_int, [C.c_uint32, _u32p, C.c_uint32, C.c_uint32, _u32p, _u32p, _u32p,
+                                     C.c_uint64, C.c_int, C.POINTER(_vp)]),
+    "rxc_graph_free": (None, [_vp]),
+    "rxc_graph_info": (C.c_int, [_vp, _u32p, _u32p, _u32p, C.POINTER(C.c_uint64),
+                                 C.POINTER(C.c_int)]),
+    "rxc_betweenness": (C.c_int, [_vp, C.c_int, C.c_int, _f64p]),
+    "rxc_edge_betweenness": (C.c_int, [_vp, C.c_int, _f64p]),
+    "rxc_closeness": (C.c_int, [_vp, C.c_int, _f64p]),
+    "rxc_distance_matrix": (C.c_int, [_vp, C.c_int, C.c_double, _f64p]),
+    "rxc_betweenness_partial": (C.c_int, [_vp, _u32p, C.c_uint64, C.c_int, _f64p]),
+    "rxc_edge_betweenness_partial": (C.c_int, [_vp, _u32p, C.c_uint64, _f64p]),
+    "rxc_closeness_partial": (C.c_int, [_vp, _u32p, C.c_uint64, C.c_int, _f64p]),
+    "rxc_distance_matrix_rows": (C.c_int, [_vp, C.c_int, C.c_double, C.c_uint32, C.c_uint32, _f64p]),
+    "rxc_rescale": (None, [_f64p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int]),
+    "rxc_comm_unique_id": (C.c_int, [_u8p]),
+    "rxc_comm_init": (C.c_int, [C.c_int, C.c_int, _u8p]),
+    "rxc_comm_reduce_sum_f64": (C.c_int, [_f64p, C.c_uint64, C.c_int]),
+    "rxc_comm_barrier": (C.c_int, []),
+    "rxc_comm_destroy": (None, []),
+    "rxc_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
+    "rxc_set_option": (C.c_int, [C.c_char_p, C.c_int64]),
+    "rxc_gen_gnp": (C.c_int64, [C.c_uint32, C.c_double, C.c_uint64, C.c_int, _u32p, _u32p,
+                                C.c_uint64]),
+    "rxc_gen_gnm": (C.c_int64, [C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, _u32p, _u32p,
+                                C.c_uint64]),
+    "rxc_gen_barabasi_albert": (C.c_int64, [C.c_uint32, C.c_uint32, C.c_uint64, _u32p, _u32p,
+                                            C.c_uint64]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load librxcuda.so (once).  Fails loudly when the extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RxCudaError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (or `make -C rustworkx_b200/csrc`).  rustworkx_b200 has no CPU fallback."
+        )
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    for name, (restype, argtypes) in SYMBOLS.items():
+        fn = getattr(L, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc == RXC_OK:
+        return
+    msg = lib().rxc_last_error().decode("utf-8", "replace")
+    if rc == RXC_ERR_OOM:
+        raise MemoryError(msg)
+    raise RxCudaError(f"librxcuda error {rc}: {msg}")
+
+
+def p_u32(a):
+    return a.ctypes.data_as(_u32p)
+
+
+def p_f64(a):
+    return a.ctypes.data_as(_f64p)
+
+
+def p_u8(a):
+    return a.ctypes.data_as(_u8p)
+
+
+def device_count():
+    return int(lib().rxc_device_count())
+
+
+def set_device(device):
+    check(lib().rxc_set_device(int(device)))
+
+
+def set_option(name, value):
+    check(lib().rxc_set_option(name.encode(), int(value)))
+
+
+class DeviceGraph:
+    """An ``rxc_graph*``: the StableGraph snapshot as compact CSR/CSC resident in HBM."""
+
+    def __init__(self, n_bound, live_nodes, e_bound, edge_src, edge_dst, edge_id, directed):
+        L = lib()
+        self.live_nodes = np.ascontiguousarray(live_nodes, dtype=np.uint32)
+        self.edge_id = np.ascontiguousarray(edge_id, dtype=np.uint32)
+        src = np.ascontiguousarray(edge_src, dtype=np.uint32)
+        dst = np.ascontiguousarray(edge_dst, dtype=np.uint32)
+        self.n_bound = int(n_bound)
+        self.e_bound = int(e_bound)
+        self.n_live = int(self.live_nodes.shape[0])
+        self.directed = bool(directed)
+        h = _vp()
+        check(L.rxc_graph_snapshot(self.n_bound, p_u32(self.live_nodes), self.n_live, self.e_bound,
+                                   p_u32(src), p_u32(dst), p_u32(self.edge_id), src.shape[0],
+                                   1 if directed else 0, C.byref(h)))
+        self._h = h
+
+    @classmethod
+    def from_graph(cls, graph):
+        """Snapshot a PyGraph / PyDiGraph (stand-in or, when importable, a real rustworkx graph --
+        both expose node_indices() / edge_indices() / edge_list(), src/graph.rs:418,462,815)."""
+        if hasattr(graph, "_snapshot_arrays"):
+            s = graph._snapshot_arrays()
+            return cls(s["n_bound"], s["live_nodes"], s["e_bound"], s["edge_src"], s["edge_dst"],
+                       s["edge_id"], s["directed"])
+        nodes = np.asarray(graph.node_indices(), dtype=np.uint32)
+        eids = np.asarray(graph.edge_indices(), dtype=np.uint32)
+        el = np.asarray(graph.edge_list(), dtype=np.uint32).reshape(-1, 2)
+        directed = type(graph).__name__ in ("PyDiGraph", "PyDAG")
+        nb = int(nodes[-1]) + 1 if nodes.size else 0
+        eb = int(eids[-1]) + 1 if eids.size else 0
+        return cls(nb, nodes, eb, el[:, 0], el[:, 1], eids, directed)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().rxc_graph_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stats(self):
+        st = Stats()
+        check(lib().rxc_get_stats(self._h, C.byref(st)))
+        return st.as_dict()
+
+    # ---- full calls -------------------------------------------------------------------------
+    def betweenness(self, include_endpoints, normalized):
+        out = np.zeros(max(self.n_bound, 1), dtype=np.float64)
+        check(lib().rxc_betweenness(self._h, int(include_endpoints), int(normalized), p_f64(out)))
+        return out[: self.n_bound]
+
+    def edge_betweenness(self, normalized):
+        out = np.zeros(max(self.e_bound, 1), dtype=np.float64)
+        check(lib().rxc_edge_betweenness(self._h, int(normalized), p_f64(out)))
+        return out[: self.e_bound]
+
+    def closeness(self, wf_improved):
+        out = np.zeros(max(self.n_bound, 1), dtype=np.float64)
+        check(lib().rxc_closeness(self._h, int(wf_improved), p_f64(out)))
+        return out[: self.n_bound]
+
+    def distance_matrix(self, as_undirected, null_value):
+        out = np.empty((self.n_live, self.n_live), dtype=np.float64)
+        if self.n_live:
+            check(lib().rxc_distance_matrix(self._h, int(as_undirected), float(null_value), p_f64(out)))
+        return out
+
+    # ---- partial calls (source shards; un-rescaled) ---------------------------------------------
+    def betweenness_partial(self, sources, include_endpoints=False):
+        src = np.ascontiguousarray(sources, dtype=np.uint32)
+        out = np.zeros(max(self.n_bound, 1), dtype=np.float64)
+        check(lib().rxc_betweenness_partial(self._h, p_u32(src), src.shape[0],
+                                            int(include_endpoints), p_f64(out)))
+        return out[: self.n_bound]
+
+    def edge_betweenness_partial(self, sources):
+        src = np.ascontiguousarray(sources, dtype=np.uint32)
+        out = np.zeros(max(self.e_bound, 1), dtype=np.float64)
+        check(lib().rxc_edge_betweenness_partial(self._h, p_u32(src), src.shape[0], p_f64(out)))
+        return out[: self.e_bound]
+
+    def closeness_partial(self, sources, wf_improved=True):
+        src = np.ascontiguousarray(sources, dtype=np.uint32)
+        out = np.zeros(max(src.shape[0], 1), dtype=np.float64)
+        check(lib().rxc_closeness_partial(self._h, p_u32(src), src.shape[0], int(wf_improved),
+                                          p_f64(out)))
+        return out[: src.shape[0]]
+
+    def distance_matrix_rows(self, row_begin, row_end, as_undirected=False, null_value=0.0):
+        out = np.empty((row_end - row_begin, self.n_live), dtype=np.float64)
+        if out.size:
+            check(lib().rxc_distance_matrix_rows(self._h, int(as_undirected), float(null_value),
+                                                 int(row_begin), int(row_end), p_f64(out)))
+        return out
+
+
+def rescale(x, node_count, normalized, directed, include_endpoints):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    lib().rxc_rescale(p_f64(x), x.shape[0], int(node_count), int(normalized), int(directed),
+                      int(include_endpoints))
+    return x

@@ -1,0 +1,196 @@
+// bfs_kernels.cuh -- distance-only batched multi-source BFS (closeness, distance_matrix).
+//
+// Replaces:
+//   closeness per-node BFS over Reversed(&graph) : rustworkx-core/src/centrality.rs:1190-1220
+//   dense bitset BFS + row fill                  : rustworkx-core/src/shortest_path/distance_matrix.rs:127-157
+//
+// Bit-parallel: 32 sources share one 32-bit word per vertex (the sparse analogue of the reference's
+// FixedBitSet rows).  Per group g:
+//   visited[g][v]  bit b = source b has reached v
+//   nextA/nextB[g][v]  bits pushed into v for the level being built (double buffered)
+// A level is ONE launch: the owner thread of each queued vertex finalises its new bits (counting,
+// distance rows), then pushes them along its arcs with atomicOr; the first push into a vertex
+// enqueues it for the next level.  Work per level is proportional to the frontier, which is what
+// the 200..2000-level graphs of config 2 (heavy-hex, grid) need.
+#pragma once
+
+#include "common.cuh"
+
+namespace rxc {
+
+struct BfsParams {
+    const uint32_t *row;  // adjacency to expand along (in-arcs for closeness, out-arcs for distances)
+    const uint32_t *col;
+    uint32_t *visited;    // [NG][n]
+    uint32_t *next0;      // [NG][n]
+    uint32_t *next1;      // [NG][n]
+    uint32_t *q0;         // [NG][n] vertex queue, even levels
+    uint32_t *q1;         // [NG][n] vertex queue, odd levels
+    uint32_t *cnt;        // [3][NG] queue lengths, rotating by level % 3
+    uint32_t *lvl_total;  // [lcap]
+    unsigned long long *reach;  // [NG][32] vertices reached per source (incl. the source)
+    unsigned long long *dsum;   // [NG][32] sum of distances per source
+    unsigned long long *stats;  // [ST_COUNT]
+    double *rows;         // [NG*32][n_cols] distance rows of this batch, or nullptr
+    const uint32_t *src;  // [NG][32] compact source ids, NO_SOURCE padded
+    uint64_t n_cols;
+    uint32_t n;
+    uint32_t ngroups;
+};
+
+__global__ void __launch_bounds__(BLOCK) bfs_fill_f64_kernel(double *x, uint64_t len, double v) {
+    for (uint64_t i = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; i < len;
+         i += (uint64_t)gridDim.x * BLOCK)
+        x[i] = v;
+}
+
+// visited = ~valid, next0 = next1 = 0 for every vertex of every group
+__global__ void __launch_bounds__(BLOCK) bfs_init_kernel(BfsParams p) {
+    const uint32_t g = blockIdx.y;
+    const uint32_t s = p.src[g * GW + lane_id()];
+    const uint32_t valid = __ballot_sync(FULL, s != NO_SOURCE);
+    const uint32_t w = blockIdx.x * BLOCK + threadIdx.x;
+    if (w < p.n) {
+        const size_t i = (size_t)g * p.n + w;
+        p.visited[i] = ~valid;
+        p.next0[i] = 0;
+        p.next1[i] = 0;
+    }
+}
+
+// one warp per group: queue the sources as level 0 with their bit already "pushed"
+__global__ void __launch_bounds__(32) bfs_seed_kernel(BfsParams p) {
+    const uint32_t g = blockIdx.x;
+    const int lane = lane_id();
+    const uint32_t s = p.src[g * GW + lane];
+    const bool ok = s != NO_SOURCE;
+    const uint32_t valid = __ballot_sync(FULL, ok);
+    if (ok) {
+        const size_t gn = (size_t)g * p.n;
+        p.next0[gn + s] = 1u << lane;  // sources of one group are distinct vertices
+        p.q0[gn + __popc(valid & lanemask_lt())] = s;
+    }
+    p.reach[g * GW + lane] = 0ull;
+    p.dsum[g * GW + lane] = 0ull;
+    if (lane == 0) {
+        p.cnt[0 * p.ngroups + g] = __popc(valid);
+        p.cnt[1 * p.ngroups + g] = 0;
+        p.cnt[2 * p.ngroups + g] = 0;
+        atomicAdd(&p.lvl_total[0], __popc(valid));
+    }
+}
+
+// One BFS level for every group of the batch (thread per queued vertex).
+template <bool ROWS>
+__global__ void __launch_bounds__(BLOCK) bfs_level_kernel(BfsParams p, uint32_t level) {
+    const uint32_t g = blockIdx.y;
+    const uint32_t *cnt_in = p.cnt + (size_t)(level % 3) * p.ngroups;
+    uint32_t *cnt_out = p.cnt + (size_t)((level + 1) % 3) * p.ngroups;
+    uint32_t *cnt_clr = p.cnt + (size_t)((level + 2) % 3) * p.ngroups;
+    const uint32_t cnt = cnt_in[g];
+    if (blockIdx.x == 0 && threadIdx.x == 0) cnt_clr[g] = 0;
+    if (cnt == 0) return;
+
+    const int lane = lane_id();
+    const size_t gn = (size_t)g * p.n;
+    uint32_t *visited = p.visited + gn;
+    uint32_t *nextA = ((level & 1) ? p.next1 : p.next0) + gn;
+    uint32_t *nextB = ((level & 1) ? p.next0 : p.next1) + gn;
+    const uint32_t *qin = ((level & 1) ? p.q1 : p.q0) + gn;
+    uint32_t *qout = ((level & 1) ? p.q0 : p.q1) + gn;
+
+    __shared__ uint32_t s_enq;
+    __shared__ unsigned long long s_reach[GW], s_te, s_v;
+    if (threadIdx.x == 0) {
+        s_enq = 0;
+        s_te = 0;
+        s_v = 0;
+    }
+    if (threadIdx.x < GW) s_reach[threadIdx.x] = 0;
+    __syncthreads();
+
+    unsigned long long my_reach = 0, my_te = 0, my_v = 0;
+    uint32_t my_enq = 0;
+    const uint32_t cnt_round = (cnt + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * BLOCK + threadIdx.x; i < cnt_round; i += gridDim.x * BLOCK) {
+        uint32_t w = 0, nm = 0;
+        if (i < cnt) {
+            w = qin[i];
+            nm = nextA[w];
+            nextA[w] = 0;
+            const uint32_t vis = visited[w];
+            nm &= ~vis;
+            if (nm) visited[w] = vis | nm;
+        }
+        // per-source counts: transpose the warp's 32 words with ballots
+        if (__ballot_sync(FULL, nm != 0)) {
+#pragma unroll 8
+            for (int b = 0; b < 32; b++) {
+                const uint32_t c = __popc(__ballot_sync(FULL, (nm >> b) & 1u));
+                if (lane == b) my_reach += c;
+            }
+        }
+        if (nm) {
+            if (ROWS) {
+                uint32_t bits = nm;
+                while (bits) {
+                    const int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    p.rows[(size_t)(g * GW + b) * p.n_cols + w] = (double)level;
+                }
+            }
+            const uint32_t e0 = p.row[w], e1 = p.row[w + 1];
+            my_te += (unsigned long long)__popc(nm) * (e1 - e0);
+            my_v += __popc(nm);
+            for (uint32_t e = e0; e < e1; e++) {
+                const uint32_t x = p.col[e];
+                const uint32_t pm = nm & ~visited[x];
+                if (pm) {
+                    const uint32_t old = atomicOr(&nextB[x], pm);
+                    if (old == 0) {
+                        const uint32_t pos = atomicAdd(&cnt_out[g], 1u);
+                        qout[pos] = x;
+                        my_enq++;
+                    }
+                }
+            }
+        }
+    }
+    if (my_reach) atomicAdd(&s_reach[lane], my_reach);
+    if (my_enq) atomicAdd(&s_enq, my_enq);
+    if (my_te) atomicAdd(&s_te, my_te);
+    if (my_v) atomicAdd(&s_v, my_v);
+    __syncthreads();
+    if (threadIdx.x < GW && s_reach[threadIdx.x]) {
+        atomicAdd(&p.reach[g * GW + threadIdx.x], s_reach[threadIdx.x]);
+        atomicAdd(&p.dsum[g * GW + threadIdx.x], s_reach[threadIdx.x] * level);
+    }
+    if (threadIdx.x == 0) {
+        if (s_enq) atomicAdd(&p.lvl_total[level + 1], s_enq);
+        if (s_te) atomicAdd(&p.stats[ST_TE], s_te);
+        if (s_v) atomicAdd(&p.stats[ST_V], s_v);
+    }
+}
+
+// closeness_finalize: centrality.rs:1209-1220 in the reference's operation order, every step
+// explicitly round-to-nearest so the result is bit-identical to the CPU.
+__global__ void __launch_bounds__(BLOCK)
+    closeness_finalize_kernel(const unsigned long long *reach, const unsigned long long *dsum,
+                              const uint32_t *src, uint32_t nslots, int wf_improved,
+                              unsigned long long node_count, double *out /* [nslots] */) {
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= nslots) return;
+    if (src[i] == NO_SOURCE) return;
+    const unsigned long long r = reach[i];
+    double c = 0.0;
+    if (r != 1) {
+        c = __ddiv_rn((double)(r - 1), (double)dsum[i]);
+        if (wf_improved) {
+            c = __dmul_rn(c, (double)(r - 1));
+            c = __ddiv_rn(c, (double)(node_count - 1));
+        }
+    }
+    out[i] = c;
+}
+
+}  // namespace rxc

@@ -1,0 +1,54 @@
+// common.cuh -- shared device/host helpers for librxcuda (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace rxc {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr int GW = 32;           // sources per group: one warp lane per source
+constexpr int BLOCK = 256;       // threads per CTA for every kernel here
+constexpr int WARPS = BLOCK / 32;
+constexpr uint32_t NO_SOURCE = 0xFFFFFFFFu;
+
+// Device-side work counters (one array per graph handle).
+enum StatSlot { ST_TE = 0, ST_DAG = 1, ST_V = 2, ST_COUNT = 4 };
+
+void set_error(const std::string &msg);
+
+struct CudaError {
+    cudaError_t code;
+    const char *file;
+    int line;
+};
+
+#define RXC_CUDA(call)                                                      \
+    do {                                                                    \
+        cudaError_t _e = (call);                                            \
+        if (_e != cudaSuccess) throw ::rxc::CudaError{_e, __FILE__, __LINE__}; \
+    } while (0)
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+    return x;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+    return x;
+}
+
+}  // namespace rxc

@@ -1,0 +1,758 @@
+// rxcuda.cu -- C-ABI (include/rxcuda.h) and host-side batch scheduler of librxcuda.so.
+//
+// Host code here plays the role the north star gives to a `rustworkx-cuda` crate: it snapshots the
+// StableGraph into device CSR/CSC, cuts the live sources into batches of 32-source groups sized for
+// HBM, drives the level-synchronous kernels of bc_kernels.cuh / bfs_kernels.cuh on one stream, and
+// scatters results back to original indices.  No PyTorch, no Triton, no CPU fallback.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/rxcuda.h"
+#include "bc_kernels.cuh"
+#include "bfs_kernels.cuh"
+#include "common.cuh"
+#include "snapshot.hpp"
+
+namespace rxc {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+
+struct OomError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    void alloc(size_t count) {
+        release();
+        if (count) {
+            cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+            if (e == cudaErrorMemoryAllocation) {
+                cudaGetLastError();
+                throw OomError("cudaMalloc of " + std::to_string(count * sizeof(T)) + " bytes failed");
+            }
+            RXC_CUDA(e);
+        }
+        n = count;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+    ~DevBuf() { release(); }
+};
+
+struct DeviceCSR {
+    DevBuf<uint32_t> row, col, eid;
+    uint64_t arcs = 0;
+    void upload(const HostCSR &h, cudaStream_t s) {
+        row.alloc(h.row.size());
+        col.alloc(h.col.size() ? h.col.size() : 1);
+        arcs = h.col.size();
+        RXC_CUDA(cudaMemcpyAsync(row.p, h.row.data(), h.row.size() * 4, cudaMemcpyHostToDevice, s));
+        if (arcs)
+            RXC_CUDA(cudaMemcpyAsync(col.p, h.col.data(), arcs * 4, cudaMemcpyHostToDevice, s));
+        if (!h.eid.empty()) {
+            eid.alloc(h.eid.size());
+            RXC_CUDA(cudaMemcpyAsync(eid.p, h.eid.data(), arcs * 4, cudaMemcpyHostToDevice, s));
+        }
+    }
+};
+
+struct Options {
+    int64_t bc_groups = 0;    // groups of 32 sources per betweenness batch (0 = auto)
+    int64_t bfs_groups = 0;   // groups per closeness / distance batch (0 = auto)
+    int64_t mem_fraction_pct = 70;
+};
+static Options g_opt;
+static int g_device = 0;
+
+static double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace rxc
+
+using namespace rxc;
+
+struct rxc_graph {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    HostSnapshot host;
+    DeviceCSR out, in, sym;
+    bool has_sym = false;
+    DevBuf<unsigned long long> d_stats;
+    rxc_stats stats;
+    double ms_snapshot = 0.0;
+    std::mutex mu;
+
+    const DeviceCSR &succ() const { return out; }
+    const DeviceCSR &pred() const { return host.directed ? in : out; }
+    ~rxc_graph() {
+        cudaSetDevice(device);
+        for (auto &e : ev)
+            if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace rxc {
+
+template <class F>
+static int guarded(F &&f) {
+    try {
+        f();
+        return RXC_OK;
+    } catch (const CudaError &e) {
+        set_error(std::string("CUDA error: ") + cudaGetErrorString(e.code) + " at " + e.file + ":" +
+                  std::to_string(e.line));
+        cudaGetLastError();
+        return RXC_ERR_CUDA;
+    } catch (const OomError &e) {
+        set_error(std::string("out of device memory: ") + e.what());
+        return RXC_ERR_OOM;
+    } catch (const std::bad_alloc &) {
+        set_error("out of host memory");
+        return RXC_ERR_OOM;
+    } catch (const LimitError &e) {
+        set_error(e.what());
+        return RXC_ERR_LIMIT;
+    } catch (const std::invalid_argument &e) {
+        set_error(std::string("invalid argument: ") + e.what());
+        return RXC_ERR_INVALID;
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        return RXC_ERR_INVALID;
+    }
+}
+
+static void require_device() {
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0) {
+        cudaGetLastError();
+        throw CudaError{e == cudaSuccess ? cudaErrorNoDevice : e, __FILE__, __LINE__};
+    }
+}
+
+static size_t device_budget() {
+    size_t free_b = 0, total_b = 0;
+    RXC_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    return (size_t)((double)free_b * (double)g_opt.mem_fraction_pct / 100.0);
+}
+
+static void reset_stats(rxc_graph *g) {
+    memset(&g->stats, 0, sizeof(g->stats));
+    g->stats.ms_snapshot = g->ms_snapshot;
+    RXC_CUDA(cudaMemsetAsync(g->d_stats.p, 0, g->d_stats.bytes(), g->stream));
+}
+
+static void fetch_stats(rxc_graph *g) {
+    unsigned long long h[ST_COUNT];
+    RXC_CUDA(cudaMemcpyAsync(h, g->d_stats.p, sizeof(h), cudaMemcpyDeviceToHost, g->stream));
+    RXC_CUDA(cudaStreamSynchronize(g->stream));
+    g->stats.te = h[ST_TE];
+    g->stats.te_dag = h[ST_DAG];
+    g->stats.v = h[ST_V];
+}
+
+// Split a source list into rounds of pairwise-distinct compact ids (a vertex listed twice must
+// not share a 32-source group with itself; contributions are additive, so extra rounds are exact).
+static std::vector<std::vector<uint32_t>> distinct_rounds(const std::vector<uint32_t> &src,
+                                                          uint32_t n) {
+    std::vector<std::vector<uint32_t>> rounds;
+    std::vector<uint32_t> seen(n, 0);
+    for (uint32_t s : src) {
+        const uint32_t r = seen[s]++;
+        if (rounds.size() <= r) rounds.emplace_back();
+        rounds[r].push_back(s);
+    }
+    return rounds;
+}
+
+// Launch `launch(level)` for level = 0, 1, ... in growing speculative chunks and return the number
+// of BFS levels (first level whose total frontier is empty).  lvl_total[l] is final once the launch
+// for level l-1 has completed; launches past the end find empty frontiers and return at once.
+template <class F>
+static uint32_t run_levels(rxc_graph *g, uint32_t *d_lvl_total, uint32_t n, F &&launch,
+                           std::vector<uint32_t> &h_totals) {
+    uint32_t level = 0, checked = 1, chunk = 4;
+    h_totals.assign(1, 0);
+    for (;;) {
+        uint32_t launched = 0;
+        while (launched < chunk && level < n) {
+            launch(level);
+            level++;
+            launched++;
+        }
+        h_totals.resize((size_t)level + 1);
+        RXC_CUDA(cudaMemcpyAsync(h_totals.data() + checked, d_lvl_total + checked,
+                                 (size_t)(level + 1 - checked) * 4, cudaMemcpyDeviceToHost,
+                                 g->stream));
+        RXC_CUDA(cudaStreamSynchronize(g->stream));
+        for (uint32_t l = checked; l <= level; l++)
+            if (h_totals[l] == 0) return l;
+        checked = level + 1;
+        if (level >= n) return level;
+        chunk = std::min<uint32_t>(chunk * 2, 64);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// betweenness (node / edge)
+// ------------------------------------------------------------------------------------------------
+struct BcWorkspace {
+    DevBuf<double> sc;
+    DevBuf<uint64_t> P0, P1;
+    DevBuf<uint32_t> visited, qv, qm, loff, lvlcnt, lvl_total, src;
+    DevBuf<unsigned long long> reach;
+};
+
+static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endpoints,
+                   bool edge_mode, double *d_acc) {
+    const uint32_t n = g->host.n_live;
+    if (sources.empty() || n == 0) return;
+    const uint64_t total_groups = (sources.size() + GW - 1) / GW;
+    const uint32_t lcap = n + 2;
+    const uint64_t qcap = (uint64_t)GW * n;
+    // bytes per group: sc row + worst-case queues + tagged masks + visited + level tables
+    const double per_group = (double)n * (256.0 + 256.0 + 16.0 + 4.0) + (double)lcap * 8.0 + 512.0;
+    uint64_t ng = g_opt.bc_groups > 0 ? (uint64_t)g_opt.bc_groups
+                                      : std::max<uint64_t>(1, (8ull << 20) / std::max<uint32_t>(n, 1));
+    ng = std::min<uint64_t>(ng, 256);
+    ng = std::min<uint64_t>(ng, std::max<uint64_t>(1, (uint64_t)((double)device_budget() / per_group)));
+    ng = std::min<uint64_t>(ng, total_groups);
+    ng = std::min<uint64_t>(ng, 65535);
+
+    BcWorkspace ws;
+    ws.sc.alloc((size_t)ng * n * GW);
+    ws.P0.alloc((size_t)ng * n);
+    ws.P1.alloc((size_t)ng * n);
+    ws.visited.alloc((size_t)ng * n);
+    ws.qv.alloc((size_t)ng * qcap);
+    ws.qm.alloc((size_t)ng * qcap);
+    ws.loff.alloc((size_t)ng * lcap);
+    ws.lvlcnt.alloc((size_t)ng * lcap);
+    ws.lvl_total.alloc(lcap);
+    ws.src.alloc((size_t)ng * GW);
+    ws.reach.alloc((size_t)ng * GW);
+    cudaStream_t st = g->stream;
+    RXC_CUDA(cudaMemsetAsync(ws.P0.p, 0, ws.P0.bytes(), st));
+    RXC_CUDA(cudaMemsetAsync(ws.P1.p, 0, ws.P1.bytes(), st));
+
+    BcParams p{};
+    p.sc = ws.sc.p;
+    p.P0 = ws.P0.p;
+    p.P1 = ws.P1.p;
+    p.visited = ws.visited.p;
+    p.qv = ws.qv.p;
+    p.qm = ws.qm.p;
+    p.loff = ws.loff.p;
+    p.lvlcnt = ws.lvlcnt.p;
+    p.lvl_total = ws.lvl_total.p;
+    p.reach = ws.reach.p;
+    p.stats = g->d_stats.p;
+    p.acc = d_acc;
+    p.src = ws.src.p;
+    p.qcap = qcap;
+    p.n = n;
+    p.lcap = lcap;
+    uint32_t tagbase = 0;
+
+    std::vector<uint32_t> h_src((size_t)ng * GW), h_totals, h_lvlcnt;
+    const uint32_t vblocks = (n + BLOCK - 1) / BLOCK;
+    uint32_t clear_levels = lcap;  // how much of the level tables the previous batch dirtied
+
+    for (uint64_t g0 = 0; g0 < total_groups; g0 += ng) {
+        const uint32_t bg = (uint32_t)std::min<uint64_t>(ng, total_groups - g0);
+        std::fill(h_src.begin(), h_src.end(), NO_SOURCE);
+        const size_t s0 = (size_t)g0 * GW;
+        const size_t cnt = std::min(sources.size() - s0, (size_t)bg * GW);
+        std::copy(sources.begin() + s0, sources.begin() + s0 + cnt, h_src.begin());
+        if ((uint64_t)tagbase + lcap + 16 > 0xFFFFFFF0ull) {
+            RXC_CUDA(cudaMemsetAsync(ws.P0.p, 0, ws.P0.bytes(), st));
+            RXC_CUDA(cudaMemsetAsync(ws.P1.p, 0, ws.P1.bytes(), st));
+            tagbase = 0;
+        }
+        p.tagbase = tagbase;
+        RXC_CUDA(cudaEventRecord(g->ev[0], st));
+        RXC_CUDA(cudaMemcpyAsync(ws.src.p, h_src.data(), (size_t)bg * GW * 4,
+                                 cudaMemcpyHostToDevice, st));
+        RXC_CUDA(cudaMemset2DAsync(ws.lvlcnt.p, (size_t)lcap * 4, 0, (size_t)clear_levels * 4, bg, st));
+        RXC_CUDA(cudaMemsetAsync(ws.lvl_total.p, 0, (size_t)clear_levels * 4, st));
+        bc_init_kernel<<<dim3(vblocks, bg), BLOCK, 0, st>>>(p);
+        bc_seed_kernel<<<bg, 32, 0, st>>>(p);
+        g->stats.launches += 2;
+
+        // forward: in-arcs (pull from predecessors)
+        p.row = g->pred().row.p;
+        p.col = g->pred().col.p;
+        p.eid = nullptr;
+        uint32_t launched_levels = 0;
+        const uint32_t L = run_levels(
+            g, ws.lvl_total.p, n,
+            [&](uint32_t level) {
+                bc_forward_kernel<<<dim3(vblocks, bg), BLOCK, 0, st>>>(p, level);
+                launched_levels++;
+            },
+            h_totals);
+        g->stats.launches += launched_levels;
+        g->stats.levels += L;
+        clear_levels = std::min<uint32_t>(lcap, launched_levels + 2);
+        RXC_CUDA(cudaEventRecord(g->ev[1], st));
+
+        // backward: out-arcs (pull from successors), deepest level first
+        h_lvlcnt.resize((size_t)bg * L);
+        RXC_CUDA(cudaMemcpy2DAsync(h_lvlcnt.data(), (size_t)L * 4, ws.lvlcnt.p, (size_t)lcap * 4,
+                                   (size_t)L * 4, bg, cudaMemcpyDeviceToHost, st));
+        RXC_CUDA(cudaStreamSynchronize(st));
+        p.row = g->succ().row.p;
+        p.col = g->succ().col.p;
+        p.eid = g->succ().eid.p;
+        const uint32_t last = edge_mode ? 0u : 1u;
+        for (uint32_t l = L; l-- > last;) {
+            uint32_t maxcnt = 0;
+            for (uint32_t gi = 0; gi < bg; gi++)
+                maxcnt = std::max(maxcnt, h_lvlcnt[(size_t)gi * L + l]);
+            if (maxcnt == 0) continue;
+            const uint32_t gx = std::min<uint32_t>((maxcnt + WARPS - 1) / WARPS, 16384);
+            const dim3 grid(gx, bg);
+            if (edge_mode)
+                bc_backward_kernel<true, false><<<grid, BLOCK, 0, st>>>(p, l);
+            else if (endpoints)
+                bc_backward_kernel<false, true><<<grid, BLOCK, 0, st>>>(p, l);
+            else
+                bc_backward_kernel<false, false><<<grid, BLOCK, 0, st>>>(p, l);
+            g->stats.launches++;
+        }
+        if (endpoints && !edge_mode) {
+            bc_endpoint_sources_kernel<<<(bg * GW + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(p, bg);
+            g->stats.launches++;
+        }
+        RXC_CUDA(cudaEventRecord(g->ev[2], st));
+        RXC_CUDA(cudaStreamSynchronize(st));
+        RXC_CUDA(cudaGetLastError());
+        float f = 0.f, b = 0.f;
+        RXC_CUDA(cudaEventElapsedTime(&f, g->ev[0], g->ev[1]));
+        RXC_CUDA(cudaEventElapsedTime(&b, g->ev[1], g->ev[2]));
+        g->stats.ms_forward += f;
+        g->stats.ms_backward += b;
+        g->stats.ms_total += f + b;
+        g->stats.batches++;
+        g->stats.sources += cnt;
+        tagbase += launched_levels + 8;
+    }
+}
+
+static std::vector<uint32_t> all_sources(const rxc_graph *g) {
+    std::vector<uint32_t> s(g->host.n_live);
+    for (uint32_t i = 0; i < g->host.n_live; i++) s[i] = i;
+    return s;
+}
+
+static std::vector<uint32_t> to_compact(const rxc_graph *g, const uint32_t *sources, uint64_t k) {
+    std::vector<uint32_t> s(k);
+    for (uint64_t i = 0; i < k; i++) {
+        const uint32_t o = sources[i];
+        if (o >= g->host.n_bound || g->host.compact_of_orig[o] == 0xFFFFFFFFu)
+            throw std::invalid_argument("source " + std::to_string(o) + " is not a live node");
+        s[i] = g->host.compact_of_orig[o];
+    }
+    return s;
+}
+
+// un-rescaled betweenness sums over `sources` (compact ids) into out (original indexing)
+static void bc_partial(rxc_graph *g, const std::vector<uint32_t> &sources, bool endpoints,
+                       bool edge_mode, double *out) {
+    std::lock_guard<std::mutex> lock(g->mu);
+    RXC_CUDA(cudaSetDevice(g->device));
+    reset_stats(g);
+    const uint32_t n = g->host.n_live;
+    const size_t out_len = edge_mode ? g->host.e_bound : g->host.n_bound;
+    const size_t acc_len = edge_mode ? g->host.e_bound : n;
+    std::fill(out, out + out_len, 0.0);
+    if (acc_len == 0) return;
+    DevBuf<double> acc;
+    acc.alloc(acc_len);
+    RXC_CUDA(cudaMemsetAsync(acc.p, 0, acc.bytes(), g->stream));
+    for (const auto &round : distinct_rounds(sources, n)) bc_run(g, round, endpoints, edge_mode, acc.p);
+    const double t0 = now_ms();
+    if (edge_mode) {
+        RXC_CUDA(cudaMemcpyAsync(out, acc.p, acc.bytes(), cudaMemcpyDeviceToHost, g->stream));
+        RXC_CUDA(cudaStreamSynchronize(g->stream));
+    } else {
+        std::vector<double> h(n);
+        RXC_CUDA(cudaMemcpyAsync(h.data(), acc.p, acc.bytes(), cudaMemcpyDeviceToHost, g->stream));
+        RXC_CUDA(cudaStreamSynchronize(g->stream));
+        for (uint32_t i = 0; i < n; i++) out[g->host.orig_of_compact[i]] = h[i];
+    }
+    fetch_stats(g);
+    g->stats.ms_d2h += now_ms() - t0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// closeness / distance matrix
+// ------------------------------------------------------------------------------------------------
+struct BfsWorkspace {
+    DevBuf<uint32_t> visited, next0, next1, q0, q1, cnt, lvl_total, src;
+    DevBuf<unsigned long long> reach, dsum;
+    DevBuf<double> vals, rows;
+};
+
+enum class BfsMode { Closeness, Rows };
+
+// sources: compact ids.  Closeness: out[i] = closeness of sources[i].  Rows: out = rows of the
+// distance matrix for sources[i] (n_live columns each).
+static void bfs_run(rxc_graph *g, const DeviceCSR &csr, const std::vector<uint32_t> &sources,
+                    BfsMode mode, bool wf_improved, double null_value, double *out) {
+    const uint32_t n = g->host.n_live;
+    if (sources.empty() || n == 0) return;
+    const bool rows_mode = mode == BfsMode::Rows;
+    const uint64_t total_groups = (sources.size() + GW - 1) / GW;
+    const uint32_t lcap = n + 2;
+    const double per_group = (double)n * 20.0 + (rows_mode ? (double)n * GW * 8.0 : 0.0) + 1024.0;
+    uint64_t ng = g_opt.bfs_groups > 0 ? (uint64_t)g_opt.bfs_groups : 4096;
+    ng = std::min<uint64_t>(ng, std::max<uint64_t>(1, (uint64_t)((double)device_budget() / per_group)));
+    if (rows_mode)  // keep one batch of rows under 8 GiB
+        ng = std::min<uint64_t>(ng, std::max<uint64_t>(1, (8ull << 30) / ((uint64_t)n * GW * 8)));
+    ng = std::min<uint64_t>(ng, total_groups);
+    ng = std::min<uint64_t>(ng, 65535);
+
+    BfsWorkspace ws;
+    ws.visited.alloc((size_t)ng * n);
+    ws.next0.alloc((size_t)ng * n);
+    ws.next1.alloc((size_t)ng * n);
+    ws.q0.alloc((size_t)ng * n);
+    ws.q1.alloc((size_t)ng * n);
+    ws.cnt.alloc((size_t)3 * ng);
+    ws.lvl_total.alloc(lcap);
+    ws.src.alloc((size_t)ng * GW);
+    ws.reach.alloc((size_t)ng * GW);
+    ws.dsum.alloc((size_t)ng * GW);
+    ws.vals.alloc((size_t)ng * GW);
+    if (rows_mode) ws.rows.alloc((size_t)ng * GW * n);
+    cudaStream_t st = g->stream;
+
+    BfsParams p{};
+    p.row = csr.row.p;
+    p.col = csr.col.p;
+    p.visited = ws.visited.p;
+    p.next0 = ws.next0.p;
+    p.next1 = ws.next1.p;
+    p.q0 = ws.q0.p;
+    p.q1 = ws.q1.p;
+    p.cnt = ws.cnt.p;
+    p.lvl_total = ws.lvl_total.p;
+    p.reach = ws.reach.p;
+    p.dsum = ws.dsum.p;
+    p.stats = g->d_stats.p;
+    p.rows = rows_mode ? ws.rows.p : nullptr;
+    p.src = ws.src.p;
+    p.n_cols = n;
+    p.n = n;
+
+    std::vector<uint32_t> h_src((size_t)ng * GW), h_totals;
+    std::vector<double> h_vals((size_t)ng * GW);
+    const uint32_t vblocks = (n + BLOCK - 1) / BLOCK;
+    uint32_t clear_levels = lcap;
+
+    for (uint64_t g0 = 0; g0 < total_groups; g0 += ng) {
+        const uint32_t bg = (uint32_t)std::min<uint64_t>(ng, total_groups - g0);
+        p.ngroups = bg;
+        std::fill(h_src.begin(), h_src.end(), NO_SOURCE);
+        const size_t s0 = (size_t)g0 * GW;
+        const size_t cnt = std::min(sources.size() - s0, (size_t)bg * GW);
+        std::copy(sources.begin() + s0, sources.begin() + s0 + cnt, h_src.begin());
+        RXC_CUDA(cudaEventRecord(g->ev[0], st));
+        RXC_CUDA(cudaMemcpyAsync(ws.src.p, h_src.data(), (size_t)bg * GW * 4,
+                                 cudaMemcpyHostToDevice, st));
+        RXC_CUDA(cudaMemsetAsync(ws.lvl_total.p, 0, (size_t)clear_levels * 4, st));
+        bfs_init_kernel<<<dim3(vblocks, bg), BLOCK, 0, st>>>(p);
+        bfs_seed_kernel<<<bg, 32, 0, st>>>(p);
+        g->stats.launches += 2;
+        if (rows_mode) {
+            const uint64_t len = (uint64_t)bg * GW * n;
+            const uint32_t fb = (uint32_t)std::min<uint64_t>((len + BLOCK - 1) / BLOCK, 148 * 16);
+            bfs_fill_f64_kernel<<<fb, BLOCK, 0, st>>>(ws.rows.p, len, null_value);
+            g->stats.launches++;
+        }
+        uint32_t launched_levels = 0;
+        // frontier sizes are only known a chunk late: size the grid from the last total seen
+        // (the kernel grid-strides, so an underestimate only costs parallelism)
+        uint32_t est = GW;
+        const uint32_t gx_fill = (148 * 4 + bg - 1) / bg;
+        const uint32_t L = run_levels(
+            g, ws.lvl_total.p, n,
+            [&](uint32_t level) {
+                if (level < h_totals.size() && h_totals[level]) est = h_totals[level] / bg + 1;
+                uint32_t gx = (4 * est + BLOCK - 1) / BLOCK;
+                gx = std::max<uint32_t>(1, std::min(std::max(gx, gx_fill), vblocks));
+                if (rows_mode)
+                    bfs_level_kernel<true><<<dim3(gx, bg), BLOCK, 0, st>>>(p, level);
+                else
+                    bfs_level_kernel<false><<<dim3(gx, bg), BLOCK, 0, st>>>(p, level);
+                launched_levels++;
+            },
+            h_totals);
+        g->stats.launches += launched_levels;
+        g->stats.levels += L;
+        clear_levels = std::min<uint32_t>(lcap, launched_levels + 2);
+        if (!rows_mode) {
+            closeness_finalize_kernel<<<(bg * GW + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(
+                ws.reach.p, ws.dsum.p, ws.src.p, bg * GW, wf_improved ? 1 : 0,
+                (unsigned long long)n, ws.vals.p);
+            g->stats.launches++;
+        }
+        RXC_CUDA(cudaEventRecord(g->ev[1], st));
+        const double t0 = now_ms();
+        if (rows_mode) {
+            RXC_CUDA(cudaMemcpyAsync(out + (size_t)s0 * n, ws.rows.p, (size_t)cnt * n * 8,
+                                     cudaMemcpyDeviceToHost, st));
+        } else {
+            RXC_CUDA(cudaMemcpyAsync(h_vals.data(), ws.vals.p, (size_t)cnt * 8,
+                                     cudaMemcpyDeviceToHost, st));
+        }
+        RXC_CUDA(cudaStreamSynchronize(st));
+        RXC_CUDA(cudaGetLastError());
+        if (!rows_mode) std::copy(h_vals.begin(), h_vals.begin() + cnt, out + s0);
+        g->stats.ms_d2h += now_ms() - t0;
+        float f = 0.f;
+        RXC_CUDA(cudaEventElapsedTime(&f, g->ev[0], g->ev[1]));
+        g->stats.ms_forward += f;
+        g->stats.ms_total += f;
+        g->stats.batches++;
+        g->stats.sources += cnt;
+    }
+}
+
+static const DeviceCSR &symmetric_csr(rxc_graph *g) {
+    if (!g->host.directed) return g->out;
+    if (!g->has_sym) {
+        HostCSR h = make_symmetric(g->host);
+        g->sym.upload(h, g->stream);
+        RXC_CUDA(cudaStreamSynchronize(g->stream));
+        g->has_sym = true;
+    }
+    return g->sym;
+}
+
+}  // namespace rxc
+
+// ================================================================================================
+// C-ABI
+// ================================================================================================
+extern "C" {
+
+const char *rxc_version(void) { return "rxcuda 0.1.0 (sm_100a)"; }
+const char *rxc_last_error(void) { return g_err.c_str(); }
+
+int rxc_device_count(void) {
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return cnt;
+}
+
+int rxc_set_device(int device) {
+    return guarded([&] {
+        require_device();
+        RXC_CUDA(cudaSetDevice(device));
+        g_device = device;
+    });
+}
+
+int rxc_get_device(void) { return g_device; }
+
+int rxc_graph_snapshot(uint32_t n_bound, const uint32_t *live_nodes, uint32_t n_live,
+                       uint32_t e_bound, const uint32_t *edge_src, const uint32_t *edge_dst,
+                       const uint32_t *edge_id, uint64_t n_edges, int directed,
+                       rxc_graph **out_graph) {
+    if (!out_graph) return RXC_ERR_INVALID;
+    *out_graph = nullptr;
+    rxc_graph *g = nullptr;
+    int rc = guarded([&] {
+        if ((n_live && !live_nodes) || (n_edges && (!edge_src || !edge_dst)))
+            throw std::invalid_argument("null array");
+        require_device();
+        const double t0 = now_ms();
+        g = new rxc_graph();
+        g->device = g_device;
+        RXC_CUDA(cudaSetDevice(g->device));
+        RXC_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+        for (auto &e : g->ev) RXC_CUDA(cudaEventCreate(&e));
+        g->host = make_snapshot(n_bound, live_nodes, n_live, e_bound, edge_src, edge_dst, edge_id,
+                                n_edges, directed != 0);
+        g->out.upload(g->host.out, g->stream);
+        if (g->host.directed) g->in.upload(g->host.in, g->stream);
+        g->d_stats.alloc(ST_COUNT);
+        RXC_CUDA(cudaMemsetAsync(g->d_stats.p, 0, g->d_stats.bytes(), g->stream));
+        RXC_CUDA(cudaStreamSynchronize(g->stream));
+        memset(&g->stats, 0, sizeof(g->stats));
+        g->ms_snapshot = now_ms() - t0;
+        g->stats.ms_snapshot = g->ms_snapshot;
+    });
+    if (rc != RXC_OK) {
+        delete g;
+        return rc;
+    }
+    *out_graph = g;
+    return RXC_OK;
+}
+
+void rxc_graph_free(rxc_graph *g) { delete g; }
+
+int rxc_graph_info(const rxc_graph *g, uint32_t *n_bound, uint32_t *n_live, uint32_t *e_bound,
+                   uint64_t *n_arcs, int *directed) {
+    if (!g) return RXC_ERR_INVALID;
+    if (n_bound) *n_bound = g->host.n_bound;
+    if (n_live) *n_live = g->host.n_live;
+    if (e_bound) *e_bound = g->host.e_bound;
+    if (n_arcs) *n_arcs = g->host.out.col.size();
+    if (directed) *directed = g->host.directed ? 1 : 0;
+    return RXC_OK;
+}
+
+void rxc_rescale(double *x, uint64_t len, uint64_t node_count, int normalized, int directed,
+                 int include_endpoints) {
+    // _rescale, rustworkx-core/src/centrality.rs:221-252: one multiply by a precomputed reciprocal
+    bool do_scale = true;
+    double scale = 1.0;
+    if (normalized) {
+        if (include_endpoints) {
+            if (node_count < 2) do_scale = false;
+            else scale = 1.0 / (double)(node_count * (node_count - 1));
+        } else if (node_count <= 2) {
+            do_scale = false;
+        } else {
+            scale = 1.0 / (double)((node_count - 1) * (node_count - 2));
+        }
+    } else if (!directed) {
+        scale = 0.5;
+    } else {
+        do_scale = false;
+    }
+    if (do_scale)
+        for (uint64_t i = 0; i < len; i++) x[i] = x[i] * scale;
+}
+
+int rxc_betweenness_partial(rxc_graph *g, const uint32_t *sources, uint64_t n_sources,
+                            int include_endpoints, double *out) {
+    if (!g || !out || (n_sources && !sources)) return RXC_ERR_INVALID;
+    return guarded([&] { bc_partial(g, to_compact(g, sources, n_sources), include_endpoints != 0, false, out); });
+}
+
+int rxc_edge_betweenness_partial(rxc_graph *g, const uint32_t *sources, uint64_t n_sources,
+                                 double *out) {
+    if (!g || !out || (n_sources && !sources)) return RXC_ERR_INVALID;
+    return guarded([&] { bc_partial(g, to_compact(g, sources, n_sources), false, true, out); });
+}
+
+int rxc_betweenness(rxc_graph *g, int include_endpoints, int normalized, double *out) {
+    if (!g || !out) return RXC_ERR_INVALID;
+    return guarded([&] {
+        bc_partial(g, all_sources(g), include_endpoints != 0, false, out);
+        rxc_rescale(out, g->host.n_bound, g->host.n_live, normalized, g->host.directed ? 1 : 0,
+                    include_endpoints);
+    });
+}
+
+int rxc_edge_betweenness(rxc_graph *g, int normalized, double *out) {
+    if (!g || !out) return RXC_ERR_INVALID;
+    return guarded([&] {
+        bc_partial(g, all_sources(g), false, true, out);
+        rxc_rescale(out, g->host.e_bound, g->host.n_live, normalized, g->host.directed ? 1 : 0, 1);
+    });
+}
+
+int rxc_closeness_partial(rxc_graph *g, const uint32_t *sources, uint64_t n_sources,
+                          int wf_improved, double *out) {
+    if (!g || !out || (n_sources && !sources)) return RXC_ERR_INVALID;
+    return guarded([&] {
+        std::lock_guard<std::mutex> lock(g->mu);
+        RXC_CUDA(cudaSetDevice(g->device));
+        reset_stats(g);
+        // closeness follows incoming edges: BFS over Reversed(&graph), centrality.rs:1208
+        bfs_run(g, g->pred(), to_compact(g, sources, n_sources), BfsMode::Closeness,
+                wf_improved != 0, 0.0, out);
+        fetch_stats(g);
+    });
+}
+
+int rxc_closeness(rxc_graph *g, int wf_improved, double *out) {
+    if (!g || !out) return RXC_ERR_INVALID;
+    return guarded([&] {
+        std::lock_guard<std::mutex> lock(g->mu);
+        RXC_CUDA(cudaSetDevice(g->device));
+        reset_stats(g);
+        std::fill(out, out + g->host.n_bound, 0.0);
+        std::vector<double> vals(g->host.n_live);
+        bfs_run(g, g->pred(), all_sources(g), BfsMode::Closeness, wf_improved != 0, 0.0, vals.data());
+        for (uint32_t i = 0; i < g->host.n_live; i++) out[g->host.orig_of_compact[i]] = vals[i];
+        fetch_stats(g);
+    });
+}
+
+int rxc_distance_matrix_rows(rxc_graph *g, int as_undirected, double null_value,
+                             uint32_t row_begin, uint32_t row_end, double *out) {
+    if (!g || (!out && row_end > row_begin)) return RXC_ERR_INVALID;
+    return guarded([&] {
+        if (row_begin > row_end || row_end > g->host.n_live)
+            throw std::invalid_argument("row range outside [0, n_live]");
+        std::lock_guard<std::mutex> lock(g->mu);
+        RXC_CUDA(cudaSetDevice(g->device));
+        reset_stats(g);
+        std::vector<uint32_t> src(row_end - row_begin);
+        for (uint32_t i = row_begin; i < row_end; i++) src[i - row_begin] = i;
+        // graph_distance_matrix always passes as_undirected=true (src/shortest_path/mod.rs:1610)
+        const DeviceCSR &csr = (as_undirected || !g->host.directed) ? symmetric_csr(g) : g->out;
+        bfs_run(g, csr, src, BfsMode::Rows, false, null_value, out);
+        fetch_stats(g);
+    });
+}
+
+int rxc_distance_matrix(rxc_graph *g, int as_undirected, double null_value, double *out) {
+    if (!g) return RXC_ERR_INVALID;
+    return rxc_distance_matrix_rows(g, as_undirected, null_value, 0, g->host.n_live, out);
+}
+
+int rxc_get_stats(const rxc_graph *g, rxc_stats *out) {
+    if (!g || !out) return RXC_ERR_INVALID;
+    *out = g->stats;
+    return RXC_OK;
+}
+
+int rxc_set_option(const char *name, int64_t value) {
+    if (!name) return RXC_ERR_INVALID;
+    const std::string k(name);
+    if (k == "bc_groups") g_opt.bc_groups = value;
+    else if (k == "bfs_groups") g_opt.bfs_groups = value;
+    else if (k == "mem_fraction_pct" && value > 0 && value <= 95) g_opt.mem_fraction_pct = value;
+    else {
+        set_error("unknown option: " + k);
+        return RXC_ERR_INVALID;
+    }
+    return RXC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,285 @@
+"""Pins the CPU oracle against every golden vector the reference's own tests hold for the hot path
+(SURVEY.md section 8c).  Exact `==` where the reference uses assert_eq / assertEqual, tolerance where
+the reference uses assert_almost_equal / assertAlmostEqual.
+"""
+
+import math
+
+import numpy as np
+import pytest
+
+
+# ----------------------------------------------------------------------------- node betweenness
+def test_bc_core_doctest(oracle):
+    # rustworkx-core/src/centrality.rs:58-66
+    g = oracle.OracleGraph.from_edges(False, [(0, 4), (1, 2), (2, 3), (3, 4), (1, 4)])
+    assert g.betweenness_centrality(True, True, 200) == [0.4, 0.5, 0.45, 0.5, 0.75]
+
+
+def _hole_graph(oracle):
+    # rustworkx-core/src/centrality.rs:640-658 and :674-691
+    g = oracle.OracleGraph(False)
+    n0 = g.add_node(); d0 = g.add_node(); n1 = g.add_node(); d1 = g.add_node()
+    n2 = g.add_node(); d2 = g.add_node(); n3 = g.add_node()
+    g.remove_node(d0); g.remove_node(d1); g.remove_node(d2)
+    g.add_edge(n0, n1); g.add_edge(n1, n2); g.add_edge(n2, n3); g.add_edge(n3, n0)
+    g.remove_edge(1)
+    return g
+
+
+def test_bc_stable_graph_with_removed_nodes_and_edges(oracle):
+    # rustworkx-core/src/centrality.rs:672-696
+    g = _hole_graph(oracle)
+    assert g.betweenness_centrality(False, False, 50) == [2.0, None, 0.0, None, 0.0, None, 2.0]
+
+
+@pytest.mark.parametrize("threshold", [50, 1])
+@pytest.mark.parametrize("directed", [False, True])
+@pytest.mark.parametrize("deleted", [False, True])
+def test_bc_python_path4(oracle, threshold, directed, deleted):
+    # tests/graph/test_centrality.py:20-103, tests/digraph/test_centrality.py:20-132
+    g = oracle.OracleGraph(directed)
+    a, b, c = g.add_node(), g.add_node(), g.add_node()
+    c0 = g.add_node() if deleted else None
+    d = g.add_node()
+    g.add_edge(a, b); g.add_edge(b, c); g.add_edge(c, d)
+    if deleted:
+        g.remove_node(c0)
+    keys = [0, 1, 2, 4] if deleted else [0, 1, 2, 3]
+
+    def as_map(v):
+        return {i: x for i, x in enumerate(v) if x is not None}
+
+    if directed:
+        exp_norm = [0.0, 0.3333333333333333, 0.3333333333333333, 0.0]
+        exp_end = [0.25, 0.41666666666666663, 0.41666666666666663, 0.25]
+    else:
+        exp_norm = [0.0, 0.6666666666666666, 0.6666666666666666, 0.0]
+        exp_end = [0.5, 0.8333333333333333, 0.8333333333333333, 0.5]
+    exp_un = [0.0, 2.0, 2.0, 0.0]
+    # python order (normalized, endpoints) -> core order (include_endpoints, normalized)
+    assert as_map(g.betweenness_centrality(False, True, threshold)) == dict(zip(keys, exp_norm))
+    assert as_map(g.betweenness_centrality(True, True, threshold)) == dict(zip(keys, exp_end))
+    assert as_map(g.betweenness_centrality(False, False, threshold)) == dict(zip(keys, exp_un))
+
+
+# ----------------------------------------------------------------------------- edge betweenness
+def test_ebc_core_doctest(oracle):
+    # rustworkx-core/src/centrality.rs:164-170
+    g = oracle.OracleGraph.from_edges(False, [(0, 4), (1, 2), (1, 3), (2, 3), (3, 4), (1, 4)])
+    assert g.edge_betweenness_centrality(False, 200) == [4.0, 2.0, 1.0, 2.0, 3.0, 3.0]
+
+
+EBC_CASES = [
+    # rustworkx-core/src/centrality.rs:528-556
+    (False, True,
+     [(0, 6), (0, 4), (0, 1), (0, 5), (1, 6), (1, 7), (1, 3), (1, 4), (2, 6), (2, 3), (3, 5),
+      (3, 7), (3, 6), (4, 5), (5, 6)],
+     [0.1023809, 0.0547619, 0.0922619, 0.05654762, 0.09940476, 0.125, 0.09940476, 0.12440476,
+      0.12857143, 0.12142857, 0.13511905, 0.125, 0.06547619, 0.08869048, 0.08154762]),
+    # :558-582
+    (False, False,
+     [(0, 2), (0, 4), (0, 1), (1, 3), (1, 5), (1, 7), (2, 7), (2, 3), (3, 5), (3, 6), (4, 6),
+      (5, 7)],
+     [3.83333, 5.5, 5.33333, 3.5, 2.5, 3.0, 3.5, 4.0, 3.66667, 6.5, 3.5, 2.16667]),
+    # :584-604
+    (True, True,
+     [(0, 1), (1, 0), (1, 3), (1, 2), (1, 4), (2, 3), (2, 4), (2, 1), (3, 2), (4, 3)],
+     [0.2, 0.2, 0.1, 0.1, 0.1, 0.05, 0.1, 0.3, 0.35, 0.2]),
+    # :606-626
+    (True, False,
+     [(0, 4), (1, 0), (1, 3), (2, 3), (2, 4), (2, 0), (3, 4), (3, 2), (3, 1), (4, 1)],
+     [4.5, 3.0, 6.5, 1.5, 1.5, 1.5, 1.5, 4.5, 2.0, 7.5]),
+]
+
+
+@pytest.mark.parametrize("directed,normalized,edges,expected", EBC_CASES)
+def test_ebc_core_unit(oracle, directed, normalized, edges, expected):
+    g = oracle.OracleGraph.from_edges(directed, edges)
+    out = g.edge_betweenness_centrality(normalized, 50)
+    assert len(out) == len(expected)
+    for x, y in zip(out, expected):
+        assert abs(x - y) < 1e-4
+
+
+def test_ebc_stable_graph_with_removed_edges(oracle):
+    # rustworkx-core/src/centrality.rs:628-636
+    g = oracle.OracleGraph.from_edges(False, [(0, 1), (1, 2), (2, 3), (3, 0)])
+    g.remove_edge(1)
+    assert g.edge_betweenness_centrality(False, 50) == [3.0, None, 3.0, 4.0]
+
+
+def test_ebc_stable_graph_with_removed_nodes_and_edges(oracle):
+    # rustworkx-core/src/centrality.rs:638-662
+    g = _hole_graph(oracle)
+    assert g.edge_betweenness_centrality(False, 50) == [3.0, None, 3.0, 4.0]
+
+
+def _gen(oracle, graph):
+    return oracle.OracleGraph.from_graph(graph)
+
+
+def test_ebc_python_goldens(oracle):
+    # tests/graph/test_centrality.py:194-248 and tests/digraph/test_centrality.py:227-259
+    import rustworkx_b200.generators as gen
+
+    def vals(g, normalized=True):
+        return _gen(oracle, g).edge_betweenness_centrality(normalized, 50)
+
+    for v in vals(gen.mesh_graph(5)):
+        assert v == pytest.approx(0.1, abs=1e-7)
+    assert vals(gen.path_graph(5)) == pytest.approx([0.4, 0.6, 0.6, 0.4], abs=1e-7)
+    for v in vals(gen.cycle_graph(5)):
+        assert v == pytest.approx(0.3, abs=1e-7)
+    assert vals(gen.full_rary_tree(2, 7), False) == pytest.approx([12, 12, 6, 6, 6, 6], abs=1e-7)
+    assert vals(gen.path_graph(5), False) == pytest.approx([4, 6, 6, 4], abs=1e-7)
+    from rustworkx_b200 import PyGraph
+
+    g = PyGraph()
+    g.add_nodes_from(range(10))
+    g.add_edges_from([(0, 1, 1), (0, 2, 1), (0, 3, 1), (0, 4, 1), (3, 5, 1), (4, 6, 1), (5, 7, 1),
+                      (6, 8, 1), (7, 8, 1), (8, 9, 1)])
+    assert vals(g, False) == pytest.approx([9, 9, 12, 15, 11, 14, 10, 13, 9, 9], abs=1e-7)
+    # directed
+    for v in vals(gen.directed_mesh_graph(5)):
+        assert v == pytest.approx(0.05, abs=1e-7)
+    assert vals(gen.directed_path_graph(5)) == pytest.approx([0.2, 0.3, 0.3, 0.2], abs=1e-7)
+    for v in vals(gen.directed_cycle_graph(5)):
+        assert v == pytest.approx(0.5, abs=1e-7)
+    assert vals(gen.full_rary_tree(2, 7).to_directed(), False) == pytest.approx(
+        [12, 12, 12, 12, 6, 6, 6, 6, 6, 6, 6, 6], abs=1e-7)
+    assert vals(gen.directed_path_graph(5), False) == pytest.approx([4, 6, 6, 4], abs=1e-7)
+
+
+# ----------------------------------------------------------------------------- closeness
+def test_closeness_core_doctest(oracle):
+    # rustworkx-core/src/centrality.rs:1146-1164
+    edges = [(0, 4), (1, 2), (2, 3), (3, 4), (1, 4)]
+    g = oracle.OracleGraph.from_edges(False, edges)
+    assert g.closeness_centrality(True, 200) == [1.0 / 2.0, 2.0 / 3.0, 4.0 / 7.0, 2.0 / 3.0, 4.0 / 5.0]
+    dg = oracle.OracleGraph.from_edges(True, edges)
+    assert dg.closeness_centrality(True, 200) == [0.0, 0.0, 1.0 / 4.0, 1.0 / 3.0, 4.0 / 5.0]
+
+
+@pytest.mark.parametrize("threshold", [200, 1])
+def test_closeness_core_integration(oracle, threshold):
+    # rustworkx-core/tests/centrality.rs:17-120
+    g = oracle.OracleGraph.from_edges(False, [(1, 2), (2, 3), (3, 4), (1, 4)])
+    assert g.closeness_centrality(True, threshold) == [0.0, 0.5625, 0.5625, 0.5625, 0.5625]
+    g = oracle.OracleGraph.from_edges(False, [(0, 1), (1, 2), (2, 3), (4, 5), (5, 6)])
+    assert g.closeness_centrality(True, threshold) == [
+        1.0 / 4.0, 3.0 / 8.0, 3.0 / 8.0, 1.0 / 4.0, 2.0 / 9.0, 1.0 / 3.0, 2.0 / 9.0]
+    assert g.closeness_centrality(False, threshold) == [
+        1.0 / 2.0, 3.0 / 4.0, 3.0 / 4.0, 1.0 / 2.0, 2.0 / 3.0, 1.0, 2.0 / 3.0]
+    g = oracle.OracleGraph.from_edges(True, [(0, 1), (1, 2)])
+    assert g.closeness_centrality(True, threshold) == [0.0, 1.0 / 2.0, 2.0 / 3.0]
+    # Reversed(&g): same as the digraph with every edge flipped
+    gr = oracle.OracleGraph.from_edges(True, [(1, 0), (2, 1)])
+    assert gr.closeness_centrality(True, threshold) == [2.0 / 3.0, 1.0 / 2.0, 0.0]
+    k5 = [(0, 1), (0, 2), (0, 3), (0, 4), (1, 2), (1, 3), (1, 4), (2, 3), (2, 4), (3, 4)]
+    assert oracle.OracleGraph.from_edges(False, k5).closeness_centrality(True, threshold) == [1.0] * 5
+    g = oracle.OracleGraph.from_edges(False, [(0, 1), (1, 2)])
+    assert g.closeness_centrality(True, threshold) == [2.0 / 3.0, 1.0, 2.0 / 3.0]
+
+
+@pytest.mark.parametrize("threshold", [50, 1])
+def test_closeness_python_deleted_node(oracle, threshold):
+    # tests/graph/test_centrality.py:105-120 and tests/digraph/test_centrality.py:134-149
+    for directed in (False, True):
+        g = oracle.OracleGraph(directed)
+        a, b, c, c0, d = (g.add_node() for _ in range(5))
+        g.add_edge(a, b); g.add_edge(b, c); g.add_edge(c, d)
+        g.remove_node(c0)
+        wf = g.closeness_centrality(True, threshold)
+        nowf = g.closeness_centrality(False, threshold)
+        if directed:
+            assert wf == [0.0, 1.0 / 3.0, 4.0 / 9.0, None, 0.5]
+            assert nowf == [0.0, 1.0, 2.0 / 3.0, None, 0.5]
+        else:
+            assert wf == [0.5, 0.75, 0.75, None, 0.5]
+            assert nowf == [0.5, 0.75, 0.75, None, 0.5]
+
+
+# ----------------------------------------------------------------------------- distance matrix
+CYCLE7 = [(0, 1), (0, 6), (1, 2), (2, 3), (3, 4), (4, 5), (5, 6)]
+CYCLE7_UNDIRECTED = np.array([
+    [0.0, 1.0, 2.0, 3.0, 3.0, 2.0, 1.0],
+    [1.0, 0.0, 1.0, 2.0, 3.0, 3.0, 2.0],
+    [2.0, 1.0, 0.0, 1.0, 2.0, 3.0, 3.0],
+    [3.0, 2.0, 1.0, 0.0, 1.0, 2.0, 3.0],
+    [3.0, 3.0, 2.0, 1.0, 0.0, 1.0, 2.0],
+    [2.0, 3.0, 3.0, 2.0, 1.0, 0.0, 1.0],
+    [1.0, 2.0, 3.0, 3.0, 2.0, 1.0, 0.0],
+])
+CYCLE7_DIRECTED = np.array([
+    [0.0, 1.0, 2.0, 3.0, 4.0, 5.0, 1.0],
+    [0.0, 0.0, 1.0, 2.0, 3.0, 4.0, 5.0],
+    [0.0, 0.0, 0.0, 1.0, 2.0, 3.0, 4.0],
+    [0.0, 0.0, 0.0, 0.0, 1.0, 2.0, 3.0],
+    [0.0, 0.0, 0.0, 0.0, 0.0, 1.0, 2.0],
+    [0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0],
+    [0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0],
+])
+
+
+def _nan_expected():
+    e = np.full((8, 8), np.nan)
+    e[:7, :7] = CYCLE7_UNDIRECTED
+    e[7, 7] = 0.0
+    return e
+
+
+@pytest.mark.parametrize("threshold", [300, 5])
+def test_distance_matrix_goldens(oracle, threshold):
+    # distance_matrix.rs:56-69; tests/graph/test_dist_matrix.py:21-95;
+    # tests/digraph/test_dist_matrix.py:21-132
+    g = oracle.OracleGraph.from_edges(False, CYCLE7)
+    assert np.array_equal(g.distance_matrix(threshold, True, 0.0), CYCLE7_UNDIRECTED)
+    assert np.array_equal(g.distance_matrix(threshold, False, 0.0), CYCLE7_UNDIRECTED)
+    dg = oracle.OracleGraph.from_edges(True, CYCLE7)
+    assert np.array_equal(dg.distance_matrix(threshold, False, 0.0), CYCLE7_DIRECTED)
+    assert np.array_equal(dg.distance_matrix(threshold, True, 0.0), CYCLE7_UNDIRECTED)
+    for directed in (False, True):
+        g = oracle.OracleGraph.from_edges(directed, CYCLE7)
+        g.add_node()
+        got = g.distance_matrix(threshold, True, math.nan)
+        assert np.array_equal(got, _nan_expected(), equal_nan=True)
+
+
+def test_distance_matrix_node_hole(oracle):
+    # tests/graph/test_dist_matrix.py:97-102, tests/digraph/test_dist_matrix.py:135-140
+    g = oracle.OracleGraph.from_edges(False, [(0, 1), (1, 2), (2, 3)])
+    g.remove_node(0)
+    assert np.array_equal(g.distance_matrix(300, True, 0.0),
+                          np.array([[0.0, 1.0, 2.0], [1.0, 0.0, 1.0], [2.0, 1.0, 0.0]]))
+    dg = oracle.OracleGraph.from_edges(True, [(0, 1), (1, 2), (2, 3)])
+    dg.remove_node(0)
+    assert np.array_equal(dg.distance_matrix(300, False, 0.0),
+                          np.array([[0.0, 1.0, 2.0], [0.0, 0.0, 1.0], [0.0, 0.0, 0.0]]))
+
+
+# ----------------------------------------------------------------------------- generators
+def test_heavy_hex_fixture(oracle):
+    # rustworkx-core/src/generators/heavy_hex_graph.rs:76-105 (doctest edge list, d=3)
+    import rustworkx_b200.generators as gen
+
+    expected = [(0, 13), (1, 13), (1, 14), (2, 14), (3, 15), (4, 15), (4, 16), (5, 16), (6, 17),
+                (7, 17), (7, 18), (8, 18), (0, 9), (3, 9), (5, 12), (8, 12), (10, 14), (10, 16),
+                (11, 15), (11, 17)]
+    g = gen.heavy_hex_graph(3)
+    assert list(g.edge_list()) == expected
+    for d in (3, 5, 7, 51):
+        g = gen.heavy_hex_graph(d)
+        assert g.num_nodes() == (5 * d * d - 2 * d - 1) // 2
+        assert g.num_edges() == 2 * d * (d - 1) + (d + 1) * (d - 1)
+
+
+def test_grid_fixture(oracle):
+    # rustworkx-core/src/generators/grid_graph.rs doctest: 3x3 grid edge order
+    import rustworkx_b200.generators as gen
+
+    g = gen.grid_graph(3, 3)
+    assert list(g.edge_list()) == [(0, 3), (0, 1), (1, 4), (1, 2), (2, 5), (3, 6), (3, 4), (4, 7),
+                                   (4, 5), (5, 8), (6, 7), (7, 8)]
+    g = gen.grid_graph(1000, 1000)
+    assert g.num_nodes() == 10**6 and g.num_edges() == 1998000
