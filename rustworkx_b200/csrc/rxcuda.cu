@@ -89,6 +89,37 @@ static double now_ms() {
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
+// Per-handle scratch in HBM, kept across calls (cudaMalloc/cudaFree of multi-GB buffers would
+// otherwise cost more than a batch of kernels).
+struct BcWorkspace {
+    DevBuf<double> sc;
+    DevBuf<uint64_t> P0, P1;
+    DevBuf<uint32_t> visited, qv, qm, loff, lvlcnt, lvl_total, src;
+    DevBuf<unsigned long long> reach;
+    uint64_t ng = 0;        // capacity in groups
+    uint32_t tagbase = 0;   // tags already used in P0/P1
+    uint32_t dirty_levels = 0;  // prefix of the level tables the last batch wrote
+    void release() {
+        sc.release(); P0.release(); P1.release(); visited.release(); qv.release(); qm.release();
+        loff.release(); lvlcnt.release(); lvl_total.release(); src.release(); reach.release();
+        ng = 0;
+    }
+};
+
+struct BfsWorkspace {
+    DevBuf<uint32_t> visited, next0, next1, q0, q1, cnt, lvl_total, src;
+    DevBuf<unsigned long long> reach, dsum;
+    DevBuf<double> vals, rows;
+    uint64_t ng = 0, ng_rows = 0;
+    uint32_t dirty_levels = 0;
+    void release() {
+        visited.release(); next0.release(); next1.release(); q0.release(); q1.release();
+        cnt.release(); lvl_total.release(); src.release(); reach.release(); dsum.release();
+        vals.release(); rows.release();
+        ng = ng_rows = 0;
+    }
+};
+
 }  // namespace rxc
 
 using namespace rxc;
@@ -96,13 +127,15 @@ using namespace rxc;
 struct rxc_graph {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [4],[5]: whole call
     HostSnapshot host;
     DeviceCSR out, in, sym;
     bool has_sym = false;
     DevBuf<unsigned long long> d_stats;
     rxc_stats stats;
     double ms_snapshot = 0.0;
+    BcWorkspace bc_ws;
+    BfsWorkspace bfs_ws;
     std::mutex mu;
 
     const DeviceCSR &succ() const { return out; }
@@ -166,6 +199,21 @@ static void reset_stats(rxc_graph *g) {
     RXC_CUDA(cudaMemsetAsync(g->d_stats.p, 0, g->d_stats.bytes(), g->stream));
 }
 
+static void begin_call(rxc_graph *g) {
+    RXC_CUDA(cudaSetDevice(g->device));
+    reset_stats(g);
+    RXC_CUDA(cudaEventRecord(g->ev[4], g->stream));
+}
+
+// ms_total = device time from the first to the last kernel of the call, host gaps included
+static void end_call(rxc_graph *g) {
+    RXC_CUDA(cudaEventRecord(g->ev[5], g->stream));
+    RXC_CUDA(cudaEventSynchronize(g->ev[5]));
+    float ms = 0.f;
+    RXC_CUDA(cudaEventElapsedTime(&ms, g->ev[4], g->ev[5]));
+    g->stats.ms_total = ms;
+}
+
 static void fetch_stats(rxc_graph *g) {
     unsigned long long h[ST_COUNT];
     RXC_CUDA(cudaMemcpyAsync(h, g->d_stats.p, sizeof(h), cudaMemcpyDeviceToHost, g->stream));
@@ -220,13 +268,6 @@ static uint32_t run_levels(rxc_graph *g, uint32_t *d_lvl_total, uint32_t n, F &&
 // ------------------------------------------------------------------------------------------------
 // betweenness (node / edge)
 // ------------------------------------------------------------------------------------------------
-struct BcWorkspace {
-    DevBuf<double> sc;
-    DevBuf<uint64_t> P0, P1;
-    DevBuf<uint32_t> visited, qv, qm, loff, lvlcnt, lvl_total, src;
-    DevBuf<unsigned long long> reach;
-};
-
 static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endpoints,
                    bool edge_mode, double *d_acc) {
     const uint32_t n = g->host.n_live;
@@ -243,21 +284,28 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
     ng = std::min<uint64_t>(ng, total_groups);
     ng = std::min<uint64_t>(ng, 65535);
 
-    BcWorkspace ws;
-    ws.sc.alloc((size_t)ng * n * GW);
-    ws.P0.alloc((size_t)ng * n);
-    ws.P1.alloc((size_t)ng * n);
-    ws.visited.alloc((size_t)ng * n);
-    ws.qv.alloc((size_t)ng * qcap);
-    ws.qm.alloc((size_t)ng * qcap);
-    ws.loff.alloc((size_t)ng * lcap);
-    ws.lvlcnt.alloc((size_t)ng * lcap);
-    ws.lvl_total.alloc(lcap);
-    ws.src.alloc((size_t)ng * GW);
-    ws.reach.alloc((size_t)ng * GW);
+    BcWorkspace &ws = g->bc_ws;
     cudaStream_t st = g->stream;
-    RXC_CUDA(cudaMemsetAsync(ws.P0.p, 0, ws.P0.bytes(), st));
-    RXC_CUDA(cudaMemsetAsync(ws.P1.p, 0, ws.P1.bytes(), st));
+    if (ws.ng < ng) {
+        ws.release();
+        g->bfs_ws.release();  // one scratch set at a time keeps the footprint predictable
+        ws.sc.alloc((size_t)ng * n * GW);
+        ws.P0.alloc((size_t)ng * n);
+        ws.P1.alloc((size_t)ng * n);
+        ws.visited.alloc((size_t)ng * n);
+        ws.qv.alloc((size_t)ng * qcap);
+        ws.qm.alloc((size_t)ng * qcap);
+        ws.loff.alloc((size_t)ng * lcap);
+        ws.lvlcnt.alloc((size_t)ng * lcap);
+        ws.lvl_total.alloc(lcap);
+        ws.src.alloc((size_t)ng * GW);
+        ws.reach.alloc((size_t)ng * GW);
+        ws.ng = ng;
+        ws.tagbase = 0;
+        ws.dirty_levels = lcap;
+        RXC_CUDA(cudaMemsetAsync(ws.P0.p, 0, ws.P0.bytes(), st));
+        RXC_CUDA(cudaMemsetAsync(ws.P1.p, 0, ws.P1.bytes(), st));
+    }
 
     BcParams p{};
     p.sc = ws.sc.p;
@@ -276,11 +324,11 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
     p.qcap = qcap;
     p.n = n;
     p.lcap = lcap;
-    uint32_t tagbase = 0;
+    uint32_t &tagbase = ws.tagbase;
 
     std::vector<uint32_t> h_src((size_t)ng * GW), h_totals, h_lvlcnt;
     const uint32_t vblocks = (n + BLOCK - 1) / BLOCK;
-    uint32_t clear_levels = lcap;  // how much of the level tables the previous batch dirtied
+    uint32_t &clear_levels = ws.dirty_levels;  // prefix of the level tables the previous batch dirtied
 
     for (uint64_t g0 = 0; g0 < total_groups; g0 += ng) {
         const uint32_t bg = (uint32_t)std::min<uint64_t>(ng, total_groups - g0);
@@ -297,7 +345,7 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
         RXC_CUDA(cudaEventRecord(g->ev[0], st));
         RXC_CUDA(cudaMemcpyAsync(ws.src.p, h_src.data(), (size_t)bg * GW * 4,
                                  cudaMemcpyHostToDevice, st));
-        RXC_CUDA(cudaMemset2DAsync(ws.lvlcnt.p, (size_t)lcap * 4, 0, (size_t)clear_levels * 4, bg, st));
+        RXC_CUDA(cudaMemset2DAsync(ws.lvlcnt.p, (size_t)lcap * 4, 0, (size_t)clear_levels * 4, ws.ng, st));
         RXC_CUDA(cudaMemsetAsync(ws.lvl_total.p, 0, (size_t)clear_levels * 4, st));
         bc_init_kernel<<<dim3(vblocks, bg), BLOCK, 0, st>>>(p);
         bc_seed_kernel<<<bg, 32, 0, st>>>(p);
@@ -328,8 +376,8 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
         p.row = g->succ().row.p;
         p.col = g->succ().col.p;
         p.eid = g->succ().eid.p;
-        const uint32_t last = edge_mode ? 0u : 1u;
-        for (uint32_t l = L; l-- > last;) {
+        // level 0 (the sources) adds nothing to node scores but is swept for the work counters
+        for (uint32_t l = L; l-- > 0;) {
             uint32_t maxcnt = 0;
             for (uint32_t gi = 0; gi < bg; gi++)
                 maxcnt = std::max(maxcnt, h_lvlcnt[(size_t)gi * L + l]);
@@ -356,7 +404,6 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
         RXC_CUDA(cudaEventElapsedTime(&b, g->ev[1], g->ev[2]));
         g->stats.ms_forward += f;
         g->stats.ms_backward += b;
-        g->stats.ms_total += f + b;
         g->stats.batches++;
         g->stats.sources += cnt;
         tagbase += launched_levels + 8;
@@ -384,17 +431,20 @@ static std::vector<uint32_t> to_compact(const rxc_graph *g, const uint32_t *sour
 static void bc_partial(rxc_graph *g, const std::vector<uint32_t> &sources, bool endpoints,
                        bool edge_mode, double *out) {
     std::lock_guard<std::mutex> lock(g->mu);
-    RXC_CUDA(cudaSetDevice(g->device));
-    reset_stats(g);
+    begin_call(g);
     const uint32_t n = g->host.n_live;
     const size_t out_len = edge_mode ? g->host.e_bound : g->host.n_bound;
     const size_t acc_len = edge_mode ? g->host.e_bound : n;
     std::fill(out, out + out_len, 0.0);
-    if (acc_len == 0) return;
+    if (acc_len == 0) {
+        end_call(g);
+        return;
+    }
     DevBuf<double> acc;
     acc.alloc(acc_len);
     RXC_CUDA(cudaMemsetAsync(acc.p, 0, acc.bytes(), g->stream));
     for (const auto &round : distinct_rounds(sources, n)) bc_run(g, round, endpoints, edge_mode, acc.p);
+    end_call(g);
     const double t0 = now_ms();
     if (edge_mode) {
         RXC_CUDA(cudaMemcpyAsync(out, acc.p, acc.bytes(), cudaMemcpyDeviceToHost, g->stream));
@@ -412,12 +462,6 @@ static void bc_partial(rxc_graph *g, const std::vector<uint32_t> &sources, bool 
 // ------------------------------------------------------------------------------------------------
 // closeness / distance matrix
 // ------------------------------------------------------------------------------------------------
-struct BfsWorkspace {
-    DevBuf<uint32_t> visited, next0, next1, q0, q1, cnt, lvl_total, src;
-    DevBuf<unsigned long long> reach, dsum;
-    DevBuf<double> vals, rows;
-};
-
 enum class BfsMode { Closeness, Rows };
 
 // sources: compact ids.  Closeness: out[i] = closeness of sources[i].  Rows: out = rows of the
@@ -437,20 +481,29 @@ static void bfs_run(rxc_graph *g, const DeviceCSR &csr, const std::vector<uint32
     ng = std::min<uint64_t>(ng, total_groups);
     ng = std::min<uint64_t>(ng, 65535);
 
-    BfsWorkspace ws;
-    ws.visited.alloc((size_t)ng * n);
-    ws.next0.alloc((size_t)ng * n);
-    ws.next1.alloc((size_t)ng * n);
-    ws.q0.alloc((size_t)ng * n);
-    ws.q1.alloc((size_t)ng * n);
-    ws.cnt.alloc((size_t)3 * ng);
-    ws.lvl_total.alloc(lcap);
-    ws.src.alloc((size_t)ng * GW);
-    ws.reach.alloc((size_t)ng * GW);
-    ws.dsum.alloc((size_t)ng * GW);
-    ws.vals.alloc((size_t)ng * GW);
-    if (rows_mode) ws.rows.alloc((size_t)ng * GW * n);
+    BfsWorkspace &ws = g->bfs_ws;
     cudaStream_t st = g->stream;
+    if (ws.ng < ng) {
+        ws.release();
+        g->bc_ws.release();
+        ws.visited.alloc((size_t)ng * n);
+        ws.next0.alloc((size_t)ng * n);
+        ws.next1.alloc((size_t)ng * n);
+        ws.q0.alloc((size_t)ng * n);
+        ws.q1.alloc((size_t)ng * n);
+        ws.cnt.alloc((size_t)3 * ng);
+        ws.lvl_total.alloc(lcap);
+        ws.src.alloc((size_t)ng * GW);
+        ws.reach.alloc((size_t)ng * GW);
+        ws.dsum.alloc((size_t)ng * GW);
+        ws.vals.alloc((size_t)ng * GW);
+        ws.ng = ng;
+        ws.dirty_levels = lcap;
+    }
+    if (rows_mode && ws.ng_rows < ng) {
+        ws.rows.alloc((size_t)ng * GW * n);
+        ws.ng_rows = ng;
+    }
 
     BfsParams p{};
     p.row = csr.row.p;
@@ -473,7 +526,7 @@ static void bfs_run(rxc_graph *g, const DeviceCSR &csr, const std::vector<uint32
     std::vector<uint32_t> h_src((size_t)ng * GW), h_totals;
     std::vector<double> h_vals((size_t)ng * GW);
     const uint32_t vblocks = (n + BLOCK - 1) / BLOCK;
-    uint32_t clear_levels = lcap;
+    uint32_t &clear_levels = ws.dirty_levels;
 
     for (uint64_t g0 = 0; g0 < total_groups; g0 += ng) {
         const uint32_t bg = (uint32_t)std::min<uint64_t>(ng, total_groups - g0);
@@ -538,7 +591,6 @@ static void bfs_run(rxc_graph *g, const DeviceCSR &csr, const std::vector<uint32
         float f = 0.f;
         RXC_CUDA(cudaEventElapsedTime(&f, g->ev[0], g->ev[1]));
         g->stats.ms_forward += f;
-        g->stats.ms_total += f;
         g->stats.batches++;
         g->stats.sources += cnt;
     }
@@ -690,11 +742,11 @@ int rxc_closeness_partial(rxc_graph *g, const uint32_t *sources, uint64_t n_sour
     if (!g || !out || (n_sources && !sources)) return RXC_ERR_INVALID;
     return guarded([&] {
         std::lock_guard<std::mutex> lock(g->mu);
-        RXC_CUDA(cudaSetDevice(g->device));
-        reset_stats(g);
+        begin_call(g);
         // closeness follows incoming edges: BFS over Reversed(&graph), centrality.rs:1208
         bfs_run(g, g->pred(), to_compact(g, sources, n_sources), BfsMode::Closeness,
                 wf_improved != 0, 0.0, out);
+        end_call(g);
         fetch_stats(g);
     });
 }
@@ -703,11 +755,11 @@ int rxc_closeness(rxc_graph *g, int wf_improved, double *out) {
     if (!g || !out) return RXC_ERR_INVALID;
     return guarded([&] {
         std::lock_guard<std::mutex> lock(g->mu);
-        RXC_CUDA(cudaSetDevice(g->device));
-        reset_stats(g);
+        begin_call(g);
         std::fill(out, out + g->host.n_bound, 0.0);
         std::vector<double> vals(g->host.n_live);
         bfs_run(g, g->pred(), all_sources(g), BfsMode::Closeness, wf_improved != 0, 0.0, vals.data());
+        end_call(g);
         for (uint32_t i = 0; i < g->host.n_live; i++) out[g->host.orig_of_compact[i]] = vals[i];
         fetch_stats(g);
     });
@@ -720,13 +772,13 @@ int rxc_distance_matrix_rows(rxc_graph *g, int as_undirected, double null_value,
         if (row_begin > row_end || row_end > g->host.n_live)
             throw std::invalid_argument("row range outside [0, n_live]");
         std::lock_guard<std::mutex> lock(g->mu);
-        RXC_CUDA(cudaSetDevice(g->device));
-        reset_stats(g);
+        begin_call(g);
         std::vector<uint32_t> src(row_end - row_begin);
         for (uint32_t i = row_begin; i < row_end; i++) src[i - row_begin] = i;
         // graph_distance_matrix always passes as_undirected=true (src/shortest_path/mod.rs:1610)
         const DeviceCSR &csr = (as_undirected || !g->host.directed) ? symmetric_csr(g) : g->out;
         bfs_run(g, csr, src, BfsMode::Rows, false, null_value, out);
+        end_call(g);
         fetch_stats(g);
     });
 }

@@ -1,0 +1,377 @@
+"""GPU parity: the CUDA path (through the C-ABI, via the rustworkx-shaped Python API) against the CPU
+oracle on the same seeded inputs, plus the reference's own golden vectors.
+
+Tolerances (BASELINE.json north_star): distance_matrix and closeness bit-exact; betweenness and edge
+betweenness within 1e-9 relative (1e-12 absolute floor for zeros).
+"""
+
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+ATOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def rx():
+    import rustworkx_b200 as rx
+    from rustworkx_b200 import _lib
+
+    if _lib.device_count() == 0:
+        pytest.fail("no CUDA device: the gpu-marked tests need a B200 (there is no CPU fallback)")
+    return rx
+
+
+def assert_close(got, want):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape
+    err = np.abs(got - want)
+    tol = ATOL + RTOL * np.abs(want)
+    bad = np.flatnonzero(~(err <= tol))
+    assert bad.size == 0, f"{bad.size} mismatches, first at {bad[:5]}: got {got[bad[:5]]} want {want[bad[:5]]}"
+
+
+def random_graph(rx, directed, n, m, seed, holes=0, multi=True, loops=True):
+    """Random multigraph with optional self-loops, parallel edges, removed nodes and removed edges."""
+    rng = np.random.default_rng(seed)
+    g = rx.PyDiGraph() if directed else rx.PyGraph()
+    g.add_nodes_from(range(n))
+    src = rng.integers(0, n, size=m)
+    dst = rng.integers(0, n, size=m)
+    if not loops:
+        keep = src != dst
+        src, dst = src[keep], dst[keep]
+    g.add_edges_from_no_data(list(zip(src.tolist(), dst.tolist())))
+    if multi and m:
+        k = max(1, m // 10)
+        idx = rng.integers(0, len(src), size=k)
+        g.add_edges_from_no_data(list(zip(src[idx].tolist(), dst[idx].tolist())))
+    for node in rng.choice(n, size=min(holes, n), replace=False).tolist():
+        g.remove_node(int(node))
+    eids = list(g.edge_indices())
+    for e in rng.choice(eids, size=min(holes, len(eids)), replace=False).tolist() if eids else []:
+        g.remove_edge_from_index(int(e))
+    # re-use some freed slots (index reuse after removal)
+    for _ in range(holes // 2):
+        g.add_node(None)
+    live = list(g.node_indices())
+    for _ in range(holes):
+        a, b = rng.choice(live, size=2).tolist()
+        g.add_edge(int(a), int(b), None)
+    return g
+
+
+def oracle_graph(oracle, g):
+    return oracle.OracleGraph.from_graph(g)
+
+
+def dense_from_mapping(mapping, bound):
+    out = np.zeros(bound)
+    present = np.zeros(bound, dtype=bool)
+    for k, v in mapping.items():
+        out[k] = v
+        present[k] = True
+    return out, present
+
+
+# ------------------------------------------------------------------------------------ goldens
+def test_reference_goldens_betweenness(rx):
+    # tests/graph/test_centrality.py:20-103 and tests/digraph/test_centrality.py:20-132
+    for cls, deleted in [(rx.PyGraph, False), (rx.PyGraph, True), (rx.PyDiGraph, False),
+                         (rx.PyDiGraph, True)]:
+        g = cls()
+        a, b, c = g.add_node("A"), g.add_node("B"), g.add_node("C")
+        c0 = g.add_node("C0") if deleted else None
+        d = g.add_node("D")
+        g.add_edges_from([(a, b, 1), (b, c, 1), (c, d, 1)])
+        if deleted:
+            g.remove_node(c0)
+        keys = [0, 1, 2, 4] if deleted else [0, 1, 2, 3]
+        if cls is rx.PyDiGraph:
+            norm = [0.0, 0.3333333333333333, 0.3333333333333333, 0.0]
+            endp = [0.25, 0.41666666666666663, 0.41666666666666663, 0.25]
+        else:
+            norm = [0.0, 0.6666666666666666, 0.6666666666666666, 0.0]
+            endp = [0.5, 0.8333333333333333, 0.8333333333333333, 0.5]
+        for threshold in (50, 1):
+            assert rx.betweenness_centrality(g, parallel_threshold=threshold) == dict(zip(keys, norm))
+            assert rx.betweenness_centrality(g, endpoints=True, parallel_threshold=threshold) == dict(zip(keys, endp))
+            assert rx.betweenness_centrality(g, endpoints=False, normalized=False,
+                                             parallel_threshold=threshold) == dict(zip(keys, [0.0, 2.0, 2.0, 0.0]))
+
+
+def test_reference_goldens_core_doctests(rx):
+    # rustworkx-core/src/centrality.rs:58-66, :164-170, :1146-1164
+    g = rx.PyGraph()
+    g.extend_from_edge_list([(0, 4), (1, 2), (2, 3), (3, 4), (1, 4)])
+    assert list(rx.betweenness_centrality(g, normalized=True, endpoints=True).values()) == pytest.approx(
+        [0.4, 0.5, 0.45, 0.5, 0.75], rel=1e-12)
+    assert rx.closeness_centrality(g) == {0: 1 / 2, 1: 2 / 3, 2: 4 / 7, 3: 2 / 3, 4: 4 / 5}
+    dg = rx.PyDiGraph()
+    dg.extend_from_edge_list([(0, 4), (1, 2), (2, 3), (3, 4), (1, 4)])
+    assert rx.closeness_centrality(dg) == {0: 0.0, 1: 0.0, 2: 1 / 4, 3: 1 / 3, 4: 4 / 5}
+    g = rx.PyGraph()
+    g.extend_from_edge_list([(0, 4), (1, 2), (1, 3), (2, 3), (3, 4), (1, 4)])
+    assert rx.edge_betweenness_centrality(g, normalized=False) == {0: 4.0, 1: 2.0, 2: 1.0, 3: 2.0, 4: 3.0, 5: 3.0}
+
+
+def test_reference_goldens_holes(rx):
+    # rustworkx-core/src/centrality.rs:628-696
+    g = rx.PyGraph()
+    n0, d0, n1, d1, n2, d2, n3 = (g.add_node(None) for _ in range(7))
+    for d in (d0, d1, d2):
+        g.remove_node(d)
+    g.add_edges_from_no_data([(n0, n1), (n1, n2), (n2, n3), (n3, n0)])
+    g.remove_edge_from_index(1)
+    assert rx.betweenness_centrality(g, normalized=False) == {0: 2.0, 2: 0.0, 4: 0.0, 6: 2.0}
+    assert rx.edge_betweenness_centrality(g, normalized=False) == {0: 3.0, 2: 3.0, 3: 4.0}
+
+
+def test_reference_goldens_edge_betweenness(rx):
+    # tests/graph/test_centrality.py:194-248, tests/digraph/test_centrality.py:227-259
+    gen = rx.generators
+
+    def check(g, expected, normalized=True):
+        got = rx.edge_betweenness_centrality(g, normalized=normalized)
+        assert list(got.keys()) == list(range(len(expected)))
+        for k, v in got.items():
+            assert v == pytest.approx(expected[k], abs=1e-7)
+
+    check(gen.mesh_graph(5), [0.1] * 10)
+    check(gen.path_graph(5), [0.4, 0.6, 0.6, 0.4])
+    check(gen.cycle_graph(5), [0.3] * 5)
+    check(gen.full_rary_tree(2, 7), [12, 12, 6, 6, 6, 6], False)
+    check(gen.path_graph(5), [4, 6, 6, 4], False)
+    g = rx.PyGraph()
+    g.add_nodes_from(range(10))
+    g.add_edges_from([(0, 1, 1), (0, 2, 1), (0, 3, 1), (0, 4, 1), (3, 5, 1), (4, 6, 1), (5, 7, 1),
+                      (6, 8, 1), (7, 8, 1), (8, 9, 1)])
+    check(g, [9, 9, 12, 15, 11, 14, 10, 13, 9, 9], False)
+    check(gen.directed_mesh_graph(5), [0.05] * 20)
+    check(gen.directed_path_graph(5), [0.2, 0.3, 0.3, 0.2])
+    check(gen.directed_cycle_graph(5), [0.5] * 5)
+    check(gen.full_rary_tree(2, 7).to_directed(), [12, 12, 12, 12, 6, 6, 6, 6, 6, 6, 6, 6], False)
+    check(gen.directed_path_graph(5), [4, 6, 6, 4], False)
+
+
+def test_reference_goldens_closeness(rx):
+    # rustworkx-core/tests/centrality.rs:17-120; tests/{graph,digraph}/test_centrality.py closeness
+    def g_from(cls, edges, n=None):
+        g = cls()
+        g.add_nodes_from(range(n if n is not None else max(max(e) for e in edges) + 1))
+        g.add_edges_from_no_data(edges)
+        return g
+
+    g = g_from(rx.PyGraph, [(1, 2), (2, 3), (3, 4), (1, 4)])
+    assert rx.closeness_centrality(g) == {0: 0.0, 1: 0.5625, 2: 0.5625, 3: 0.5625, 4: 0.5625}
+    g = g_from(rx.PyGraph, [(0, 1), (1, 2), (2, 3), (4, 5), (5, 6)])
+    assert rx.closeness_centrality(g) == {0: 1 / 4, 1: 3 / 8, 2: 3 / 8, 3: 1 / 4, 4: 2 / 9, 5: 1 / 3, 6: 2 / 9}
+    assert rx.closeness_centrality(g, wf_improved=False) == {0: 1 / 2, 1: 3 / 4, 2: 3 / 4, 3: 1 / 2,
+                                                             4: 2 / 3, 5: 1.0, 6: 2 / 3}
+    g = g_from(rx.PyDiGraph, [(0, 1), (1, 2)])
+    assert rx.closeness_centrality(g) == {0: 0.0, 1: 1 / 2, 2: 2 / 3}
+    assert rx.closeness_centrality(rx.generators.mesh_graph(5)) == {i: 1.0 for i in range(5)}
+    assert rx.closeness_centrality(rx.generators.path_graph(3)) == {0: 2 / 3, 1: 1.0, 2: 2 / 3}
+    for cls in (rx.PyGraph, rx.PyDiGraph):
+        g = cls()
+        a, b, c, c0, d = (g.add_node(x) for x in "ABCXD")
+        g.add_edges_from([(a, b, 1), (b, c, 1), (c, d, 1)])
+        g.remove_node(c0)
+        for thr in (50, 1):
+            if cls is rx.PyGraph:
+                assert rx.closeness_centrality(g, parallel_threshold=thr) == {0: 0.5, 1: 0.75, 2: 0.75, 4: 0.5}
+                assert rx.closeness_centrality(g, wf_improved=False) == {0: 0.5, 1: 0.75, 2: 0.75, 4: 0.5}
+            else:
+                assert rx.closeness_centrality(g, parallel_threshold=thr) == {0: 0.0, 1: 1 / 3, 2: 4 / 9, 4: 0.5}
+                assert rx.closeness_centrality(g, wf_improved=False) == {0: 0.0, 1: 1.0, 2: 2 / 3, 4: 0.5}
+
+
+def test_reference_goldens_distance_matrix(rx):
+    # tests/graph/test_dist_matrix.py:21-102, tests/digraph/test_dist_matrix.py:21-140
+    from test_oracle_golden import CYCLE7, CYCLE7_DIRECTED, CYCLE7_UNDIRECTED, _nan_expected
+
+    g = rx.PyGraph()
+    g.add_nodes_from(range(7))
+    g.add_edges_from_no_data(CYCLE7)
+    assert np.array_equal(rx.graph_distance_matrix(g), CYCLE7_UNDIRECTED)
+    assert np.array_equal(rx.graph_distance_matrix(g, parallel_threshold=5), CYCLE7_UNDIRECTED)
+    g.add_node(7)
+    assert np.array_equal(rx.graph_distance_matrix(g, null_value=np.nan), _nan_expected(), equal_nan=True)
+    dg = rx.PyDiGraph()
+    dg.add_nodes_from(range(7))
+    dg.add_edges_from_no_data(CYCLE7)
+    assert np.array_equal(rx.digraph_distance_matrix(dg), CYCLE7_DIRECTED)
+    assert np.array_equal(rx.digraph_distance_matrix(dg, as_undirected=True), CYCLE7_UNDIRECTED)
+    dg.add_node(7)
+    assert np.array_equal(rx.distance_matrix(dg, as_undirected=True, null_value=np.nan),
+                          _nan_expected(), equal_nan=True)
+    g = rx.generators.path_graph(4)
+    g.remove_node(0)
+    assert np.array_equal(rx.graph_distance_matrix(g), np.array([[0., 1, 2], [1, 0, 1], [2, 1, 0]]))
+    dg = rx.generators.directed_path_graph(4)
+    dg.remove_node(0)
+    assert np.array_equal(rx.digraph_distance_matrix(dg), np.array([[0., 1, 2], [0, 0, 1], [0, 0, 0]]))
+
+
+def test_dispatch_and_errors(rx):
+    # tests/test_dispatch.py:29-38,99-101
+    with pytest.raises(TypeError):
+        rx.betweenness_centrality("not a graph")
+    with pytest.raises(TypeError):
+        rx.distance_matrix(rx.PyGraph(), as_undirected=True)  # graph_distance_matrix has no such kwarg
+    with pytest.raises(OverflowError):
+        rx.betweenness_centrality(rx.PyGraph(), parallel_threshold=-1)
+    with pytest.raises(TypeError):
+        rx.graph_betweenness_centrality(rx.PyDiGraph())
+    assert rx.betweenness_centrality(rx.PyGraph()) == {}
+    assert rx.closeness_centrality(rx.PyDiGraph()) == {}
+    assert rx.distance_matrix(rx.PyGraph()).shape == (0, 0)
+    g = rx.PyGraph()
+    g.add_node(None)
+    assert rx.betweenness_centrality(g) == {0: 0.0}
+    assert rx.closeness_centrality(g) == {0: 0.0}
+    assert np.array_equal(rx.distance_matrix(g), np.zeros((1, 1)))
+
+
+# ------------------------------------------------------------------------------------ vs oracle
+CASES = [
+    # directed, n, m, seed, holes
+    (False, 40, 60, 1, 0),
+    (True, 40, 90, 2, 0),
+    (False, 97, 300, 3, 7),
+    (True, 97, 400, 4, 9),
+    (False, 300, 450, 5, 20),   # sparse: several components
+    (True, 300, 700, 6, 20),
+    (False, 1000, 4000, 7, 0),
+    (True, 1000, 6000, 8, 30),
+]
+
+
+@pytest.mark.parametrize("directed,n,m,seed,holes", CASES)
+def test_betweenness_vs_oracle(rx, oracle, directed, n, m, seed, holes):
+    g = random_graph(rx, directed, n, m, seed, holes)
+    og = oracle_graph(oracle, g)
+    nb, _ = g._bounds()
+    for normalized in (True, False):
+        for endpoints in (False, True):
+            want, present = og.betweenness_centrality(endpoints, normalized, 1 << 30, as_arrays=True)
+            got = rx.betweenness_centrality(g, normalized=normalized, endpoints=endpoints)
+            gd, gp = dense_from_mapping(got, nb)
+            assert np.array_equal(gp, present.astype(bool))
+            assert list(got.keys()) == list(g.node_indices())
+            assert_close(gd, want)
+
+
+@pytest.mark.parametrize("directed,n,m,seed,holes", CASES)
+def test_edge_betweenness_vs_oracle(rx, oracle, directed, n, m, seed, holes):
+    g = random_graph(rx, directed, n, m, seed, holes)
+    og = oracle_graph(oracle, g)
+    _, eb = g._bounds()
+    for normalized in (True, False):
+        want, present = og.edge_betweenness_centrality(normalized, 1 << 30, as_arrays=True)
+        got = rx.edge_betweenness_centrality(g, normalized=normalized)
+        gd, gp = dense_from_mapping(got, eb)
+        assert np.array_equal(gp, present.astype(bool))
+        assert list(got.keys()) == list(g.edge_indices())
+        assert_close(gd, want)
+
+
+@pytest.mark.parametrize("directed,n,m,seed,holes", CASES)
+def test_closeness_vs_oracle_bit_exact(rx, oracle, directed, n, m, seed, holes):
+    g = random_graph(rx, directed, n, m, seed, holes)
+    og = oracle_graph(oracle, g)
+    nb, _ = g._bounds()
+    for wf in (True, False):
+        want, present = og.closeness_centrality(wf, 1 << 30, as_arrays=True)
+        got = rx.closeness_centrality(g, wf_improved=wf)
+        gd, gp = dense_from_mapping(got, nb)
+        assert np.array_equal(gp, present.astype(bool))
+        assert np.array_equal(gd, want)  # bit exact
+
+
+@pytest.mark.parametrize("directed,n,m,seed,holes", CASES)
+def test_distance_matrix_vs_oracle_bit_exact(rx, oracle, directed, n, m, seed, holes):
+    g = random_graph(rx, directed, n, m, seed, holes)
+    og = oracle_graph(oracle, g)
+    for null in (0.0, math.nan, -1.0):
+        if directed:
+            for und in (False, True):
+                want = og.distance_matrix(300, und, null)
+                got = rx.digraph_distance_matrix(g, as_undirected=und, null_value=null)
+                assert got.dtype == np.float64 and got.flags.c_contiguous
+                assert np.array_equal(got, want, equal_nan=True)
+        else:
+            want = og.distance_matrix(300, True, null)
+            got = rx.graph_distance_matrix(g, null_value=null)
+            assert np.array_equal(got, want, equal_nan=True)
+
+
+def test_config1_gnp5000_betweenness(rx, oracle):
+    # BASELINE.json configs[0]: betweenness on undirected_gnp_random_graph(5000, 0.002, seed=42)
+    g = rx.undirected_gnp_random_graph(5000, 0.002, seed=42)
+    og = oracle_graph(oracle, g)
+    for normalized, endpoints in ((True, False), (False, True)):
+        want, _ = og.betweenness_centrality(endpoints, normalized, 50, as_arrays=True)
+        got = rx.betweenness_centrality(g, normalized=normalized, endpoints=endpoints)
+        assert_close(np.array(list(got.values())), want)
+
+
+def test_config2_heavy_hex(rx, oracle):
+    # BASELINE.json configs[1]: distance_matrix + closeness on heavy_hex_graph(d); d=15 on the CPU
+    # side keeps the oracle's O(n^2/64)-per-level bitset BFS within seconds, d=51 uses invariants
+    g = rx.generators.heavy_hex_graph(15)
+    og = oracle_graph(oracle, g)
+    assert np.array_equal(rx.distance_matrix(g), og.distance_matrix(300, True, 0.0))
+    for wf in (True, False):
+        want, _ = og.closeness_centrality(wf, 50, as_arrays=True)
+        assert np.array_equal(np.array(list(rx.closeness_centrality(g, wf_improved=wf).values())), want)
+    g = rx.generators.heavy_hex_graph(51)
+    n = g.num_nodes()
+    dm = rx.distance_matrix(g)
+    assert dm.shape == (n, n)
+    assert np.array_equal(dm, dm.T) and np.all(np.diag(dm) == 0.0)
+    assert np.all(dm[~np.eye(n, dtype=bool)] >= 1.0)
+    src, dst = g._esrc[: g._elen], g._edst[: g._elen]
+    assert np.all(dm[src, dst] == 1.0)
+    # closeness must equal (n-1)/rowsum * (n-1)/(n-1) computed from the matrix (connected graph)
+    cc = np.array(list(rx.closeness_centrality(g).values()))
+    rowsum = dm.sum(axis=0)
+    assert np.array_equal(cc, ((n - 1) / rowsum) * (n - 1) / (n - 1))
+    sample = np.arange(0, n, 97, dtype=np.uint32)
+    want, _ = oracle_graph(oracle, g).closeness_partial(sample, True, threads=oracle.max_threads())
+    assert np.array_equal(cc[sample], want[sample])
+
+
+def test_sampled_sources_large_ba(rx, oracle):
+    # config 3 shape at reduced size: BA graph, un-rescaled partial sums over sampled sources
+    from rustworkx_b200 import device_snapshot
+
+    g = rx.barabasi_albert_graph(20000, 8, seed=1)
+    og = oracle_graph(oracle, g)
+    rng = np.random.default_rng(0)
+    sources = rng.choice(20000, size=96, replace=False).astype(np.uint32)
+    dg = device_snapshot(g)
+    want, st = og.betweenness_partial(sources, False, threads=oracle.max_threads())
+    got = dg.betweenness_partial(sources, False)
+    assert_close(got, want)
+    gst = dg.stats()
+    assert gst["te"] == st["te"] and gst["te_dag"] == st["te_dag"] and gst["v"] == st["v"]
+    want_e, _ = og.edge_betweenness_partial(sources, threads=oracle.max_threads())
+    assert_close(dg.edge_betweenness_partial(sources), want_e)
+    # duplicates in the source list are counted twice, as additive contributions
+    dup = np.concatenate([sources[:5], sources[:5]])
+    assert_close(dg.betweenness_partial(dup, True), 2 * og.betweenness_partial(sources[:5], True)[0])
+
+
+def test_grid_closeness_sample(rx, oracle):
+    # config 2 high-diameter shape at reduced size, bit exact against the oracle
+    g = rx.generators.grid_graph(120, 90)
+    og = oracle_graph(oracle, g)
+    want, _ = og.closeness_centrality(True, 50, as_arrays=True)
+    got = np.array(list(rx.closeness_centrality(g).values()))
+    assert np.array_equal(got, want)
