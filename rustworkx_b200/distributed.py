@@ -1,0 +1,128 @@
+"""Multi-GPU host logic: one process per GPU, sources sharded, ONE reduce at the end.
+
+The reference is single-process: rayon workers take sources from a shared iterator and add into one
+vector behind an ``RwLock`` (``rustworkx-core/src/centrality.rs:107-121,280,317``).  Brandes'
+contributions are additive over sources, so here every rank
+
+1. snapshots the whole graph onto its own GPU (the CSR is small: 68 MB for the 1M-node config),
+2. runs ``rxc_*_partial`` on its round-robin shard of the live sources,
+3. takes part in a single sum-reduce of the partial vector (``rxc_comm_reduce_sum_f64`` = ncclReduce
+   over NVLink; with a ``gloo`` process group -- the CPU tests -- ``torch.distributed.reduce``),
+
+and rank 0 applies ``_rescale`` (``centrality.rs:221-252``).  Closeness and distance-matrix outputs
+are disjoint per source, so they need no reduction, only a gather of slices.
+
+``torch.distributed`` is plumbing only (rendezvous, the 128-byte NCCL id, the gloo test path).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+
+def shard_sources(sources, rank, world):
+    """Round-robin shard: rank r takes sources[r::world] (balances BA's age-correlated degrees)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad shard {rank}/{world}")
+    return np.ascontiguousarray(np.asarray(sources)[rank::world])
+
+
+def _dist():
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return None
+    return dist
+
+
+_COMM_READY = False
+
+
+def init_nccl_comm():
+    """Create librxcuda's own NCCL communicator; the unique id travels over torch.distributed."""
+    global _COMM_READY
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1 or _COMM_READY:
+        return
+    import torch
+
+    ident = np.zeros(128, dtype=np.uint8)
+    if dist.get_rank() == 0:
+        _lib.check(_lib.lib().rxc_comm_unique_id(_lib.p_u8(ident)))
+    obj = [ident.tobytes()]
+    dist.broadcast_object_list(obj, src=0)
+    ident = np.frombuffer(obj[0], dtype=np.uint8).copy()
+    _lib.check(_lib.lib().rxc_comm_init(dist.get_rank(), dist.get_world_size(), _lib.p_u8(ident)))
+    _COMM_READY = True
+    del torch
+
+
+def reduce_partial(partial, root=0):
+    """Sum-reduce a host f64 vector to ``root``.  NCCL (ours) when a CUDA process group is up,
+    gloo otherwise (CPU tests).  Returns the reduced vector on root, the local one elsewhere."""
+    dist = _dist()
+    partial = np.ascontiguousarray(partial, dtype=np.float64)
+    if dist is None or dist.get_world_size() == 1:
+        return partial
+    if dist.get_backend() == "nccl":
+        init_nccl_comm()
+        _lib.check(_lib.lib().rxc_comm_reduce_sum_f64(_lib.p_f64(partial), partial.shape[0], root))
+        return partial
+    import torch
+
+    t = torch.from_numpy(partial)
+    dist.reduce(t, dst=root, op=dist.ReduceOp.SUM)
+    return t.numpy()
+
+
+def _device_partial(graph, kind):
+    from . import device_snapshot
+
+    dg = device_snapshot(graph)
+    if kind == "node":
+        return lambda sources, endpoints: dg.betweenness_partial(sources, endpoints)
+    return lambda sources, endpoints: dg.edge_betweenness_partial(sources)
+
+
+def betweenness_centrality(graph, normalized=True, endpoints=False, *, rank=None, world=None,
+                           compute_partial=None):
+    """All-sources betweenness with the sources sharded over the process group.
+
+    Returns the dense, rescaled vector (original node indexing) on rank 0 and ``None`` elsewhere.
+    ``compute_partial(sources, endpoints) -> f64[n_bound]`` defaults to the CUDA path; the CPU tests
+    inject the oracle to exercise the sharding / reduce logic without a GPU.
+    """
+    dist = _dist()
+    if rank is None:
+        rank = dist.get_rank() if dist else 0
+    if world is None:
+        world = dist.get_world_size() if dist else 1
+    snap = graph._snapshot_arrays()
+    mine = shard_sources(snap["live_nodes"], rank, world)
+    fn = compute_partial or _device_partial(graph, "node")
+    partial = fn(mine, bool(endpoints))
+    total = reduce_partial(partial)
+    if rank != 0:
+        return None
+    return _lib.rescale(total.copy(), snap["live_nodes"].shape[0], normalized, snap["directed"],
+                        endpoints)
+
+
+def edge_betweenness_centrality(graph, normalized=True, *, rank=None, world=None,
+                                compute_partial=None):
+    """Edge variant of :func:`betweenness_centrality` (dense over original edge indices)."""
+    dist = _dist()
+    if rank is None:
+        rank = dist.get_rank() if dist else 0
+    if world is None:
+        world = dist.get_world_size() if dist else 1
+    snap = graph._snapshot_arrays()
+    mine = shard_sources(snap["live_nodes"], rank, world)
+    fn = compute_partial or _device_partial(graph, "edge")
+    total = reduce_partial(fn(mine, False))
+    if rank != 0:
+        return None
+    # edge betweenness always rescales with include_endpoints=true (centrality.rs:211-217)
+    return _lib.rescale(total.copy(), snap["live_nodes"].shape[0], normalized, snap["directed"], True)

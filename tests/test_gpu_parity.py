@@ -375,3 +375,26 @@ def test_grid_closeness_sample(rx, oracle):
     want, _ = og.closeness_centrality(True, 50, as_arrays=True)
     got = np.array(list(rx.closeness_centrality(g).values()))
     assert np.array_equal(got, want)
+
+
+def test_networkx_golden_fixture(rx):
+    # committed vectors from an independent implementation (tests/golden/make_golden.py)
+    import json
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nx_golden.json")
+    for case in json.load(open(path))["cases"]:
+        g = rx.PyDiGraph() if case["directed"] else rx.PyGraph()
+        g.add_nodes_from(range(case["n"]))
+        g.add_edges_from_no_data([tuple(e) for e in case["edges"]])
+        bc = rx.betweenness_centrality(g, normalized=case["normalized"], endpoints=case["endpoints"])
+        assert_close(list(bc.values()), case["betweenness"])
+        ebc = rx.edge_betweenness_centrality(g, normalized=case["normalized"])
+        assert_close(list(ebc.values()), case["edge_betweenness"])
+        cc = rx.closeness_centrality(g)
+        assert np.allclose(list(cc.values()), case["closeness_wf"], rtol=4e-16, atol=0)
+        if case["directed"]:
+            dm = rx.digraph_distance_matrix(g, null_value=-1.0)
+        else:
+            dm = rx.graph_distance_matrix(g, null_value=-1.0)
+        assert np.array_equal(dm, np.array(case["distance_matrix"]))
