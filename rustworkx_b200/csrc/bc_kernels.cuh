@@ -4,125 +4,328 @@
 //   forward  BFS + sigma : rustworkx-core/src/centrality.rs:406-445 (node), :459-511 (edge)
 //   backward dependency  : rustworkx-core/src/centrality.rs:254-299 (node), :301-327 (edge)
 //
-// Layout: sources are processed in GROUPS of 32 -- one warp lane per source.  For a
-// group g, every per-(vertex, source) f64 lives in a 256-byte row  sc[g][v][0..31]  so that the
-// random gather a BFS does per arc moves eight full 32-byte sectors instead of one 8-byte value per
-// sector.  Which of the 32 sources an arc matters for is decided from 32-bit masks:
-//   visited[g][v]   bit b = source b has reached v
-//   P[par][g][v]    (tag << 32) | mask of sources for which v sits at the level the tag names
-// The tag makes the two P arrays reusable across levels and batches without clearing.
-// Every level also appends its (vertex, mask) pairs to a per-group queue; the backward sweep replays
-// the queue levels in reverse and pulls from successors (no atomics on the f64 rows).
+// Layout.  Sources are processed in GROUPS of 128.  For a group g every
+// per-(vertex, source) f64 lives in one 1 KB row  sc[g][v][0..127]; warp lane l owns the 32-byte
+// sector sc[g][v][4l..4l+3], i.e. FOUR sources (slot k of lane l is source 32k+l of the group).
+// The irregular access of a BFS -- "for each arc (v,w) read something of v" -- therefore moves whole
+// DRAM sectors, one per lane, and a lane only issues its load when one of its four sources needs
+// the arc.  Which sources need it is decided from 128-bit masks (word k, bit l <-> lane l, slot k):
+//   visited[g][v]   source has reached v
+//   P[par][g][v]    {tag, mask}: sources for which v sits on the level the tag names (one 32-byte
+//                   entry = one sector per look-up; the tag makes clearing unnecessary)
+// Every level appends its (vertex, mask) pairs to a per-group queue; the backward sweep replays the
+// queue levels in reverse and pulls from successors (no atomics on the f64 rows).
+//
+// Why 128: ncu on the 32-source version showed ~40 issued instructions per gathered row and half
+// of all issue slots busy; with four sources per lane the per-arc look-up, shuffles and address
+// arithmetic are amortised over 4x the sources and every load carries 32 bytes per lane.
+// Vertices above `hub_degree` are deferred to a CTA-per-vertex kernel so that one warp never
+// serialises a hub's thousands of arcs.
 #pragma once
 
 #include "common.cuh"
 
 namespace rxc {
 
+constexpr int BG = 128;  // sources per betweenness group
+constexpr int BK = 4;    // sources per lane (one 32-byte sector of f64)
+
+struct __align__(16) Mask128 {
+    uint32_t w[BK];
+};
+
+struct __align__(32) PEntry {
+    uint32_t tag;
+    uint32_t pad[3];
+    Mask128 m;
+};
+
+__device__ __forceinline__ Mask128 mask_zero() {
+    Mask128 r;
+    r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0;
+    return r;
+}
+__device__ __forceinline__ uint32_t mask_or(const Mask128 &a) {
+    return a.w[0] | a.w[1] | a.w[2] | a.w[3];
+}
+__device__ __forceinline__ bool mask_any(const Mask128 &a) { return mask_or(a) != 0; }
+__device__ __forceinline__ uint32_t mask_popc(const Mask128 &a) {
+    return __popc(a.w[0]) + __popc(a.w[1]) + __popc(a.w[2]) + __popc(a.w[3]);
+}
+__device__ __forceinline__ Mask128 mask_load(const Mask128 *p) {
+    const uint4 t = *reinterpret_cast<const uint4 *>(p);
+    Mask128 r;
+    r.w[0] = t.x;
+    r.w[1] = t.y;
+    r.w[2] = t.z;
+    r.w[3] = t.w;
+    return r;
+}
+__device__ __forceinline__ void mask_store(Mask128 *p, const Mask128 &a) {
+    *reinterpret_cast<uint4 *>(p) = make_uint4(a.w[0], a.w[1], a.w[2], a.w[3]);
+}
+__device__ __forceinline__ Mask128 mask_shfl(const Mask128 &a, int src) {
+    Mask128 r;
+#pragma unroll
+    for (int k = 0; k < BK; k++) r.w[k] = __shfl_sync(FULL, a.w[k], src);
+    return r;
+}
+
 struct BcParams {
     const uint32_t *row;  // CSR offsets of the adjacency this kernel walks
     const uint32_t *col;  // CSR targets (compact vertex ids)
     const uint32_t *eid;  // arc -> original edge index (edge betweenness only)
-    double *sc;           // [NG][n][32] sigma on the way down, (1+delta)/sigma on the way up
-    uint64_t *P0;         // [NG][n] tagged level masks, even levels
-    uint64_t *P1;         // [NG][n] tagged level masks, odd levels
-    uint32_t *visited;    // [NG][n]
+    double *sc;           // [NG][n][128] sigma on the way down, (1+delta)/sigma on the way up
+    PEntry *P0;           // [NG][n] tagged level masks, even levels
+    PEntry *P1;           // [NG][n] tagged level masks, odd levels
+    Mask128 *visited;     // [NG][n]
     uint32_t *qv;         // [NG][qcap] level queues: vertex
-    uint32_t *qm;         // [NG][qcap] level queues: source mask
+    Mask128 *qm;          // [NG][qcap] level queues: source mask
     uint32_t *loff;       // [NG][lcap] queue offset of each level
     uint32_t *lvlcnt;     // [NG][lcap] entries of each level
     uint32_t *lvl_total;  // [lcap] entries of each level summed over groups
-    unsigned long long *reach;  // [NG][32] vertices reached per source, excluding the source
+    uint32_t *hubv;       // [NG][hubcap] deferred high-degree work items: vertex
+    Mask128 *hubm;        // [NG][hubcap] deferred high-degree work items: mask
+    uint32_t *hubcnt;     // [2][NG] number of deferred items, by level parity
+    unsigned long long *reach;  // [NG][128] vertices reached per source, excluding the source
     unsigned long long *stats;  // [ST_COUNT]
     double *acc;          // node mode: [n] by compact vertex; edge mode: [e_bound] by edge index
-    const uint32_t *src;  // [NG][32] compact source ids, NO_SOURCE padded
+    const uint32_t *src;  // [NG][128] compact source ids, NO_SOURCE padded; slot 32k+l = lane l, k
     uint64_t qcap;
     uint32_t n;
     uint32_t lcap;
+    uint32_t hubcap;
+    uint32_t hub_degree;  // arcs; above this a vertex is handled by a whole CTA
+    uint32_t ngroups;     // groups in this batch (stride of hubcnt)
     uint32_t tagbase;     // tag of level l is tagbase + l + 1
 };
 
-__device__ __forceinline__ uint64_t *bc_P(const BcParams &p, uint32_t level) {
+__device__ __forceinline__ PEntry *bc_P(const BcParams &p, uint32_t level) {
     return (level & 1) ? p.P1 : p.P0;
 }
 
-// visited[g][*] = ~valid(g): lanes without a source count as "reached everywhere".
-__global__ void __launch_bounds__(BLOCK) bc_init_kernel(BcParams p) {
-    const uint32_t g = blockIdx.y;
-    const uint32_t s = p.src[g * GW + lane_id()];
-    const uint32_t valid = __ballot_sync(FULL, s != NO_SOURCE);
-    const uint32_t w = blockIdx.x * BLOCK + threadIdx.x;
-    if (w < p.n) p.visited[(size_t)g * p.n + w] = ~valid;
+__device__ __forceinline__ uint32_t *bc_hubcnt(const BcParams &p, uint32_t level, uint32_t g) {
+    return p.hubcnt + (size_t)(level & 1) * p.ngroups + g;
 }
 
-// Level 0: one warp per group seeds its (up to) 32 sources.
+// Mask of vertex v if it sits on the level `tag` names, else empty; one sector per look-up.
+__device__ __forceinline__ Mask128 bc_level_mask(const PEntry *P, uint32_t v, uint32_t tag) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(&P[v]);
+    const uint4 t = q[0], mm = q[1];
+    Mask128 m;
+    const bool ok = t.x == tag;
+    m.w[0] = ok ? mm.x : 0u;
+    m.w[1] = ok ? mm.y : 0u;
+    m.w[2] = ok ? mm.z : 0u;
+    m.w[3] = ok ? mm.w : 0u;
+    return m;
+}
+
+__device__ __forceinline__ void bc_store_level(PEntry *P, uint32_t v, uint32_t tag,
+                                               const Mask128 &m) {
+    uint4 *q = reinterpret_cast<uint4 *>(&P[v]);
+    q[0] = make_uint4(tag, 0, 0, 0);
+    q[1] = make_uint4(m.w[0], m.w[1], m.w[2], m.w[3]);
+}
+
+// Defer a high-degree work item (warp-uniform v, mask) to the CTA-per-vertex kernel; called by
+// the whole warp, appended once by lane 0.  False when the list is full.
+__device__ __forceinline__ bool bc_defer_hub(const BcParams &p, uint32_t level, uint32_t g,
+                                             uint32_t v, const Mask128 &mask) {
+    int ok = 0;
+    if (lane_id() == 0) {
+        const uint32_t h = atomicAdd(bc_hubcnt(p, level, g), 1u);
+        if (h < p.hubcap) {
+            p.hubv[(size_t)g * p.hubcap + h] = v;
+            mask_store(&p.hubm[(size_t)g * p.hubcap + h], mask);
+            ok = 1;
+        }
+    }
+    return __shfl_sync(FULL, ok, 0) != 0;
+}
+
+__device__ __forceinline__ Mask128 bc_valid_mask(const BcParams &p, uint32_t g) {
+    Mask128 valid;
+#pragma unroll
+    for (int k = 0; k < BK; k++)
+        valid.w[k] = __ballot_sync(FULL, p.src[(size_t)g * BG + k * 32 + lane_id()] != NO_SOURCE);
+    return valid;
+}
+
+// visited[g][*] = ~valid(g): slots without a source count as "reached everywhere".
+__global__ void __launch_bounds__(BLOCK) bc_init_kernel(BcParams p) {
+    const uint32_t g = blockIdx.y;
+    const Mask128 valid = bc_valid_mask(p, g);
+    const uint32_t w = blockIdx.x * BLOCK + threadIdx.x;
+    if (w < p.n) {
+        Mask128 nv;
+#pragma unroll
+        for (int k = 0; k < BK; k++) nv.w[k] = ~valid.w[k];
+        mask_store(&p.visited[(size_t)g * p.n + w], nv);
+    }
+}
+
+// Level 0: one warp per group seeds its (up to) 128 sources.
 __global__ void __launch_bounds__(32) bc_seed_kernel(BcParams p) {
     const uint32_t g = blockIdx.x;
     const int lane = lane_id();
-    const uint32_t s = p.src[g * GW + lane];
-    const bool ok = s != NO_SOURCE;
-    const uint32_t valid = __ballot_sync(FULL, ok);
-    const uint32_t cnt = __popc(valid);
-    if (ok) {
-        const size_t gv = (size_t)g * p.n + s;
-        const uint32_t bit = 1u << lane;
-        p.visited[gv] = ~valid | bit;
-        p.P0[gv] = ((uint64_t)(p.tagbase + 1) << 32) | bit;
-        p.sc[gv * GW + lane] = 1.0;
-        const uint32_t i = __popc(valid & lanemask_lt());
-        p.qv[(size_t)g * p.qcap + i] = s;
-        p.qm[(size_t)g * p.qcap + i] = bit;
+    const Mask128 valid = bc_valid_mask(p, g);
+    uint32_t base = 0;
+#pragma unroll
+    for (int k = 0; k < BK; k++) {
+        const uint32_t s = p.src[(size_t)g * BG + k * 32 + lane];
+        if (s != NO_SOURCE) {
+            const size_t gv = (size_t)g * p.n + s;
+            Mask128 bit = mask_zero();
+            bit.w[k] = 1u << lane;
+            Mask128 vis;
+#pragma unroll
+            for (int j = 0; j < BK; j++) vis.w[j] = ~valid.w[j] | bit.w[j];
+            mask_store(&p.visited[gv], vis);  // sources of a group are distinct vertices
+            bc_store_level(p.P0 + (size_t)g * p.n, s, p.tagbase + 1, bit);
+            p.sc[gv * BG + lane * BK + k] = 1.0;
+            const uint32_t i = base + __popc(valid.w[k] & lanemask_lt());
+            p.qv[(size_t)g * p.qcap + i] = s;
+            mask_store(&p.qm[(size_t)g * p.qcap + i], bit);
+        }
+        base += __popc(valid.w[k]);
+        p.reach[(size_t)g * BG + k * 32 + lane] = 0ull;
     }
-    p.reach[g * GW + lane] = 0ull;
     if (lane == 0) {
         p.loff[(size_t)g * p.lcap] = 0;
-        p.lvlcnt[(size_t)g * p.lcap] = cnt;
-        atomicAdd(&p.lvl_total[0], cnt);
+        p.lvlcnt[(size_t)g * p.lcap] = base;
+        p.hubcnt[g] = 0;
+        p.hubcnt[p.ngroups + g] = 0;
+        atomicAdd(&p.lvl_total[0], base);
     }
 }
 
-// Gather rows[vj][lane] for up to four arcs per round so that four 256-byte rows are in flight
-// per warp.  v_lane/m_lane hold one arc per lane; nz = ballot of lanes whose mask is non-zero.
-__device__ __forceinline__ void bc_gather(const double *__restrict__ rows, uint32_t v_lane,
-                                          uint32_t m_lane, uint32_t nz, int lane, double &acc,
-                                          uint32_t &seen, unsigned long long &dag) {
+// ---------------------------------------------------------------------------------------------
+// row gathers: lane = sector of four sources
+// ---------------------------------------------------------------------------------------------
+struct Row4 {
+    double x[BK];
+};
+
+__device__ __forceinline__ Row4 row_load(const double *rows, uint32_t v, int lane, bool on) {
+    Row4 r;
+    if (on) {
+        const double2 *q = reinterpret_cast<const double2 *>(rows + (size_t)v * BG + lane * BK);
+        const double2 a = q[0], b = q[1];
+        r.x[0] = a.x;
+        r.x[1] = a.y;
+        r.x[2] = b.x;
+        r.x[3] = b.y;
+    } else {
+        r.x[0] = r.x[1] = r.x[2] = r.x[3] = 0.0;
+    }
+    return r;
+}
+
+// Staging area: every warp owns STAGE row slots of 1 KB in (dynamic) shared memory.  cp.async
+// (LDGSTS, 16-byte, L1-bypassing) fetches a lane's 32-byte sector into its own slice of the slot;
+// lanes none of whose four sources needs the arc zero-fill without touching memory.  A lane later
+// reads only bytes it copied itself, so cp.async.wait_all is the only synchronisation needed and
+// up to STAGE KB per warp are in flight without holding registers.
+constexpr int STAGE = 8;
+constexpr int BC_SMEM_BYTES = WARPS * STAGE * BG * 8;  // 64 KB per CTA
+
+__device__ __forceinline__ void cp_async_sector(double *smem_dst, const double *gsrc, bool on) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int sz = on ? 16 : 0;  // src-size 0: zero-fill, no global access
+    asm volatile(
+        "cp.async.cg.shared.global [%0], [%1], 16, %2;\n"
+        "cp.async.cg.shared.global [%3], [%4], 16, %2;\n" ::"r"(d),
+        "l"(gsrc), "r"(sz), "r"(d + 16), "l"(gsrc + 2)
+        : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+}
+
+// acc[k] += rows[v][lane][k] over the arcs in nz (lanes of v_lane / m_lane with a non-empty mask)
+// for the sources the arc's mask names, arc order preserved; up to STAGE rows in flight per warp.
+__device__ __forceinline__ void bc_gather(const double *rows, uint32_t v_lane, const Mask128 &m_lane,
+                                          uint32_t nz, int lane, double *stage, double (&acc)[BK],
+                                          Mask128 &seen, unsigned long long &dag) {
     while (nz) {
-        uint32_t vj[4], mj[4];
+        uint32_t todo = nz;
+        int cnt = 0;
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const bool ok = nz != 0;
-            const int j = ok ? (__ffs(nz) - 1) : 0;
-            nz &= nz - 1;
-            vj[u] = __shfl_sync(FULL, v_lane, j);
-            const uint32_t mm = __shfl_sync(FULL, m_lane, j);
-            mj[u] = ok ? mm : 0u;
+        for (int i = 0; i < STAGE; i++) {
+            if (nz) {  // warp-uniform
+                const int a = __ffs(nz) - 1;
+                nz &= nz - 1;
+                const uint32_t vj = __shfl_sync(FULL, v_lane, a);
+                const uint32_t any = __shfl_sync(FULL, mask_or(m_lane), a);
+                cp_async_sector(stage + i * BG + lane * BK, rows + (size_t)vj * BG + lane * BK,
+                                (any >> lane) & 1u);
+                cnt = i + 1;
+            }
         }
-        double x[4];
+        cp_async_wait_all();
 #pragma unroll
-        for (int u = 0; u < 4; u++)
-            x[u] = ((mj[u] >> lane) & 1u) ? rows[(size_t)vj[u] * GW + lane] : 0.0;
+        for (int i = 0; i < STAGE; i++) {
+            if (i < cnt) {
+                const int a = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const Mask128 mj = mask_shfl(m_lane, a);
+                const double2 *q = reinterpret_cast<const double2 *>(stage + i * BG + lane * BK);
+                const double2 x0 = q[0], x1 = q[1];
+                if ((mj.w[0] >> lane) & 1u) acc[0] += x0.x;
+                if ((mj.w[1] >> lane) & 1u) acc[1] += x0.y;
+                if ((mj.w[2] >> lane) & 1u) acc[2] += x1.x;
+                if ((mj.w[3] >> lane) & 1u) acc[3] += x1.y;
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            acc += x[u];
-            seen |= mj[u];
-            dag += __popc(mj[u]);
+                for (int k = 0; k < BK; k++) seen.w[k] |= mj.w[k];
+                dag += mask_popc(mj);
+            }
         }
     }
 }
 
-// One BFS level for every group of the batch: vertices not yet reached by all 32 sources scan
-// their in-arcs, pick up the sources whose frontier (level `level`) holds the neighbour, and sum the
-// neighbours' sigma rows -- the bottom-up form of centrality.rs:427-437.  No early exit: every
-// frontier parent contributes to sigma.
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+
+// One warp: scan the in-arcs of a vertex (chunks of 32 arcs starting at e0+first, stride `step`),
+// pick up the sources whose frontier holds the neighbour, and sum the neighbours' sigma rows.
+__device__ __forceinline__ void bc_fwd_scan(const BcParams &p, const double *rows, const PEntry *Pcur,
+                                            uint32_t tag_cur, uint32_t e0, uint32_t e1,
+                                            uint32_t first, uint32_t step, const Mask128 &unv,
+                                            int lane, double *stage, double (&acc)[BK],
+                                            Mask128 &newm, unsigned long long &dag) {
+    for (uint32_t e = e0 + first; e < e1; e += step) {
+        const uint32_t idx = e + lane;
+        uint32_t v = 0;
+        Mask128 m = mask_zero();
+        if (idx < e1) {
+            v = p.col[idx];
+            m = bc_level_mask(Pcur, v, tag_cur);
+#pragma unroll
+            for (int k = 0; k < BK; k++) m.w[k] &= unv.w[k];
+        }
+        const uint32_t nz = __ballot_sync(FULL, mask_any(m));
+        bc_gather(rows, v, m, nz, lane, stage, acc, newm, dag);
+    }
+}
+
+// One BFS level for every group of the batch: vertices not yet reached by all 128 sources scan
+// their in-arcs -- the bottom-up form of centrality.rs:427-437.  No early exit: every frontier
+// parent contributes to sigma.
 __global__ void __launch_bounds__(BLOCK) bc_forward_kernel(BcParams p, uint32_t level) {
     const uint32_t g = blockIdx.y;
     uint32_t *lc = p.lvlcnt + (size_t)g * p.lcap;
     uint32_t *lo = p.loff + (size_t)g * p.lcap;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *bc_hubcnt(p, level + 1, g) = 0;  // for the next launch
     const uint32_t fcnt = lc[level];
     if (fcnt == 0) return;  // this group's BFS has finished
 
-    __shared__ uint32_t s_w[BLOCK], s_unv[BLOCK], s_ov[BLOCK], s_om[BLOCK];
+    __shared__ Mask128 s_unv[BLOCK], s_om[BLOCK];
+    __shared__ uint32_t s_w[BLOCK], s_ov[BLOCK];
     __shared__ uint32_t s_ncand, s_next, s_nout, s_base;
+    extern __shared__ __align__(16) double s_dyn_stage[];
+    double *stage = s_dyn_stage + (size_t)(threadIdx.x >> 5) * STAGE * BG;
     const int tid = threadIdx.x, lane = lane_id();
     if (tid == 0) {
         s_ncand = 0;
@@ -132,21 +335,27 @@ __global__ void __launch_bounds__(BLOCK) bc_forward_kernel(BcParams p, uint32_t 
     __syncthreads();
 
     const size_t gn = (size_t)g * p.n;
-    uint32_t *visited = p.visited + gn;
-    const uint64_t *Pcur = bc_P(p, level) + gn;
-    uint64_t *Pnext = bc_P(p, level + 1) + gn;
-    double *rows = p.sc + gn * GW;
+    Mask128 *visited = p.visited + gn;
+    const PEntry *Pcur = bc_P(p, level) + gn;
+    PEntry *Pnext = bc_P(p, level + 1) + gn;
+    double *rows = p.sc + gn * BG;
     const uint32_t tag_cur = p.tagbase + level + 1, tag_next = tag_cur + 1;
 
-    // 1. coalesced read of this CTA's 256 visited words; compact the unfinished vertices
+    // 1. coalesced read of this CTA's 256 visited masks; compact the unfinished vertices
     {
         const uint32_t w = blockIdx.x * BLOCK + tid;
-        const uint32_t unv = (w < p.n) ? ~visited[w] : 0u;
-        const uint32_t bal = __ballot_sync(FULL, unv != 0);
+        Mask128 unv = mask_zero();
+        if (w < p.n) {
+            const Mask128 vis = mask_load(&visited[w]);
+#pragma unroll
+            for (int k = 0; k < BK; k++) unv.w[k] = ~vis.w[k];
+        }
+        const bool any = mask_any(unv);
+        const uint32_t bal = __ballot_sync(FULL, any);
         uint32_t wbase = 0;
         if (lane == 0 && bal) wbase = atomicAdd(&s_ncand, __popc(bal));
         wbase = __shfl_sync(FULL, wbase, 0);
-        if (unv) {
+        if (any) {
             const uint32_t i = wbase + __popc(bal & lanemask_lt());
             s_w[i] = w;
             s_unv[i] = unv;
@@ -162,27 +371,24 @@ __global__ void __launch_bounds__(BLOCK) bc_forward_kernel(BcParams p, uint32_t 
         if (lane == 0) i = atomicAdd(&s_next, 1);
         i = __shfl_sync(FULL, i, 0);
         if (i >= ncand) break;
-        const uint32_t w = s_w[i], unv = s_unv[i];
+        const uint32_t w = s_w[i];
+        const Mask128 unv = s_unv[i];
         const uint32_t e0 = p.row[w], e1 = p.row[w + 1];
-        double acc = 0.0;
-        uint32_t newm = 0;
-        for (uint32_t e = e0; e < e1; e += 32) {
-            const uint32_t idx = e + lane;
-            uint32_t v = 0, m = 0;
-            if (idx < e1) {
-                v = p.col[idx];
-                const uint64_t pv = Pcur[v];
-                if ((uint32_t)(pv >> 32) == tag_cur) m = (uint32_t)pv & unv;
-            }
-            const uint32_t nz = __ballot_sync(FULL, m != 0);
-            bc_gather(rows, v, m, nz, lane, acc, newm, dag);
-        }
-        if (newm) {
-            if ((newm >> lane) & 1u) rows[(size_t)w * GW + lane] = acc;
+        if (e1 - e0 > p.hub_degree && bc_defer_hub(p, level, g, w, unv)) continue;
+        double acc[BK] = {0.0, 0.0, 0.0, 0.0};
+        Mask128 newm = mask_zero();
+        bc_fwd_scan(p, rows, Pcur, tag_cur, e0, e1, 0, 32, unv, lane, stage, acc, newm, dag);
+        if (mask_any(newm)) {
+#pragma unroll
+            for (int k = 0; k < BK; k++)
+                if ((newm.w[k] >> lane) & 1u) rows[(size_t)w * BG + lane * BK + k] = acc[k];
             if (lane == 0) {
-                visited[w] = ~unv | newm;
-                Pnext[w] = ((uint64_t)tag_next << 32) | newm;
-                const uint32_t j = atomicAdd(&s_nout, 1);
+                Mask128 vis;
+#pragma unroll
+                for (int k = 0; k < BK; k++) vis.w[k] = ~unv.w[k] | newm.w[k];
+                mask_store(&visited[w], vis);
+                bc_store_level(Pnext, w, tag_next, newm);
+                const uint32_t j = atomicAdd(&s_nout, 1u);
                 s_ov[j] = w;
                 s_om[j] = newm;
             }
@@ -206,98 +412,256 @@ __global__ void __launch_bounds__(BLOCK) bc_forward_kernel(BcParams p, uint32_t 
     if ((uint32_t)tid < nout) {
         const size_t q = (size_t)g * p.qcap + s_base + tid;
         p.qv[q] = s_ov[tid];
-        p.qm[q] = s_om[tid];
+        mask_store(&p.qm[q], s_om[tid]);
     }
-    (void)dag;
+}
+
+// Deferred high-degree vertices of the forward level: one CTA per vertex, warps split the arcs.
+__global__ void __launch_bounds__(BLOCK) bc_forward_hub_kernel(BcParams p, uint32_t level) {
+    const uint32_t g = blockIdx.y;
+    uint32_t *lc = p.lvlcnt + (size_t)g * p.lcap;
+    uint32_t *lo = p.loff + (size_t)g * p.lcap;
+    const uint32_t fcnt = lc[level];
+    const uint32_t nh = min(*bc_hubcnt(p, level, g), p.hubcap);
+    if (fcnt == 0 || nh == 0) return;
+    const int tid = threadIdx.x, lane = lane_id(), wid = tid >> 5;
+    const size_t gn = (size_t)g * p.n;
+    Mask128 *visited = p.visited + gn;
+    const PEntry *Pcur = bc_P(p, level) + gn;
+    PEntry *Pnext = bc_P(p, level + 1) + gn;
+    double *rows = p.sc + gn * BG;
+    const uint32_t tag_cur = p.tagbase + level + 1, tag_next = tag_cur + 1;
+    __shared__ double s_acc[WARPS][BG];
+    __shared__ Mask128 s_new[WARPS];
+    extern __shared__ __align__(16) double s_dyn_stage[];
+    double *stage = s_dyn_stage + (size_t)(threadIdx.x >> 5) * STAGE * BG;
+
+    for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
+        const uint32_t w = p.hubv[(size_t)g * p.hubcap + h];
+        const Mask128 unv = mask_load(&p.hubm[(size_t)g * p.hubcap + h]);
+        const uint32_t e0 = p.row[w], e1 = p.row[w + 1];
+        double acc[BK] = {0.0, 0.0, 0.0, 0.0};
+        Mask128 newm = mask_zero();
+        unsigned long long dag = 0;
+        bc_fwd_scan(p, rows, Pcur, tag_cur, e0, e1, wid * 32, WARPS * 32, unv, lane, stage, acc, newm,
+                    dag);
+#pragma unroll
+        for (int k = 0; k < BK; k++) s_acc[wid][lane * BK + k] = acc[k];
+        if (lane == 0) s_new[wid] = newm;
+        __syncthreads();
+        if (wid == 0) {
+            double tot[BK] = {0.0, 0.0, 0.0, 0.0};
+            Mask128 nm = mask_zero();
+            for (int q = 0; q < WARPS; q++) {
+#pragma unroll
+                for (int k = 0; k < BK; k++) {
+                    tot[k] += s_acc[q][lane * BK + k];
+                    nm.w[k] |= s_new[q].w[k];
+                }
+            }
+            if (mask_any(nm)) {
+#pragma unroll
+                for (int k = 0; k < BK; k++)
+                    if ((nm.w[k] >> lane) & 1u) rows[(size_t)w * BG + lane * BK + k] = tot[k];
+                if (lane == 0) {
+                    Mask128 vis;
+#pragma unroll
+                    for (int k = 0; k < BK; k++) vis.w[k] = ~unv.w[k] | nm.w[k];
+                    mask_store(&visited[w], vis);
+                    bc_store_level(Pnext, w, tag_next, nm);
+                    const uint32_t pos = atomicAdd(&lc[level + 1], 1u);
+                    atomicAdd(&p.lvl_total[level + 1], 1u);
+                    const size_t q = (size_t)g * p.qcap + lo[level] + fcnt + pos;
+                    p.qv[q] = w;
+                    mask_store(&p.qm[q], nm);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+
+// Successor pull of one warp over chunks of 32 arcs starting at e0+first with stride `step`.
+// Node mode sums coef rows into acc; edge mode adds sigma[v][b]*coef[w][b], summed over b, to the
+// arc's edge and the same products into acc (centrality.rs:318-325).
+template <bool EDGE>
+__device__ __forceinline__ void bc_bwd_scan(const BcParams &p, const double *rows,
+                                            const PEntry *Pnext, uint32_t tag_next, uint32_t e0,
+                                            uint32_t e1, uint32_t first, uint32_t step,
+                                            const Mask128 &fm, const double (&sig)[BK], int lane,
+                                            double *stage, double (&acc)[BK],
+                                            unsigned long long &dag) {
+    for (uint32_t e = e0 + first; e < e1; e += step) {
+        const uint32_t idx = e + lane;
+        uint32_t w = 0, ed = 0;
+        Mask128 m = mask_zero();
+        if (idx < e1) {
+            w = p.col[idx];
+            m = bc_level_mask(Pnext, w, tag_next);
+#pragma unroll
+            for (int k = 0; k < BK; k++) m.w[k] &= fm.w[k];
+            if (EDGE && mask_any(m)) ed = p.eid[idx];
+        }
+        uint32_t nz = __ballot_sync(FULL, mask_any(m));
+        if (!EDGE) {
+            Mask128 seen = mask_zero();
+            bc_gather(rows, w, m, nz, lane, stage, acc, seen, dag);
+        } else {
+            while (nz) {
+                const int a = __ffs(nz) - 1;
+                nz &= nz - 1;
+                const uint32_t wj = __shfl_sync(FULL, w, a);
+                const uint32_t ej = __shfl_sync(FULL, ed, a);
+                const Mask128 mj = mask_shfl(m, a);
+                const Row4 x = row_load(rows, wj, lane, (mask_or(mj) >> lane) & 1u);
+                double c = 0.0;
+#pragma unroll
+                for (int k = 0; k < BK; k++) {
+                    if ((mj.w[k] >> lane) & 1u) {
+                        const double ck = sig[k] * x.x[k];  // sigma[v] * coeff, centrality.rs:322
+                        acc[k] += ck;
+                        c += ck;
+                    }
+                }
+                dag += mask_popc(mj);
+                const double tot = warp_sum(c);
+                if (lane == 0) atomicAdd(&p.acc[ej], tot);
+            }
+        }
+    }
+}
+
+// Finish one queue entry (v, fm): rewrite the row with (1+delta)/sigma, add the vertex score,
+// restore P for the level above.  centrality.rs:274-279 (coeff) and :281-298 (accumulation).
+template <bool EDGE, bool ENDPOINTS>
+__device__ __forceinline__ void bc_bwd_finish(const BcParams &p, uint32_t v, const Mask128 &fm,
+                                              const double (&sig)[BK], const double (&acc)[BK],
+                                              double *rows, PEntry *Pcur, uint32_t tag_cur,
+                                              uint32_t level, int lane) {
+    double contrib = 0.0;
+#pragma unroll
+    for (int k = 0; k < BK; k++) {
+        if ((fm.w[k] >> lane) & 1u) {
+            const double delta = EDGE ? acc[k] : sig[k] * acc[k];
+            rows[(size_t)v * BG + lane * BK + k] = (1.0 + delta) / sig[k];
+            if (!EDGE && level > 0) contrib += ENDPOINTS ? delta + 1.0 : delta;
+        }
+    }
+    if (!EDGE && level > 0) {
+        const double tot = warp_sum(contrib);
+        if (lane == 0) atomicAdd(&p.acc[v], tot);
+    }
+    if (lane == 0) bc_store_level(Pcur, v, tag_cur, fm);
 }
 
 // One level of the dependency sweep (deepest level first).  A warp owns one queue entry (v, fm):
-// delta[v][b] = sigma[v][b] * sum_{w in N+(v), depth_b(w) = level+1} (1+delta[w][b])/sigma[w][b]
+//   delta[v][b] = sigma[v][b] * sum_{w in N+(v), depth_b(w) = level+1} (1+delta[w][b])/sigma[w][b]
 // which regroups centrality.rs:272-279 by predecessor (pull instead of push; no f64 atomics on the
 // rows).  The row of v is then overwritten with (1+delta)/sigma for the level above to pull.
-//   node mode : acc[v] += sum_b delta[v][b] (+1 per reached source when endpoints), :281-298
-//   edge mode : acc[eid(v->w)] += sum_b sigma[v][b] * coef[w][b], :318-325
 template <bool EDGE, bool ENDPOINTS>
 __global__ void __launch_bounds__(BLOCK) bc_backward_kernel(BcParams p, uint32_t level) {
     const uint32_t g = blockIdx.y;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *bc_hubcnt(p, level + 1, g) = 0;  // for the next launch
     const uint32_t cnt = p.lvlcnt[(size_t)g * p.lcap + level];
     const uint32_t off = p.loff[(size_t)g * p.lcap + level];
     const int lane = lane_id();
     const size_t gn = (size_t)g * p.n;
-    const uint64_t *Pnext = bc_P(p, level + 1) + gn;
-    uint64_t *Pcur = bc_P(p, level) + gn;
-    double *rows = p.sc + gn * GW;
+    const PEntry *Pnext = bc_P(p, level + 1) + gn;
+    PEntry *Pcur = bc_P(p, level) + gn;
+    double *rows = p.sc + gn * BG;
     const uint32_t tag_cur = p.tagbase + level + 1, tag_next = tag_cur + 1;
     const uint32_t *qv = p.qv + (size_t)g * p.qcap + off;
-    const uint32_t *qm = p.qm + (size_t)g * p.qcap + off;
+    const Mask128 *qm = p.qm + (size_t)g * p.qcap + off;
 
-    unsigned long long te = 0, vv = 0, reach = 0;
-    unsigned long long dag = 0;
+    extern __shared__ __align__(16) double s_dyn_stage[];
+    double *stage = s_dyn_stage + (size_t)(threadIdx.x >> 5) * STAGE * BG;
+    unsigned long long te = 0, vv = 0, dag = 0;
+    unsigned long long reach[BK] = {0, 0, 0, 0};
     const uint32_t warp = blockIdx.x * WARPS + (threadIdx.x >> 5);
     for (uint32_t i = warp; i < cnt; i += gridDim.x * WARPS) {
-        const uint32_t v = qv[i], fm = qm[i];
+        const uint32_t v = qv[i];
+        const Mask128 fm = mask_load(&qm[i]);
         const uint32_t e0 = p.row[v], e1 = p.row[v + 1];
-        const bool mine = (fm >> lane) & 1u;
-        const double sig = mine ? rows[(size_t)v * GW + lane] : 0.0;
-        double acc = 0.0;
-        uint32_t seen = 0;
-        for (uint32_t e = e0; e < e1; e += 32) {
-            const uint32_t idx = e + lane;
-            uint32_t w = 0, m = 0, ed = 0;
-            if (idx < e1) {
-                w = p.col[idx];
-                const uint64_t pw = Pnext[w];
-                if ((uint32_t)(pw >> 32) == tag_next) m = (uint32_t)pw & fm;
-                if (EDGE && m) ed = p.eid[idx];
-            }
-            uint32_t nz = __ballot_sync(FULL, m != 0);
-            if (!EDGE) {
-                bc_gather(rows, w, m, nz, lane, acc, seen, dag);
-            } else {
-                while (nz) {
-                    const int j = __ffs(nz) - 1;
-                    nz &= nz - 1;
-                    const uint32_t wj = __shfl_sync(FULL, w, j);
-                    const uint32_t mj = __shfl_sync(FULL, m, j);
-                    const uint32_t ej = __shfl_sync(FULL, ed, j);
-                    const double coef = ((mj >> lane) & 1u) ? rows[(size_t)wj * GW + lane] : 0.0;
-                    const double c = sig * coef;  // sigma[v] * coeff, centrality.rs:322
-                    acc += c;
-                    dag += __popc(mj);
-                    const double tot = warp_sum(c);
-                    if (lane == 0) atomicAdd(&p.acc[ej], tot);
-                }
-            }
-        }
-        double contrib = 0.0;
-        if (mine) {
-            const double delta = EDGE ? acc : sig * acc;
-            rows[(size_t)v * GW + lane] = (1.0 + delta) / sig;
-            if (!EDGE && level > 0) contrib = ENDPOINTS ? delta + 1.0 : delta;
-        }
-        if (!EDGE && level > 0) {
-            const double tot = warp_sum(contrib);
-            if (lane == 0) atomicAdd(&p.acc[v], tot);
-        }
-        if (lane == 0) Pcur[v] = ((uint64_t)tag_cur << 32) | fm;
-        if (level > 0 && mine) reach++;
         if (lane == 0) {
-            te += (unsigned long long)__popc(fm) * (e1 - e0);
-            vv += __popc(fm);
+            te += (unsigned long long)mask_popc(fm) * (e1 - e0);
+            vv += mask_popc(fm);
         }
+        if (ENDPOINTS && level > 0) {
+#pragma unroll
+            for (int k = 0; k < BK; k++) reach[k] += (fm.w[k] >> lane) & 1u;
+        }
+        if (e1 - e0 > p.hub_degree && bc_defer_hub(p, level, g, v, fm)) continue;
+        const Row4 sg = row_load(rows, v, lane, (mask_or(fm) >> lane) & 1u);
+        double acc[BK] = {0.0, 0.0, 0.0, 0.0};
+        bc_bwd_scan<EDGE>(p, rows, Pnext, tag_next, e0, e1, 0, 32, fm, sg.x, lane, stage, acc, dag);
+        bc_bwd_finish<EDGE, ENDPOINTS>(p, v, fm, sg.x, acc, rows, Pcur, tag_cur, level, lane);
     }
-    if (ENDPOINTS && reach) atomicAdd(&p.reach[g * GW + lane], reach);
+    if (ENDPOINTS) {
+#pragma unroll
+        for (int k = 0; k < BK; k++)
+            if (reach[k]) atomicAdd(&p.reach[(size_t)g * BG + k * 32 + lane], reach[k]);
+    }
     if (lane == 0 && (te | vv | dag)) {  // dag is warp-uniform
         atomicAdd(&p.stats[ST_TE], te);
         atomicAdd(&p.stats[ST_V], vv);
-        atomicAdd(&p.stats[ST_DAG], (unsigned long long)dag);
+        atomicAdd(&p.stats[ST_DAG], dag);
+    }
+}
+
+// Deferred high-degree entries of a backward level: one CTA per entry, warps split the arcs.
+template <bool EDGE, bool ENDPOINTS>
+__global__ void __launch_bounds__(BLOCK) bc_backward_hub_kernel(BcParams p, uint32_t level) {
+    const uint32_t g = blockIdx.y;
+    const uint32_t nh = min(*bc_hubcnt(p, level, g), p.hubcap);
+    if (nh == 0) return;
+    const int tid = threadIdx.x, lane = lane_id(), wid = tid >> 5;
+    const size_t gn = (size_t)g * p.n;
+    const PEntry *Pnext = bc_P(p, level + 1) + gn;
+    PEntry *Pcur = bc_P(p, level) + gn;
+    double *rows = p.sc + gn * BG;
+    const uint32_t tag_cur = p.tagbase + level + 1, tag_next = tag_cur + 1;
+    __shared__ double s_acc[WARPS][BG];
+    __shared__ unsigned long long s_dag[WARPS];
+    extern __shared__ __align__(16) double s_dyn_stage[];
+    double *stage = s_dyn_stage + (size_t)(threadIdx.x >> 5) * STAGE * BG;
+
+    for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
+        const uint32_t v = p.hubv[(size_t)g * p.hubcap + h];
+        const Mask128 fm = mask_load(&p.hubm[(size_t)g * p.hubcap + h]);
+        const uint32_t e0 = p.row[v], e1 = p.row[v + 1];
+        const Row4 sg = row_load(rows, v, lane, (mask_or(fm) >> lane) & 1u);
+        double acc[BK] = {0.0, 0.0, 0.0, 0.0};
+        unsigned long long dag = 0;
+        bc_bwd_scan<EDGE>(p, rows, Pnext, tag_next, e0, e1, wid * 32, WARPS * 32, fm, sg.x, lane,
+                          stage, acc, dag);
+        __syncthreads();  // every warp has read row v before warp 0 rewrites it
+#pragma unroll
+        for (int k = 0; k < BK; k++) s_acc[wid][lane * BK + k] = acc[k];
+        if (lane == 0) s_dag[wid] = dag;
+        __syncthreads();
+        if (wid == 0) {
+            double tot[BK] = {0.0, 0.0, 0.0, 0.0};
+            unsigned long long d = 0;
+            for (int q = 0; q < WARPS; q++) {
+#pragma unroll
+                for (int k = 0; k < BK; k++) tot[k] += s_acc[q][lane * BK + k];
+                d += s_dag[q];
+            }
+            bc_bwd_finish<EDGE, ENDPOINTS>(p, v, fm, sg.x, tot, rows, Pcur, tag_cur, level, lane);
+            if (lane == 0 && d) atomicAdd(&p.stats[ST_DAG], d);
+        }
+        __syncthreads();
     }
 }
 
 // endpoints: the source itself receives |S| - 1 (centrality.rs:282-284)
 __global__ void __launch_bounds__(BLOCK) bc_endpoint_sources_kernel(BcParams p, uint32_t ngroups) {
     const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
-    if (i >= ngroups * GW) return;
+    if (i >= ngroups * BG) return;
     const uint32_t s = p.src[i];
     if (s != NO_SOURCE) atomicAdd(&p.acc[s], (double)p.reach[i]);
 }

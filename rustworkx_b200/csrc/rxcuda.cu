@@ -80,8 +80,11 @@ struct Options {
     int64_t bc_groups = 0;    // groups of 32 sources per betweenness batch (0 = auto)
     int64_t bfs_groups = 0;   // groups per closeness / distance batch (0 = auto)
     int64_t mem_fraction_pct = 70;
+    int64_t hub_degree = 2048;  // vertices above this degree get a whole CTA
 };
 static Options g_opt;
+constexpr uint32_t HUB_CAP = 4096;  // deferred high-degree work items per group and level
+constexpr uint32_t HUB_CTAS = 32;   // CTAs per group in the hub kernels
 static int g_device = 0;
 
 static double now_ms() {
@@ -93,8 +96,9 @@ static double now_ms() {
 // otherwise cost more than a batch of kernels).
 struct BcWorkspace {
     DevBuf<double> sc;
-    DevBuf<uint64_t> P0, P1;
-    DevBuf<uint32_t> visited, qv, qm, loff, lvlcnt, lvl_total, src;
+    DevBuf<PEntry> P0, P1;
+    DevBuf<Mask128> visited, qm, hubm;
+    DevBuf<uint32_t> qv, loff, lvlcnt, lvl_total, src, hubv, hubcnt;
     DevBuf<unsigned long long> reach;
     uint64_t ng = 0;        // capacity in groups
     uint32_t tagbase = 0;   // tags already used in P0/P1
@@ -102,6 +106,7 @@ struct BcWorkspace {
     void release() {
         sc.release(); P0.release(); P1.release(); visited.release(); qv.release(); qm.release();
         loff.release(); lvlcnt.release(); lvl_total.release(); src.release(); reach.release();
+        hubv.release(); hubm.release(); hubcnt.release();
         ng = 0;
     }
 };
@@ -268,28 +273,43 @@ static uint32_t run_levels(rxc_graph *g, uint32_t *d_lvl_total, uint32_t n, F &&
 // ------------------------------------------------------------------------------------------------
 // betweenness (node / edge)
 // ------------------------------------------------------------------------------------------------
+static void bc_enable_smem() {
+    static bool done = false;
+    if (done) return;
+    const int b = BC_SMEM_BYTES;
+    RXC_CUDA(cudaFuncSetAttribute(bc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    RXC_CUDA(cudaFuncSetAttribute(bc_forward_hub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    RXC_CUDA(cudaFuncSetAttribute(bc_backward_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    RXC_CUDA(cudaFuncSetAttribute(bc_backward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    RXC_CUDA(cudaFuncSetAttribute(bc_backward_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    RXC_CUDA(cudaFuncSetAttribute(bc_backward_hub_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    RXC_CUDA(cudaFuncSetAttribute(bc_backward_hub_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    RXC_CUDA(cudaFuncSetAttribute(bc_backward_hub_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    done = true;
+}
+
 static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endpoints,
                    bool edge_mode, double *d_acc) {
+    bc_enable_smem();
     const uint32_t n = g->host.n_live;
     if (sources.empty() || n == 0) return;
-    const uint64_t total_groups = (sources.size() + GW - 1) / GW;
+    const uint64_t total_groups = (sources.size() + BG - 1) / BG;
     const uint32_t lcap = n + 2;
-    const uint64_t qcap = (uint64_t)GW * n;
-    // bytes per group: sc row + worst-case queues + tagged masks + visited + level tables
-    const double per_group = (double)n * (256.0 + 256.0 + 16.0 + 4.0) + (double)lcap * 8.0 + 512.0;
+    const uint64_t qcap = (uint64_t)BG * n;  // worst case: a vertex sits on a different level per source
+    // bytes per group: 1 KB row + worst-case queues + two tagged mask arrays + visited + level tables
+    const double per_group = (double)n * (1024.0 + 20.0 * BG + 64.0 + 16.0) + (double)lcap * 8.0 + 4096.0;
     uint64_t ng = g_opt.bc_groups > 0 ? (uint64_t)g_opt.bc_groups
-                                      : std::max<uint64_t>(1, (8ull << 20) / std::max<uint32_t>(n, 1));
-    ng = std::min<uint64_t>(ng, 256);
+                                      : std::max<uint64_t>(1, (2ull << 20) / std::max<uint32_t>(n, 1));
+    ng = std::min<uint64_t>(ng, 64);
     ng = std::min<uint64_t>(ng, std::max<uint64_t>(1, (uint64_t)((double)device_budget() / per_group)));
     ng = std::min<uint64_t>(ng, total_groups);
-    ng = std::min<uint64_t>(ng, 65535);
 
     BcWorkspace &ws = g->bc_ws;
     cudaStream_t st = g->stream;
     if (ws.ng < ng) {
         ws.release();
         g->bfs_ws.release();  // one scratch set at a time keeps the footprint predictable
-        ws.sc.alloc((size_t)ng * n * GW);
+        ws.sc.alloc((size_t)ng * n * BG);
         ws.P0.alloc((size_t)ng * n);
         ws.P1.alloc((size_t)ng * n);
         ws.visited.alloc((size_t)ng * n);
@@ -298,8 +318,11 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
         ws.loff.alloc((size_t)ng * lcap);
         ws.lvlcnt.alloc((size_t)ng * lcap);
         ws.lvl_total.alloc(lcap);
-        ws.src.alloc((size_t)ng * GW);
-        ws.reach.alloc((size_t)ng * GW);
+        ws.src.alloc((size_t)ng * BG);
+        ws.reach.alloc((size_t)ng * BG);
+        ws.hubv.alloc((size_t)ng * HUB_CAP);
+        ws.hubm.alloc((size_t)ng * HUB_CAP);
+        ws.hubcnt.alloc((size_t)2 * ng);
         ws.ng = ng;
         ws.tagbase = 0;
         ws.dirty_levels = lcap;
@@ -321,20 +344,25 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
     p.stats = g->d_stats.p;
     p.acc = d_acc;
     p.src = ws.src.p;
+    p.hubv = ws.hubv.p;
+    p.hubm = ws.hubm.p;
+    p.hubcnt = ws.hubcnt.p;
+    p.hubcap = HUB_CAP;
+    p.hub_degree = (uint32_t)std::min<int64_t>(g_opt.hub_degree, 0x7FFFFFFF);
     p.qcap = qcap;
     p.n = n;
     p.lcap = lcap;
     uint32_t &tagbase = ws.tagbase;
 
-    std::vector<uint32_t> h_src((size_t)ng * GW), h_totals, h_lvlcnt;
+    std::vector<uint32_t> h_src((size_t)ng * BG), h_totals, h_lvlcnt;
     const uint32_t vblocks = (n + BLOCK - 1) / BLOCK;
     uint32_t &clear_levels = ws.dirty_levels;  // prefix of the level tables the previous batch dirtied
 
     for (uint64_t g0 = 0; g0 < total_groups; g0 += ng) {
         const uint32_t bg = (uint32_t)std::min<uint64_t>(ng, total_groups - g0);
         std::fill(h_src.begin(), h_src.end(), NO_SOURCE);
-        const size_t s0 = (size_t)g0 * GW;
-        const size_t cnt = std::min(sources.size() - s0, (size_t)bg * GW);
+        const size_t s0 = (size_t)g0 * BG;
+        const size_t cnt = std::min(sources.size() - s0, (size_t)bg * BG);
         std::copy(sources.begin() + s0, sources.begin() + s0 + cnt, h_src.begin());
         if ((uint64_t)tagbase + lcap + 16 > 0xFFFFFFF0ull) {
             RXC_CUDA(cudaMemsetAsync(ws.P0.p, 0, ws.P0.bytes(), st));
@@ -342,8 +370,9 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
             tagbase = 0;
         }
         p.tagbase = tagbase;
+        p.ngroups = bg;
         RXC_CUDA(cudaEventRecord(g->ev[0], st));
-        RXC_CUDA(cudaMemcpyAsync(ws.src.p, h_src.data(), (size_t)bg * GW * 4,
+        RXC_CUDA(cudaMemcpyAsync(ws.src.p, h_src.data(), (size_t)bg * BG * 4,
                                  cudaMemcpyHostToDevice, st));
         RXC_CUDA(cudaMemset2DAsync(ws.lvlcnt.p, (size_t)lcap * 4, 0, (size_t)clear_levels * 4, ws.ng, st));
         RXC_CUDA(cudaMemsetAsync(ws.lvl_total.p, 0, (size_t)clear_levels * 4, st));
@@ -359,13 +388,15 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
         const uint32_t L = run_levels(
             g, ws.lvl_total.p, n,
             [&](uint32_t level) {
-                bc_forward_kernel<<<dim3(vblocks, bg), BLOCK, 0, st>>>(p, level);
+                bc_forward_kernel<<<dim3(vblocks, bg), BLOCK, BC_SMEM_BYTES, st>>>(p, level);
+                bc_forward_hub_kernel<<<dim3(HUB_CTAS, bg), BLOCK, BC_SMEM_BYTES, st>>>(p, level);
                 launched_levels++;
             },
             h_totals);
-        g->stats.launches += launched_levels;
+        g->stats.launches += 2 * launched_levels;
         g->stats.levels += L;
         clear_levels = std::min<uint32_t>(lcap, launched_levels + 2);
+        RXC_CUDA(cudaMemsetAsync(ws.hubcnt.p, 0, ws.hubcnt.bytes(), st));
         RXC_CUDA(cudaEventRecord(g->ev[1], st));
 
         // backward: out-arcs (pull from successors), deepest level first
@@ -383,17 +414,21 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
                 maxcnt = std::max(maxcnt, h_lvlcnt[(size_t)gi * L + l]);
             if (maxcnt == 0) continue;
             const uint32_t gx = std::min<uint32_t>((maxcnt + WARPS - 1) / WARPS, 16384);
-            const dim3 grid(gx, bg);
-            if (edge_mode)
-                bc_backward_kernel<true, false><<<grid, BLOCK, 0, st>>>(p, l);
-            else if (endpoints)
-                bc_backward_kernel<false, true><<<grid, BLOCK, 0, st>>>(p, l);
-            else
-                bc_backward_kernel<false, false><<<grid, BLOCK, 0, st>>>(p, l);
-            g->stats.launches++;
+            const dim3 grid(gx, bg), hgrid(HUB_CTAS, bg);
+            if (edge_mode) {
+                bc_backward_kernel<true, false><<<grid, BLOCK, BC_SMEM_BYTES, st>>>(p, l);
+                bc_backward_hub_kernel<true, false><<<hgrid, BLOCK, BC_SMEM_BYTES, st>>>(p, l);
+            } else if (endpoints) {
+                bc_backward_kernel<false, true><<<grid, BLOCK, BC_SMEM_BYTES, st>>>(p, l);
+                bc_backward_hub_kernel<false, true><<<hgrid, BLOCK, BC_SMEM_BYTES, st>>>(p, l);
+            } else {
+                bc_backward_kernel<false, false><<<grid, BLOCK, BC_SMEM_BYTES, st>>>(p, l);
+                bc_backward_hub_kernel<false, false><<<hgrid, BLOCK, BC_SMEM_BYTES, st>>>(p, l);
+            }
+            g->stats.launches += 2;
         }
         if (endpoints && !edge_mode) {
-            bc_endpoint_sources_kernel<<<(bg * GW + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(p, bg);
+            bc_endpoint_sources_kernel<<<(bg * BG + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(p, bg);
             g->stats.launches++;
         }
         RXC_CUDA(cudaEventRecord(g->ev[2], st));
@@ -799,6 +834,7 @@ int rxc_set_option(const char *name, int64_t value) {
     const std::string k(name);
     if (k == "bc_groups") g_opt.bc_groups = value;
     else if (k == "bfs_groups") g_opt.bfs_groups = value;
+    else if (k == "hub_degree" && value > 0) g_opt.hub_degree = value;
     else if (k == "mem_fraction_pct" && value > 0 && value <= 95) g_opt.mem_fraction_pct = value;
     else {
         set_error("unknown option: " + k);
