@@ -193,4 +193,136 @@ __global__ void __launch_bounds__(BLOCK)
     out[i] = c;
 }
 
+
+
+// ================================================================================================
+// One CTA per source with the visited bitmap in shared memory -- the high-diameter regime.
+//
+// On lattices and other long, thin graphs (grid 1000x1000: 1998 levels, heavy-hex: ~200) the
+// frontiers of different sources never coincide, so bit-parallel words hold one or two sources and
+// every level launch touches gigabytes of per-group state for a few thousand vertices.  Here a
+// source's whole BFS stays on one SM: the visited bitmap (n/8 bytes; 125 KB at n = 10^6) and the
+// first QS entries of both frontier queues live in shared memory, only the CSR is read from
+// L2/HBM, and a level costs two __syncthreads instead of a kernel launch.  CTAs are persistent and
+// take sources from a global counter.
+// ================================================================================================
+constexpr uint32_t SB_QS = 8192;  // most frontier entries kept in shared memory per queue
+
+struct SmemBfsParams {
+    const uint32_t *row;
+    const uint32_t *col;
+    const uint32_t *sources;       // compact ids
+    uint32_t *qspill;              // [gridDim.x][2][n] queue entries beyond SB_QS
+    uint32_t *next_source;         // dynamic source counter
+    unsigned long long *reach;     // [nsrc]
+    unsigned long long *dsum;      // [nsrc]
+    uint32_t *depth;               // [nsrc] number of BFS levels of each source, or nullptr
+    unsigned long long *stats;
+    double *rows;                  // [nsrc][n_cols] or nullptr
+    uint64_t n_cols;
+    uint32_t n;
+    uint32_t nsrc;
+    uint32_t words;                // ceil(n / 32)
+    uint32_t qs;                   // frontier entries per queue held in shared memory (<= SB_QS)
+};
+
+template <bool ROWS>
+__global__ void __launch_bounds__(1024, 1) bfs_smem_kernel(SmemBfsParams p) {
+    extern __shared__ uint32_t sb_smem[];
+    uint32_t *vis = sb_smem;
+    uint32_t *q0 = vis + p.words;
+    uint32_t *q1 = q0 + p.qs;
+    __shared__ uint32_t s_src, s_tail[2];
+    __shared__ unsigned long long s_te;
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+    uint32_t *spill0 = p.qspill + (size_t)blockIdx.x * 2 * p.n;
+    uint32_t *spill1 = spill0 + p.n;
+
+    for (;;) {
+        if (tid == 0) {
+            s_src = atomicAdd(p.next_source, 1u);
+            s_tail[0] = 0;
+            s_tail[1] = 0;
+            s_te = 0;
+        }
+        __syncthreads();
+        const uint32_t si = s_src;
+        if (si >= p.nsrc) break;
+        const uint32_t s = p.sources[si];
+        for (uint32_t i = tid; i < p.words; i += nthr) vis[i] = 0;
+        __syncthreads();
+        if (tid == 0) {
+            vis[s >> 5] = 1u << (s & 31);
+            q0[0] = s;
+        }
+        __syncthreads();
+        uint32_t size = 1, level = 0;
+        unsigned long long reach = 0, dsum = 0, te = 0;
+        uint32_t *qc = q0, *qn = q1, *sc = spill0, *sn = spill1;
+        while (size) {
+            reach += size;
+            dsum += (unsigned long long)size * level;
+            for (uint32_t i = tid; i < size; i += nthr) {
+                const uint32_t v = (i < p.qs) ? qc[i] : sc[i];
+                if (ROWS) p.rows[(size_t)si * p.n_cols + v] = (double)level;
+                const uint32_t e0 = p.row[v], e1 = p.row[v + 1];
+                te += e1 - e0;
+                for (uint32_t e = e0; e < e1; e += 4) {
+                    // four independent target loads in flight before any is used
+                    uint32_t w[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) w[u] = (e + u < e1) ? p.col[e + u] : 0xFFFFFFFFu;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (w[u] == 0xFFFFFFFFu) continue;
+                        const uint32_t bit = 1u << (w[u] & 31);
+                        if (!(vis[w[u] >> 5] & bit)) {
+                            const uint32_t old = atomicOr(&vis[w[u] >> 5], bit);
+                            if (!(old & bit)) {
+                                const uint32_t pos = atomicAdd(&s_tail[level & 1], 1u);
+                                if (pos < p.qs) qn[pos] = w[u];
+                                else sn[pos] = w[u];
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            size = s_tail[level & 1];
+            if (tid == 0) s_tail[(level + 1) & 1] = 0;  // the counter the next level appends to
+            __syncthreads();
+            uint32_t *t = qc; qc = qn; qn = t;
+            t = sc; sc = sn; sn = t;
+            level++;
+        }
+        if (te) atomicAdd(&s_te, te);
+        __syncthreads();
+        if (tid == 0) {
+            p.reach[si] = reach;
+            p.dsum[si] = dsum;
+            if (p.depth) p.depth[si] = level;
+            atomicAdd(&p.stats[ST_TE], s_te);
+            atomicAdd(&p.stats[ST_V], reach);
+        }
+    }
+}
+
+// closeness_finalize for the CTA-per-source path (no NO_SOURCE padding)
+__global__ void __launch_bounds__(BLOCK)
+    closeness_finalize_flat_kernel(const unsigned long long *reach, const unsigned long long *dsum,
+                                   uint32_t nsrc, int wf_improved, unsigned long long node_count,
+                                   double *out) {
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= nsrc) return;
+    const unsigned long long r = reach[i];
+    double c = 0.0;
+    if (r != 1) {
+        c = __ddiv_rn((double)(r - 1), (double)dsum[i]);
+        if (wf_improved) {
+            c = __dmul_rn(c, (double)(r - 1));
+            c = __ddiv_rn(c, (double)(node_count - 1));
+        }
+    }
+    out[i] = c;
+}
 }  // namespace rxc

@@ -80,7 +80,9 @@ struct Options {
     int64_t bc_groups = 0;    // groups of 32 sources per betweenness batch (0 = auto)
     int64_t bfs_groups = 0;   // groups per closeness / distance batch (0 = auto)
     int64_t mem_fraction_pct = 70;
-    int64_t hub_degree = 2048;  // vertices above this degree get a whole CTA
+    int64_t hub_degree = 512;    // vertices above this degree get a whole CTA
+    int64_t bfs_mode = 0;        // 0 auto, 1 bit-parallel level launches, 2 CTA-per-source in smem
+    int64_t bfs_depth_switch = 48;  // auto: pilot BFS deeper than this many levels -> mode 2
 };
 static Options g_opt;
 constexpr uint32_t HUB_CAP = 4096;  // deferred high-degree work items per group and level
@@ -139,6 +141,7 @@ struct rxc_graph {
     DevBuf<unsigned long long> d_stats;
     rxc_stats stats;
     double ms_snapshot = 0.0;
+    uint64_t last_bfs_entries = 0;  // queue entries of the bit-parallel batches of this call
     BcWorkspace bc_ws;
     BfsWorkspace bfs_ws;
     std::mutex mu;
@@ -206,6 +209,7 @@ static void reset_stats(rxc_graph *g) {
 
 static void begin_call(rxc_graph *g) {
     RXC_CUDA(cudaSetDevice(g->device));
+    g->last_bfs_entries = 0;
     reset_stats(g);
     RXC_CUDA(cudaEventRecord(g->ev[4], g->stream));
 }
@@ -603,6 +607,7 @@ static void bfs_run(rxc_graph *g, const DeviceCSR &csr, const std::vector<uint32
             h_totals);
         g->stats.launches += launched_levels;
         g->stats.levels += L;
+        for (uint32_t l = 0; l < L && l < h_totals.size(); l++) g->last_bfs_entries += h_totals[l];
         clear_levels = std::min<uint32_t>(lcap, launched_levels + 2);
         if (!rows_mode) {
             closeness_finalize_kernel<<<(bg * GW + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(
@@ -629,6 +634,149 @@ static void bfs_run(rxc_graph *g, const DeviceCSR &csr, const std::vector<uint32
         g->stats.batches++;
         g->stats.sources += cnt;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-per-source BFS with the visited bitmap in shared memory (high-diameter graphs)
+// ------------------------------------------------------------------------------------------------
+static bool smem_bfs_fits(uint32_t n, uint32_t *qs_out, size_t *bytes_out) {
+    const uint32_t words = (n + 31) / 32;
+    const uint32_t qs = std::min<uint32_t>(SB_QS, ((n + 31) / 32) * 32);
+    const size_t bytes = ((size_t)words + 2 * (size_t)qs) * 4;
+    if (qs_out) *qs_out = qs;
+    if (bytes_out) *bytes_out = bytes;
+    return bytes <= 200 * 1024;
+}
+
+static void bfs_smem_run(rxc_graph *g, const DeviceCSR &csr, const uint32_t *sources, size_t k,
+                         BfsMode mode, bool wf_improved, double null_value, double *out,
+                         uint32_t *max_depth_out = nullptr) {
+    const uint32_t n = g->host.n_live;
+    if (k == 0 || n == 0) return;
+    const bool rows_mode = mode == BfsMode::Rows;
+    uint32_t qs = 0;
+    size_t smem = 0;
+    smem_bfs_fits(n, &qs, &smem);
+    static bool attr_done = false;
+    if (!attr_done) {
+        RXC_CUDA(cudaFuncSetAttribute(bfs_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        RXC_CUDA(cudaFuncSetAttribute(bfs_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done = true;
+    }
+    const int threads = n >= (1u << 18) ? 1024 : 256;
+    int per_sm = 1, sms = 148;
+    RXC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device));
+    if (rows_mode)
+        RXC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_smem_kernel<true>, threads, smem));
+    else
+        RXC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_smem_kernel<false>, threads, smem));
+    per_sm = std::max(per_sm, 1);
+    cudaStream_t st = g->stream;
+
+    // rows mode: keep one batch of rows under 8 GiB
+    size_t batch = k;
+    if (rows_mode) batch = std::max<size_t>(1, std::min<size_t>(k, (8ull << 30) / ((size_t)n * 8)));
+    const uint32_t grid = (uint32_t)std::min<size_t>(batch, (size_t)sms * per_sm);
+    DevBuf<uint32_t> d_src, d_spill, d_counter;
+    DevBuf<unsigned long long> d_reach, d_dsum;
+    DevBuf<double> d_vals, d_rows;
+    DevBuf<uint32_t> d_depth;
+    if (max_depth_out) d_depth.alloc(batch);
+    d_src.alloc(batch);
+    d_spill.alloc((size_t)grid * 2 * n);
+    d_counter.alloc(1);
+    d_reach.alloc(batch);
+    d_dsum.alloc(batch);
+    if (rows_mode) d_rows.alloc(batch * n);
+    else d_vals.alloc(batch);
+
+    SmemBfsParams p{};
+    p.row = csr.row.p;
+    p.col = csr.col.p;
+    p.sources = d_src.p;
+    p.qspill = d_spill.p;
+    p.next_source = d_counter.p;
+    p.reach = d_reach.p;
+    p.dsum = d_dsum.p;
+    p.depth = max_depth_out ? d_depth.p : nullptr;
+    p.stats = g->d_stats.p;
+    p.rows = rows_mode ? d_rows.p : nullptr;
+    p.n_cols = n;
+    p.n = n;
+    p.words = (n + 31) / 32;
+    p.qs = qs;
+    std::vector<double> h_vals(rows_mode ? 0 : batch);
+    for (size_t s0 = 0; s0 < k; s0 += batch) {
+        const size_t cnt = std::min(batch, k - s0);
+        p.nsrc = (uint32_t)cnt;
+        RXC_CUDA(cudaEventRecord(g->ev[0], st));
+        RXC_CUDA(cudaMemcpyAsync(d_src.p, sources + s0, cnt * 4, cudaMemcpyHostToDevice, st));
+        RXC_CUDA(cudaMemsetAsync(d_counter.p, 0, 4, st));
+        if (rows_mode) {
+            const uint64_t len = (uint64_t)cnt * n;
+            const uint32_t fb = (uint32_t)std::min<uint64_t>((len + BLOCK - 1) / BLOCK, 148 * 16);
+            bfs_fill_f64_kernel<<<fb, BLOCK, 0, st>>>(d_rows.p, len, null_value);
+            bfs_smem_kernel<true><<<grid, threads, smem, st>>>(p);
+            g->stats.launches += 2;
+        } else {
+            bfs_smem_kernel<false><<<grid, threads, smem, st>>>(p);
+            closeness_finalize_flat_kernel<<<((uint32_t)cnt + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(
+                d_reach.p, d_dsum.p, (uint32_t)cnt, wf_improved ? 1 : 0, (unsigned long long)n,
+                d_vals.p);
+            g->stats.launches += 2;
+        }
+        RXC_CUDA(cudaEventRecord(g->ev[1], st));
+        const double t0 = now_ms();
+        if (rows_mode)
+            RXC_CUDA(cudaMemcpyAsync(out + s0 * n, d_rows.p, cnt * (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        else
+            RXC_CUDA(cudaMemcpyAsync(h_vals.data(), d_vals.p, cnt * 8, cudaMemcpyDeviceToHost, st));
+        RXC_CUDA(cudaStreamSynchronize(st));
+        RXC_CUDA(cudaGetLastError());
+        if (!rows_mode) std::copy(h_vals.begin(), h_vals.begin() + cnt, out + s0);
+        if (max_depth_out) {
+            std::vector<uint32_t> h_depth(cnt);
+            RXC_CUDA(cudaMemcpy(h_depth.data(), d_depth.p, cnt * 4, cudaMemcpyDeviceToHost));
+            for (uint32_t d : h_depth) *max_depth_out = std::max(*max_depth_out, d);
+        }
+        g->stats.ms_d2h += now_ms() - t0;
+        float f = 0.f;
+        RXC_CUDA(cudaEventElapsedTime(&f, g->ev[0], g->ev[1]));
+        g->stats.ms_forward += f;
+        g->stats.batches++;
+        g->stats.sources += cnt;
+    }
+}
+
+// Pick the regime.  Bit-parallel words pay off when the frontiers of different sources coincide
+// (small-world graphs: a handful of levels); on lattices and other long, thin graphs every word
+// carries one or two sources and a level launch per BFS level is pure overhead.  A pilot of up to
+// eight sources spread over the list runs CTA-per-source (cheap: one CTA each) and reports its BFS
+// depth; deep graphs stay in that regime, shallow ones go bit-parallel.
+static void bfs_dispatch(rxc_graph *g, const DeviceCSR &csr, const std::vector<uint32_t> &sources,
+                         BfsMode mode, bool wf_improved, double null_value, double *out) {
+    const uint32_t n = g->host.n_live;
+    if (sources.empty() || n == 0) return;
+    const size_t stride = mode == BfsMode::Rows ? (size_t)n : 1;
+    const bool fits = smem_bfs_fits(n, nullptr, nullptr);
+    int64_t regime = g_opt.bfs_mode;  // 0 auto, 1 bit-parallel, 2 CTA-per-source
+    if (!fits) regime = 1;
+    if (regime == 0) {
+        const size_t k = sources.size(), np = std::min<size_t>(8, k);
+        std::vector<uint32_t> pilot(np);
+        for (size_t i = 0; i < np; i++) pilot[i] = sources[i * k / np];
+        std::vector<double> scratch(np * stride);
+        uint32_t depth = 0;
+        bfs_smem_run(g, csr, pilot.data(), np, mode, wf_improved, null_value, scratch.data(), &depth);
+        // the pilot's work is redone below with everything else: keep the counters exact
+        RXC_CUDA(cudaMemsetAsync(g->d_stats.p, 0, g->d_stats.bytes(), g->stream));
+        g->stats.sources -= np;
+        regime = depth > (uint32_t)g_opt.bfs_depth_switch ? 2 : 1;
+    }
+    if (regime == 2)
+        bfs_smem_run(g, csr, sources.data(), sources.size(), mode, wf_improved, null_value, out);
+    else
+        bfs_run(g, csr, sources, mode, wf_improved, null_value, out);
 }
 
 static const DeviceCSR &symmetric_csr(rxc_graph *g) {
@@ -779,8 +927,8 @@ int rxc_closeness_partial(rxc_graph *g, const uint32_t *sources, uint64_t n_sour
         std::lock_guard<std::mutex> lock(g->mu);
         begin_call(g);
         // closeness follows incoming edges: BFS over Reversed(&graph), centrality.rs:1208
-        bfs_run(g, g->pred(), to_compact(g, sources, n_sources), BfsMode::Closeness,
-                wf_improved != 0, 0.0, out);
+        bfs_dispatch(g, g->pred(), to_compact(g, sources, n_sources), BfsMode::Closeness,
+                     wf_improved != 0, 0.0, out);
         end_call(g);
         fetch_stats(g);
     });
@@ -793,7 +941,7 @@ int rxc_closeness(rxc_graph *g, int wf_improved, double *out) {
         begin_call(g);
         std::fill(out, out + g->host.n_bound, 0.0);
         std::vector<double> vals(g->host.n_live);
-        bfs_run(g, g->pred(), all_sources(g), BfsMode::Closeness, wf_improved != 0, 0.0, vals.data());
+        bfs_dispatch(g, g->pred(), all_sources(g), BfsMode::Closeness, wf_improved != 0, 0.0, vals.data());
         end_call(g);
         for (uint32_t i = 0; i < g->host.n_live; i++) out[g->host.orig_of_compact[i]] = vals[i];
         fetch_stats(g);
@@ -812,7 +960,7 @@ int rxc_distance_matrix_rows(rxc_graph *g, int as_undirected, double null_value,
         for (uint32_t i = row_begin; i < row_end; i++) src[i - row_begin] = i;
         // graph_distance_matrix always passes as_undirected=true (src/shortest_path/mod.rs:1610)
         const DeviceCSR &csr = (as_undirected || !g->host.directed) ? symmetric_csr(g) : g->out;
-        bfs_run(g, csr, src, BfsMode::Rows, false, null_value, out);
+        bfs_dispatch(g, csr, src, BfsMode::Rows, false, null_value, out);
         end_call(g);
         fetch_stats(g);
     });
@@ -835,6 +983,8 @@ int rxc_set_option(const char *name, int64_t value) {
     if (k == "bc_groups") g_opt.bc_groups = value;
     else if (k == "bfs_groups") g_opt.bfs_groups = value;
     else if (k == "hub_degree" && value > 0) g_opt.hub_degree = value;
+    else if (k == "bfs_mode" && value >= 0 && value <= 2) g_opt.bfs_mode = value;
+    else if (k == "bfs_depth_switch" && value >= 0) g_opt.bfs_depth_switch = value;
     else if (k == "mem_fraction_pct" && value > 0 && value <= 95) g_opt.mem_fraction_pct = value;
     else {
         set_error("unknown option: " + k);

@@ -398,3 +398,31 @@ def test_networkx_golden_fixture(rx):
         else:
             dm = rx.graph_distance_matrix(g, null_value=-1.0)
         assert np.array_equal(dm, np.array(case["distance_matrix"]))
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_distance_regimes_agree_with_oracle(rx, oracle, mode):
+    """Both distance-only regimes (bit-parallel level launches, CTA-per-source in shared memory) are
+    forced in turn and must be bit-exact; auto mode picks between them with a pilot group."""
+    from rustworkx_b200 import _lib
+
+    _lib.set_option("bfs_mode", mode)
+    try:
+        for g in (rx.generators.grid_graph(37, 23), rx.generators.heavy_hex_graph(7),
+                  random_graph(rx, True, 500, 1500, 11, holes=10),
+                  random_graph(rx, False, 700, 900, 12, holes=5)):
+            og = oracle_graph(oracle, g)
+            nb, _ = g._bounds()
+            for wf in (True, False):
+                want, present = og.closeness_centrality(wf, 1 << 30, as_arrays=True)
+                gd, gp = dense_from_mapping(rx.closeness_centrality(g, wf_improved=wf), nb)
+                assert np.array_equal(gd, want) and np.array_equal(gp, present.astype(bool))
+            if isinstance(g, rx.PyDiGraph):
+                for und in (False, True):
+                    assert np.array_equal(rx.digraph_distance_matrix(g, as_undirected=und, null_value=-1.0),
+                                          og.distance_matrix(300, und, -1.0))
+            else:
+                assert np.array_equal(rx.graph_distance_matrix(g, null_value=math.nan),
+                                      og.distance_matrix(300, True, math.nan), equal_nan=True)
+    finally:
+        _lib.set_option("bfs_mode", 0)
