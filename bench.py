@@ -15,7 +15,7 @@ accumulates a partial vector, and ONE NCCL reduce at the end of the timed region
                library's own stream, max over ranks).  TE = (source, arc) pairs traversed, counted
                once per source although Brandes sweeps each twice.
 * ``e2e``    : the same metric through the C-ABI with HOST buffers: every step re-snapshots the graph
-               from host edge arrays (host CSR build + H2D), runs the step and reads the partial
+               from host edge arrays (H2D + device CSR build), runs the step and reads the partial
                vector back (D2H); wall clock around the calls.
 * ``roofline``: algorithmic bytes of the dominant kernel / its CUDA-event time, against the measured
                HBM copy peak in MEASURED_PEAKS.json.
@@ -300,11 +300,10 @@ def run_b200(args):
             tc = torch.tensor([float(te_e2e)], dtype=torch.float64, device="cuda")
             dist.all_reduce(tc, op=dist.ReduceOp.SUM)
             te_e2e = tc.item()
-        n_arcs = 2 * graph.num_edges()
-        h2d = 4 * (n + 1) + 8 * n_arcs + 4 * S  # row_ptr + col + eid, + the step's sources
+        h2d = 4 * n + 12 * graph.num_edges() + 4 * S  # live nodes + (src, dst, id) per edge + sources
         e2e = {"value": te_e2e / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(8 * n), "steps": e2e_steps,
-               "includes": "host CSR build + H2D snapshot + kernels + D2H partial vector"}
+               "includes": "H2D of the edge list + device CSR build + kernels + D2H partial vector"}
 
     if rank != 0:
         if dist is not None:

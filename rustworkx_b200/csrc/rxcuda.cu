@@ -20,6 +20,7 @@
 #include "bc_kernels.cuh"
 #include "bfs_kernels.cuh"
 #include "common.cuh"
+#include "csr_build.cuh"
 #include "snapshot.hpp"
 
 namespace rxc {
@@ -82,6 +83,7 @@ struct Options {
     int64_t mem_fraction_pct = 70;
     int64_t hub_degree = 512;    // vertices above this degree get a whole CTA
     int64_t bfs_mode = 0;        // 0 auto, 1 bit-parallel level launches, 2 CTA-per-source in smem
+    int64_t device_csr = 1;      // build the CSR on the device (0: host counting sort)
     int64_t bfs_depth_switch = 48;  // auto: pilot BFS deeper than this many levels -> mode 2
 };
 static Options g_opt;
@@ -138,6 +140,8 @@ struct rxc_graph {
     HostSnapshot host;
     DeviceCSR out, in, sym;
     bool has_sym = false;
+    DevBuf<uint32_t> d_esrc, d_edst;  // compact endpoints of every edge (device build; directed only)
+    uint64_t n_arcs = 0;
     DevBuf<unsigned long long> d_stats;
     rxc_stats stats;
     double ms_snapshot = 0.0;
@@ -199,6 +203,141 @@ static size_t device_budget() {
     size_t free_b = 0, total_b = 0;
     RXC_CUDA(cudaMemGetInfo(&free_b, &total_b));
     return (size_t)((double)free_b * (double)g_opt.mem_fraction_pct / 100.0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// device CSR build (csr_build.cuh)
+// ------------------------------------------------------------------------------------------------
+static void device_scan(const uint32_t *in, uint32_t *out_row, uint32_t n, DevBuf<uint32_t> &tiles,
+                        uint32_t *d_total, cudaStream_t st) {
+    const uint32_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (tiles.n < ntiles + 1) tiles.alloc(ntiles + 1);
+    scan_tile_kernel<<<std::max(ntiles, 1u), BLOCK, 0, st>>>(in, out_row, n, tiles.p);
+    scan_sums_kernel<<<1, BLOCK, 0, st>>>(tiles.p, ntiles, d_total);
+    scan_add_kernel<<<std::max(ntiles, 1u), BLOCK, 0, st>>>(out_row, n, tiles.p, d_total);
+}
+
+static void device_sort_rows(DeviceCSR &csr, uint32_t n, DevBuf<uint32_t> &long_rows,
+                             uint32_t *d_nlong, cudaStream_t st) {
+    if (n == 0 || !csr.eid.p) return;
+    static bool attr_done = false;
+    if (!attr_done) {
+        RXC_CUDA(cudaFuncSetAttribute(csr_sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(CSR_SORT_MAX * 8)));
+        attr_done = true;
+    }
+    RXC_CUDA(cudaMemsetAsync(d_nlong, 0, 4, st));
+    csr_sort_rows_kernel<<<(n + WARPS - 1) / WARPS, BLOCK, 0, st>>>(csr.row.p, n, csr.col.p, csr.eid.p,
+                                                                   long_rows.p, d_nlong);
+    csr_sort_long_kernel<<<296, BLOCK, CSR_SORT_MAX * 8, st>>>(csr.row.p, long_rows.p, d_nlong,
+                                                              csr.col.p, csr.eid.p);
+}
+
+// mode 0 successors, 1 predecessors, 2 both directions in one structure
+static void device_build_csr(DeviceCSR &csr, uint32_t n, const uint32_t *d_src, const uint32_t *d_dst,
+                             const uint32_t *d_eid, uint64_t n_edges, int mode,
+                             const uint32_t *d_deg, DevBuf<uint32_t> &cursor, DevBuf<uint32_t> &tiles,
+                             uint32_t *d_total, cudaStream_t st) {
+    const uint64_t cap = mode == 2 ? 2 * n_edges : n_edges;
+    csr.row.alloc((size_t)n + 1);
+    csr.col.alloc(cap ? cap : 1);
+    if (d_eid) csr.eid.alloc(cap ? cap : 1);
+    device_scan(d_deg, csr.row.p, n, tiles, d_total, st);
+    RXC_CUDA(cudaMemsetAsync(cursor.p, 0, ((size_t)n + 1) * 4, st));
+    if (n_edges) {
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_edges + BLOCK - 1) / BLOCK, 148 * 32);
+        csr_scatter_kernel<<<blocks, BLOCK, 0, st>>>(d_src, d_dst, d_eid, n_edges, mode, csr.row.p,
+                                                     cursor.p, csr.col.p, d_eid ? csr.eid.p : nullptr);
+    }
+}
+
+static void device_snapshot(rxc_graph *g, uint32_t n_bound, const uint32_t *live_nodes,
+                            uint32_t n_live, uint32_t e_bound, const uint32_t *esrc,
+                            const uint32_t *edst, const uint32_t *eid, uint64_t n_edges,
+                            bool directed) {
+    HostSnapshot &h = g->host;
+    h.n_bound = n_bound;
+    h.n_live = n_live;
+    h.e_bound = e_bound;
+    h.n_edges = n_edges;
+    h.directed = directed;
+    h.orig_of_compact.assign(live_nodes, live_nodes + n_live);
+    h.compact_of_orig.assign(n_bound, 0xFFFFFFFFu);
+    for (uint32_t i = 0; i < n_live; i++) {
+        const uint32_t o = live_nodes[i];
+        if (o >= n_bound) throw std::invalid_argument("live node index >= n_bound");
+        if (i > 0 && live_nodes[i - 1] >= o)
+            throw std::invalid_argument("live_nodes must be strictly ascending");
+        h.compact_of_orig[o] = i;
+    }
+    if ((directed ? n_edges : 2 * n_edges) >= 0xFFFFFFFFull)
+        throw LimitError("more than 2^32-2 arcs are not supported");
+    cudaStream_t st = g->stream;
+    const uint32_t n = n_live;
+    DevBuf<uint32_t> d_live, d_cmap, d_eid, d_deg_a, d_deg_b, cursor, tiles, d_small, long_rows;
+    DevBuf<uint32_t> &d_src = g->d_esrc, &d_dst = g->d_edst;
+    d_live.alloc(std::max<uint32_t>(n_live, 1));
+    d_cmap.alloc(std::max<uint32_t>(n_bound, 1));
+    d_src.alloc(std::max<uint64_t>(n_edges, 1));
+    d_dst.alloc(std::max<uint64_t>(n_edges, 1));
+    d_eid.alloc(std::max<uint64_t>(n_edges, 1));
+    d_deg_a.alloc((size_t)n + 1);
+    if (directed) d_deg_b.alloc((size_t)n + 1);
+    cursor.alloc((size_t)n + 1);
+    long_rows.alloc(std::max<uint32_t>(n, 1));
+    d_small.alloc(4);  // [0] error flags, [1] scan total, [2] long-row count
+    RXC_CUDA(cudaMemsetAsync(d_small.p, 0, 16, st));
+    if (n_live) RXC_CUDA(cudaMemcpyAsync(d_live.p, live_nodes, (size_t)n_live * 4, cudaMemcpyHostToDevice, st));
+    if (n_edges) {
+        RXC_CUDA(cudaMemcpyAsync(d_src.p, esrc, n_edges * 4, cudaMemcpyHostToDevice, st));
+        RXC_CUDA(cudaMemcpyAsync(d_dst.p, edst, n_edges * 4, cudaMemcpyHostToDevice, st));
+        if (eid) {
+            RXC_CUDA(cudaMemcpyAsync(d_eid.p, eid, n_edges * 4, cudaMemcpyHostToDevice, st));
+        } else {  // edge ids default to the position in the list
+            std::vector<uint32_t> iota(n_edges);
+            for (uint64_t i = 0; i < n_edges; i++) iota[i] = (uint32_t)i;
+            RXC_CUDA(cudaMemcpyAsync(d_eid.p, iota.data(), n_edges * 4, cudaMemcpyHostToDevice, st));
+            RXC_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+    RXC_CUDA(cudaMemsetAsync(d_cmap.p, 0xFF, d_cmap.bytes(), st));
+    RXC_CUDA(cudaMemsetAsync(d_deg_a.p, 0, d_deg_a.bytes(), st));
+    if (directed) RXC_CUDA(cudaMemsetAsync(d_deg_b.p, 0, d_deg_b.bytes(), st));
+    if (n_live)
+        csr_map_kernel<<<(n_live + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(d_live.p, n_live, n_bound, d_cmap.p, d_small.p);
+    const uint32_t *d_eid_p = d_eid.p;
+    if (n_edges) {
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_edges + BLOCK - 1) / BLOCK, 148 * 32);
+        csr_count_kernel<<<blocks, BLOCK, 0, st>>>(d_src.p, d_dst.p, d_eid_p, n_edges, d_cmap.p, n_bound,
+                                                   e_bound, d_deg_a.p, directed ? d_deg_b.p : d_deg_a.p,
+                                                   d_small.p);
+    }
+    if (directed) {
+        device_build_csr(g->out, n, d_src.p, d_dst.p, d_eid_p, n_edges, 0, d_deg_a.p,
+                         cursor, tiles, d_small.p + 1, st);
+        device_build_csr(g->in, n, d_src.p, d_dst.p, d_eid_p, n_edges, 1, d_deg_b.p,
+                         cursor, tiles, d_small.p + 1, st);
+    } else {
+        device_build_csr(g->out, n, d_src.p, d_dst.p, d_eid_p, n_edges, 2, d_deg_a.p,
+                         cursor, tiles, d_small.p + 1, st);
+    }
+    device_sort_rows(g->out, n, long_rows, d_small.p + 2, st);
+    if (directed) device_sort_rows(g->in, n, long_rows, d_small.p + 2, st);
+    uint32_t h_err = 0, h_arcs = 0;
+    RXC_CUDA(cudaMemcpyAsync(&h_err, d_small.p, 4, cudaMemcpyDeviceToHost, st));
+    RXC_CUDA(cudaMemcpyAsync(&h_arcs, g->out.row.p + n, 4, cudaMemcpyDeviceToHost, st));
+    RXC_CUDA(cudaStreamSynchronize(st));
+    RXC_CUDA(cudaGetLastError());
+    if (h_err & CSR_ERR_ENDPOINT_RANGE) throw std::invalid_argument("edge endpoint >= n_bound");
+    if (h_err & CSR_ERR_ENDPOINT_DEAD) throw std::invalid_argument("edge endpoint is not a live node");
+    if (h_err & CSR_ERR_EDGE_ID) throw std::invalid_argument("edge index >= e_bound");
+    g->out.arcs = h_arcs;
+    g->in.arcs = directed ? h_arcs : 0;
+    g->n_arcs = h_arcs;
+    if (!directed) {  // the symmetric structure is `out` itself
+        g->d_esrc.release();
+        g->d_edst.release();
+    }
 }
 
 static void reset_stats(rxc_graph *g) {
@@ -782,8 +921,22 @@ static void bfs_dispatch(rxc_graph *g, const DeviceCSR &csr, const std::vector<u
 static const DeviceCSR &symmetric_csr(rxc_graph *g) {
     if (!g->host.directed) return g->out;
     if (!g->has_sym) {
-        HostCSR h = make_symmetric(g->host);
-        g->sym.upload(h, g->stream);
+        if (g->d_esrc.p) {  // device build: both directions of every edge, no edge ids needed
+            const uint32_t n = g->host.n_live;
+            const uint64_t m = g->host.n_edges;
+            DevBuf<uint32_t> deg, cursor, tiles, small;
+            deg.alloc((size_t)n + 1);
+            cursor.alloc((size_t)n + 1);
+            small.alloc(4);
+            // degree = out-degree + in-degree, read off the two row arrays built at snapshot time
+            csr_degree_sum_kernel<<<(n + BLOCK) / BLOCK, BLOCK, 0, g->stream>>>(g->out.row.p, g->in.row.p, n, deg.p);
+            device_build_csr(g->sym, n, g->d_esrc.p, g->d_edst.p, nullptr, m, 2, deg.p, cursor, tiles,
+                             small.p + 1, g->stream);
+            g->sym.arcs = 2 * (uint64_t)g->n_arcs;
+        } else {
+            HostCSR h = make_symmetric(g->host);
+            g->sym.upload(h, g->stream);
+        }
         RXC_CUDA(cudaStreamSynchronize(g->stream));
         g->has_sym = true;
     }
@@ -836,10 +989,16 @@ int rxc_graph_snapshot(uint32_t n_bound, const uint32_t *live_nodes, uint32_t n_
         RXC_CUDA(cudaSetDevice(g->device));
         RXC_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
         for (auto &e : g->ev) RXC_CUDA(cudaEventCreate(&e));
-        g->host = make_snapshot(n_bound, live_nodes, n_live, e_bound, edge_src, edge_dst, edge_id,
-                                n_edges, directed != 0);
-        g->out.upload(g->host.out, g->stream);
-        if (g->host.directed) g->in.upload(g->host.in, g->stream);
+        if (g_opt.device_csr) {
+            device_snapshot(g, n_bound, live_nodes, n_live, e_bound, edge_src, edge_dst, edge_id,
+                            n_edges, directed != 0);
+        } else {
+            g->host = make_snapshot(n_bound, live_nodes, n_live, e_bound, edge_src, edge_dst, edge_id,
+                                    n_edges, directed != 0);
+            g->out.upload(g->host.out, g->stream);
+            if (g->host.directed) g->in.upload(g->host.in, g->stream);
+            g->n_arcs = g->host.out.col.size();
+        }
         g->d_stats.alloc(ST_COUNT);
         RXC_CUDA(cudaMemsetAsync(g->d_stats.p, 0, g->d_stats.bytes(), g->stream));
         RXC_CUDA(cudaStreamSynchronize(g->stream));
@@ -863,7 +1022,7 @@ int rxc_graph_info(const rxc_graph *g, uint32_t *n_bound, uint32_t *n_live, uint
     if (n_bound) *n_bound = g->host.n_bound;
     if (n_live) *n_live = g->host.n_live;
     if (e_bound) *e_bound = g->host.e_bound;
-    if (n_arcs) *n_arcs = g->host.out.col.size();
+    if (n_arcs) *n_arcs = g->n_arcs;
     if (directed) *directed = g->host.directed ? 1 : 0;
     return RXC_OK;
 }
@@ -985,6 +1144,7 @@ int rxc_set_option(const char *name, int64_t value) {
     else if (k == "hub_degree" && value > 0) g_opt.hub_degree = value;
     else if (k == "bfs_mode" && value >= 0 && value <= 2) g_opt.bfs_mode = value;
     else if (k == "bfs_depth_switch" && value >= 0) g_opt.bfs_depth_switch = value;
+    else if (k == "device_csr" && (value == 0 || value == 1)) g_opt.device_csr = value;
     else if (k == "mem_fraction_pct" && value > 0 && value <= 95) g_opt.mem_fraction_pct = value;
     else {
         set_error("unknown option: " + k);

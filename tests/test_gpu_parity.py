@@ -426,3 +426,33 @@ def test_distance_regimes_agree_with_oracle(rx, oracle, mode):
                                       og.distance_matrix(300, True, math.nan), equal_nan=True)
     finally:
         _lib.set_option("bfs_mode", 0)
+
+
+def test_device_and_host_csr_builders_agree(rx, oracle):
+    """rxc_graph_snapshot builds the CSR on the device by default; the host counting sort is kept as
+    a cross-check.  Results must be identical for the exact ops and within tolerance for BC."""
+    from rustworkx_b200 import _lib
+
+    for g in (random_graph(rx, True, 3000, 20000, 21, holes=40),
+              random_graph(rx, False, 3000, 12000, 22, holes=40),
+              rx.barabasi_albert_graph(30000, 6, seed=2)):
+        res = {}
+        for flag in (1, 0):
+            _lib.set_option("device_csr", flag)
+            try:
+                dg = _lib.DeviceGraph.from_graph(g)
+                src = np.asarray(g.node_indices()[:64], dtype=np.uint32)
+                res[flag] = (dg.closeness(True), dg.betweenness_partial(src, True),
+                             dg.edge_betweenness_partial(src),
+                             dg.distance_matrix_rows(0, 8, as_undirected=True, null_value=-1.0))
+                dg.close()
+            finally:
+                _lib.set_option("device_csr", 1)
+        assert np.array_equal(res[1][0], res[0][0])
+        assert_close(res[1][1], res[0][1])
+        assert_close(res[1][2], res[0][2])
+        assert np.array_equal(res[1][3], res[0][3])
+    # invalid inputs are rejected by the device builder too
+    with pytest.raises(_lib.RxCudaError):
+        _lib.DeviceGraph(4, np.array([0, 1, 2], np.uint32), 1, np.array([0], np.uint32),
+                         np.array([3], np.uint32), np.array([0], np.uint32), False)
