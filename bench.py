@@ -234,6 +234,8 @@ def run_b200(args):
         dist.broadcast(t, 0)
         ident = t.cpu().numpy().copy()
         _lib.check(_lib.lib().rxc_comm_init(rank, world, _lib.p_u8(ident)))
+        warm = np.zeros(1024, dtype=np.float64)  # first collective pays NCCL's lazy connection setup
+        _lib.check(_lib.lib().rxc_comm_reduce_sum_f64(_lib.p_f64(warm), warm.shape[0], 0))
 
     dg = make_device_graph()  # inputs resident in HBM before the timed region
     partial = np.zeros(snap["n_bound"], dtype=np.float64)
