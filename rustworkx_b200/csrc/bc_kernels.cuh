@@ -75,6 +75,9 @@ struct BcParams {
     const uint32_t *row;  // CSR offsets of the adjacency this kernel walks
     const uint32_t *col;  // CSR targets (compact vertex ids)
     const uint32_t *eid;  // arc -> original edge index (edge betweenness only)
+    const uint32_t *srow; // successor CSR (frontier marking in the forward pass)
+    const uint32_t *scol;
+    uint32_t *maybe;      // [NG][mwords] bit v: v has a neighbour on the current frontier (sparse levels)
     double *sc;           // [NG][n][128] sigma on the way down, (1+delta)/sigma on the way up
     PEntry *P0;           // [NG][n] tagged level masks, even levels
     PEntry *P1;           // [NG][n] tagged level masks, odd levels
@@ -96,6 +99,8 @@ struct BcParams {
     uint32_t lcap;
     uint32_t hubcap;
     uint32_t hub_degree;  // arcs; above this a vertex is handled by a whole CTA
+    uint32_t mwords;      // words per group in `maybe`: ceil(n / 32)
+    uint32_t sparse_max;  // a level with at most this many queue entries is filtered through `maybe`
     uint32_t ngroups;     // groups in this batch (stride of hubcnt)
     uint32_t tagbase;     // tag of level l is tagbase + l + 1
 };
@@ -288,6 +293,30 @@ __device__ __forceinline__ void bc_gather(const double *rows, uint32_t v_lane, c
 // forward
 // ---------------------------------------------------------------------------------------------
 
+// Sparse levels: when a group's frontier is small, only vertices adjacent to it can be discovered.
+// One warp per frontier entry sets the bit of every successor in `maybe`; the forward kernel then
+// skips every vertex whose bit is clear (and clears the words it consumed), so the cost of an early
+// BFS level -- or of any level of a long, thin graph -- is proportional to the frontier instead of n.
+__global__ void __launch_bounds__(BLOCK) bc_mark_kernel(BcParams p, uint32_t level) {
+    const uint32_t g = blockIdx.y;
+    const uint32_t cnt = p.lvlcnt[(size_t)g * p.lcap + level];
+    if (cnt == 0 || cnt > p.sparse_max) return;
+    const uint32_t off = p.loff[(size_t)g * p.lcap + level];
+    const uint32_t *qv = p.qv + (size_t)g * p.qcap + off;
+    uint32_t *maybe = p.maybe + (size_t)g * p.mwords;
+    const int lane = lane_id();
+    for (uint32_t i = blockIdx.x * WARPS + (threadIdx.x >> 5); i < cnt; i += gridDim.x * WARPS) {
+        const uint32_t v = qv[i];
+        const uint32_t e0 = p.srow[v], e1 = p.srow[v + 1];
+        for (uint32_t e = e0 + lane; e < e1; e += 32) {
+            const uint32_t w = p.scol[e];
+            const uint32_t bit = 1u << (w & 31);
+            if (!(maybe[w >> 5] & bit)) atomicOr(&maybe[w >> 5], bit);
+        }
+    }
+}
+
+
 // One warp: scan the in-arcs of a vertex (chunks of 32 arcs starting at e0+first, stride `step`),
 // pick up the sources whose frontier holds the neighbour, and sum the neighbours' sigma rows.
 __device__ __forceinline__ void bc_fwd_scan(const BcParams &p, const double *rows, const PEntry *Pcur,
@@ -345,7 +374,15 @@ __global__ void __launch_bounds__(BLOCK) bc_forward_kernel(BcParams p, uint32_t 
     {
         const uint32_t w = blockIdx.x * BLOCK + tid;
         Mask128 unv = mask_zero();
-        if (w < p.n) {
+        bool look = w < p.n;
+        if (fcnt <= p.sparse_max) {  // sparse level: only neighbours of the frontier can be reached
+            uint32_t *word = p.maybe + (size_t)g * p.mwords + (w >> 5);
+            const uint32_t bits = (w < p.n) ? *word : 0u;  // one word per warp (256 | 32)
+            look = (bits >> lane) & 1u;
+            __syncwarp();
+            if (lane == 0 && bits) *word = 0;  // consumed: clean for the next level
+        }
+        if (look) {
             const Mask128 vis = mask_load(&visited[w]);
 #pragma unroll
             for (int k = 0; k < BK; k++) unv.w[k] = ~vis.w[k];
@@ -512,24 +549,64 @@ __device__ __forceinline__ void bc_bwd_scan(const BcParams &p, const double *row
             bc_gather(rows, w, m, nz, lane, stage, acc, seen, dag);
         } else {
             while (nz) {
-                const int a = __ffs(nz) - 1;
-                nz &= nz - 1;
-                const uint32_t wj = __shfl_sync(FULL, w, a);
-                const uint32_t ej = __shfl_sync(FULL, ed, a);
-                const Mask128 mj = mask_shfl(m, a);
-                const Row4 x = row_load(rows, wj, lane, (mask_or(mj) >> lane) & 1u);
-                double c = 0.0;
+                // stage up to STAGE successor rows, then form per-arc sums over all 128 sources
+                uint32_t todo = nz;
+                int cnt = 0;
 #pragma unroll
-                for (int k = 0; k < BK; k++) {
-                    if ((mj.w[k] >> lane) & 1u) {
-                        const double ck = sig[k] * x.x[k];  // sigma[v] * coeff, centrality.rs:322
-                        acc[k] += ck;
-                        c += ck;
+                for (int i = 0; i < STAGE; i++) {
+                    if (nz) {  // warp-uniform
+                        const int a = __ffs(nz) - 1;
+                        nz &= nz - 1;
+                        const uint32_t wj = __shfl_sync(FULL, w, a);
+                        const uint32_t any = __shfl_sync(FULL, mask_or(m), a);
+                        cp_async_sector(stage + i * BG + lane * BK, rows + (size_t)wj * BG + lane * BK,
+                                        (any >> lane) & 1u);
+                        cnt = i + 1;
                     }
                 }
-                dag += mask_popc(mj);
-                const double tot = warp_sum(c);
-                if (lane == 0) atomicAdd(&p.acc[ej], tot);
+                cp_async_wait_all();
+                double c[STAGE];
+                uint32_t my_e = 0;
+#pragma unroll
+                for (int i = 0; i < STAGE; i++) {
+                    c[i] = 0.0;
+                    if (i < cnt) {
+                        const int a = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const Mask128 mj = mask_shfl(m, a);
+                        const uint32_t ej = __shfl_sync(FULL, ed, a);
+                        if ((lane >> 2) == i) my_e = ej;
+                        const double2 *q = reinterpret_cast<const double2 *>(stage + i * BG + lane * BK);
+                        const double2 x0 = q[0], x1 = q[1];
+                        const double xs[BK] = {x0.x, x0.y, x1.x, x1.y};
+#pragma unroll
+                        for (int k = 0; k < BK; k++) {
+                            if ((mj.w[k] >> lane) & 1u) {
+                                const double ck = sig[k] * xs[k];  // sigma[v]*coeff, centrality.rs:322
+                                acc[k] += ck;
+                                c[i] += ck;
+                            }
+                        }
+                        dag += mask_popc(mj);
+                    }
+                }
+                // reduce the STAGE per-arc sums over the warp at once: after the three halving
+                // exchanges lane l holds arc (l >> 2) & 7, two more steps finish the sum
+                static_assert(STAGE == 8, "the exchange network below is written for 8 values");
+#pragma unroll
+                for (int half = 4, off = 16; half >= 1; half >>= 1, off >>= 1) {
+                    const bool upper = lane & off;
+#pragma unroll
+                    for (int j = 0; j < half; j++) {
+                        const double send = upper ? c[j] : c[j + half];
+                        const double recv = __shfl_xor_sync(FULL, send, off);
+                        c[j] = (upper ? c[j + half] : c[j]) + recv;
+                    }
+                }
+                double tot = c[0];
+                tot += __shfl_xor_sync(FULL, tot, 2);
+                tot += __shfl_xor_sync(FULL, tot, 1);
+                if ((lane & 3) == 0 && (lane >> 2) < cnt) atomicAdd(&p.acc[my_e], tot);
             }
         }
     }

@@ -83,12 +83,14 @@ struct Options {
     int64_t mem_fraction_pct = 70;
     int64_t hub_degree = 512;    // vertices above this degree get a whole CTA
     int64_t bfs_mode = 0;        // 0 auto, 1 bit-parallel level launches, 2 CTA-per-source in smem
+    int64_t bc_sparse_div = 16;  // forward levels with <= n/this queue entries use the frontier filter (0: off)
     int64_t device_csr = 1;      // build the CSR on the device (0: host counting sort)
     int64_t bfs_depth_switch = 48;  // auto: pilot BFS deeper than this many levels -> mode 2
 };
 static Options g_opt;
 constexpr uint32_t HUB_CAP = 4096;  // deferred high-degree work items per group and level
 constexpr uint32_t HUB_CTAS = 32;   // CTAs per group in the hub kernels
+constexpr uint32_t MARK_CTAS = 64;  // CTAs per group in the frontier-marking kernel
 static int g_device = 0;
 
 static double now_ms() {
@@ -102,15 +104,16 @@ struct BcWorkspace {
     DevBuf<double> sc;
     DevBuf<PEntry> P0, P1;
     DevBuf<Mask128> visited, qm, hubm;
-    DevBuf<uint32_t> qv, loff, lvlcnt, lvl_total, src, hubv, hubcnt;
+    DevBuf<uint32_t> qv, loff, lvlcnt, lvl_total, src, hubv, hubcnt, maybe;
     DevBuf<unsigned long long> reach;
     uint64_t ng = 0;        // capacity in groups
+    uint64_t wanted = 0;    // groups asked for when `ng` was sized (may have been clamped by memory)
     uint32_t tagbase = 0;   // tags already used in P0/P1
     uint32_t dirty_levels = 0;  // prefix of the level tables the last batch wrote
     void release() {
         sc.release(); P0.release(); P1.release(); visited.release(); qv.release(); qm.release();
         loff.release(); lvlcnt.release(); lvl_total.release(); src.release(); reach.release();
-        hubv.release(); hubm.release(); hubcnt.release();
+        hubv.release(); hubm.release(); hubcnt.release(); maybe.release();
         ng = 0;
     }
 };
@@ -119,7 +122,7 @@ struct BfsWorkspace {
     DevBuf<uint32_t> visited, next0, next1, q0, q1, cnt, lvl_total, src;
     DevBuf<unsigned long long> reach, dsum;
     DevBuf<double> vals, rows;
-    uint64_t ng = 0, ng_rows = 0;
+    uint64_t ng = 0, ng_rows = 0, wanted = 0;
     uint32_t dirty_levels = 0;
     void release() {
         visited.release(); next0.release(); next1.release(); q0.release(); q1.release();
@@ -148,6 +151,7 @@ struct rxc_graph {
     uint64_t last_bfs_entries = 0;  // queue entries of the bit-parallel batches of this call
     BcWorkspace bc_ws;
     BfsWorkspace bfs_ws;
+    DevBuf<double> acc_buf;  // partial centrality vector of the current call
     std::mutex mu;
 
     const DeviceCSR &succ() const { return out; }
@@ -444,14 +448,16 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
     uint64_t ng = g_opt.bc_groups > 0 ? (uint64_t)g_opt.bc_groups
                                       : std::max<uint64_t>(1, (2ull << 20) / std::max<uint32_t>(n, 1));
     ng = std::min<uint64_t>(ng, 64);
-    ng = std::min<uint64_t>(ng, std::max<uint64_t>(1, (uint64_t)((double)device_budget() / per_group)));
     ng = std::min<uint64_t>(ng, total_groups);
 
     BcWorkspace &ws = g->bc_ws;
     cudaStream_t st = g->stream;
+    if (ws.ng < ng && ws.wanted >= ng) ng = ws.ng;  // already clamped by memory for this request
     if (ws.ng < ng) {
         ws.release();
         g->bfs_ws.release();  // one scratch set at a time keeps the footprint predictable
+        ws.wanted = ng;
+        ng = std::min<uint64_t>(ng, std::max<uint64_t>(1, (uint64_t)((double)device_budget() / per_group)));
         ws.sc.alloc((size_t)ng * n * BG);
         ws.P0.alloc((size_t)ng * n);
         ws.P1.alloc((size_t)ng * n);
@@ -466,6 +472,8 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
         ws.hubv.alloc((size_t)ng * HUB_CAP);
         ws.hubm.alloc((size_t)ng * HUB_CAP);
         ws.hubcnt.alloc((size_t)2 * ng);
+        ws.maybe.alloc((size_t)ng * ((n + 31) / 32));
+        RXC_CUDA(cudaMemsetAsync(ws.maybe.p, 0, ws.maybe.bytes(), st));
         ws.ng = ng;
         ws.tagbase = 0;
         ws.dirty_levels = lcap;
@@ -491,6 +499,11 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
     p.hubm = ws.hubm.p;
     p.hubcnt = ws.hubcnt.p;
     p.hubcap = HUB_CAP;
+    p.maybe = ws.maybe.p;
+    p.mwords = (n + 31) / 32;
+    p.sparse_max = (uint32_t)std::min<int64_t>(g_opt.bc_sparse_div > 0 ? n / g_opt.bc_sparse_div : 0, 0x7FFFFFFF);
+    p.srow = g->succ().row.p;
+    p.scol = g->succ().col.p;
     p.hub_degree = (uint32_t)std::min<int64_t>(g_opt.hub_degree, 0x7FFFFFFF);
     p.qcap = qcap;
     p.n = n;
@@ -531,12 +544,13 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
         const uint32_t L = run_levels(
             g, ws.lvl_total.p, n,
             [&](uint32_t level) {
+                if (p.sparse_max) bc_mark_kernel<<<dim3(MARK_CTAS, bg), BLOCK, 0, st>>>(p, level);
                 bc_forward_kernel<<<dim3(vblocks, bg), BLOCK, BC_SMEM_BYTES, st>>>(p, level);
                 bc_forward_hub_kernel<<<dim3(HUB_CTAS, bg), BLOCK, BC_SMEM_BYTES, st>>>(p, level);
                 launched_levels++;
             },
             h_totals);
-        g->stats.launches += 2 * launched_levels;
+        g->stats.launches += (p.sparse_max ? 3 : 2) * launched_levels;
         g->stats.levels += L;
         clear_levels = std::min<uint32_t>(lcap, launched_levels + 2);
         RXC_CUDA(cudaMemsetAsync(ws.hubcnt.p, 0, ws.hubcnt.bytes(), st));
@@ -618,18 +632,18 @@ static void bc_partial(rxc_graph *g, const std::vector<uint32_t> &sources, bool 
         end_call(g);
         return;
     }
-    DevBuf<double> acc;
-    acc.alloc(acc_len);
-    RXC_CUDA(cudaMemsetAsync(acc.p, 0, acc.bytes(), g->stream));
+    DevBuf<double> &acc = g->acc_buf;  // kept across calls: cudaMalloc/cudaFree would serialise the device
+    if (acc.n < acc_len) acc.alloc(acc_len);
+    RXC_CUDA(cudaMemsetAsync(acc.p, 0, acc_len * sizeof(double), g->stream));
     for (const auto &round : distinct_rounds(sources, n)) bc_run(g, round, endpoints, edge_mode, acc.p);
     end_call(g);
     const double t0 = now_ms();
     if (edge_mode) {
-        RXC_CUDA(cudaMemcpyAsync(out, acc.p, acc.bytes(), cudaMemcpyDeviceToHost, g->stream));
+        RXC_CUDA(cudaMemcpyAsync(out, acc.p, acc_len * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
         RXC_CUDA(cudaStreamSynchronize(g->stream));
     } else {
         std::vector<double> h(n);
-        RXC_CUDA(cudaMemcpyAsync(h.data(), acc.p, acc.bytes(), cudaMemcpyDeviceToHost, g->stream));
+        RXC_CUDA(cudaMemcpyAsync(h.data(), acc.p, acc_len * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
         RXC_CUDA(cudaStreamSynchronize(g->stream));
         for (uint32_t i = 0; i < n; i++) out[g->host.orig_of_compact[i]] = h[i];
     }
@@ -653,7 +667,17 @@ static void bfs_run(rxc_graph *g, const DeviceCSR &csr, const std::vector<uint32
     const uint32_t lcap = n + 2;
     const double per_group = (double)n * 20.0 + (rows_mode ? (double)n * GW * 8.0 : 0.0) + 1024.0;
     uint64_t ng = g_opt.bfs_groups > 0 ? (uint64_t)g_opt.bfs_groups : 4096;
-    ng = std::min<uint64_t>(ng, std::max<uint64_t>(1, (uint64_t)((double)device_budget() / per_group)));
+    {
+        const uint64_t want = std::min<uint64_t>(ng, total_groups);
+        BfsWorkspace &w0 = g->bfs_ws;
+        const bool have = w0.ng >= want && (!rows_mode || w0.ng_rows >= want);
+        if (!have && w0.wanted >= want && w0.ng > 0 && (!rows_mode || w0.ng_rows > 0)) {
+            ng = rows_mode ? std::min(w0.ng, w0.ng_rows) : w0.ng;  // clamped by memory earlier
+        } else if (!have) {
+            w0.wanted = want;
+            ng = std::min<uint64_t>(ng, std::max<uint64_t>(1, (uint64_t)((double)device_budget() / per_group)));
+        }
+    }
     if (rows_mode)  // keep one batch of rows under 8 GiB
         ng = std::min<uint64_t>(ng, std::max<uint64_t>(1, (8ull << 30) / ((uint64_t)n * GW * 8)));
     ng = std::min<uint64_t>(ng, total_groups);
@@ -1145,6 +1169,7 @@ int rxc_set_option(const char *name, int64_t value) {
     else if (k == "bfs_mode" && value >= 0 && value <= 2) g_opt.bfs_mode = value;
     else if (k == "bfs_depth_switch" && value >= 0) g_opt.bfs_depth_switch = value;
     else if (k == "device_csr" && (value == 0 || value == 1)) g_opt.device_csr = value;
+    else if (k == "bc_sparse_div" && value >= 0) g_opt.bc_sparse_div = value;
     else if (k == "mem_fraction_pct" && value > 0 && value <= 95) g_opt.mem_fraction_pct = value;
     else {
         set_error("unknown option: " + k);
