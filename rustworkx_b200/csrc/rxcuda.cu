@@ -32,6 +32,21 @@ struct OomError : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
 
+// Device buffers come from the device's stream-ordered memory pool with an unlimited release
+// threshold: freeing a multi-GB workspace (rxc_graph_free) hands it back to the pool, and the next
+// snapshot gets it again without a round trip through the driver's physical allocator.
+static void pool_setup(int device) {
+    static bool done[64] = {false};
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t threshold = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    cudaGetLastError();
+    done[device] = true;
+}
+
 template <class T>
 struct DevBuf {
     T *p = nullptr;
@@ -42,17 +57,20 @@ struct DevBuf {
     void alloc(size_t count) {
         release();
         if (count) {
-            cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+            cudaError_t e = cudaMallocAsync((void **)&p, count * sizeof(T), 0);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(0);
             if (e == cudaErrorMemoryAllocation) {
                 cudaGetLastError();
-                throw OomError("cudaMalloc of " + std::to_string(count * sizeof(T)) + " bytes failed");
+                p = nullptr;
+                throw OomError("device allocation of " + std::to_string(count * sizeof(T)) + " bytes failed");
             }
             RXC_CUDA(e);
         }
         n = count;
     }
+    // callers only release buffers whose consumer stream has been synchronised
     void release() {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, 0);
         p = nullptr;
         n = 0;
     }
@@ -158,6 +176,7 @@ struct rxc_graph {
     const DeviceCSR &pred() const { return host.directed ? in : out; }
     ~rxc_graph() {
         cudaSetDevice(device);
+        if (stream) cudaStreamSynchronize(stream);  // members return their buffers to the pool after this
         for (auto &e : ev)
             if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
@@ -206,6 +225,18 @@ static void require_device() {
 static size_t device_budget() {
     size_t free_b = 0, total_b = 0;
     RXC_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    // memory parked in the pool (reserved, not in use) is available to us as well
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t reserved = 0, used = 0;
+        if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess &&
+            reserved > used)
+            free_b += (size_t)(reserved - used);
+    }
+    cudaGetLastError();
     return (size_t)((double)free_b * (double)g_opt.mem_fraction_pct / 100.0);
 }
 
@@ -1011,6 +1042,7 @@ int rxc_graph_snapshot(uint32_t n_bound, const uint32_t *live_nodes, uint32_t n_
         g = new rxc_graph();
         g->device = g_device;
         RXC_CUDA(cudaSetDevice(g->device));
+        pool_setup(g->device);
         RXC_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
         for (auto &e : g->ev) RXC_CUDA(cudaEventCreate(&e));
         if (g_opt.device_csr) {
