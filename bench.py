@@ -82,6 +82,18 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel, sources_per_step):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed
+    `ncu --set full` capture of one 256-source batch of this same workload (profiles/)."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic_batch256.json")
+    try:
+        with open(path) as f:
+            rec = json.load(f)[kernel]
+        return rec["dram_bytes"] / rec["launches"], "profiles/r01_traffic_batch256.json (ncu --set full, per launch)"
+    except Exception:
+        return None, "no ncu capture committed"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
 
@@ -324,9 +336,12 @@ def run_b200(args):
     dom = max(kernels, key=lambda k: kernels[k]["ms"])
     achieved = kernels[dom]["bytes"] / (kernels[dom]["ms"] * 1e-3) / 1e9
     whole = (bytes_fwd + bytes_bwd) / (agg["ms_total"] * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(dom, S)
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+        "algorithmic_bytes_per_launch": kernels[dom]["bytes"] / max(1, agg["levels"]),
+        "peak_source": peak_src,
         "whole_step": {"achieved": whole, "frac": whole / peak,
                        "bytes_model": "16*TE + 24*TE_dag + 44*V"},
         "frac_of_8TBs_nominal": achieved / 8000.0,

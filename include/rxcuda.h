@@ -90,6 +90,12 @@ int rxc_closeness(rxc_graph *g, int wf_improved, double *out /* n_bound */);
 int rxc_distance_matrix(rxc_graph *g, int as_undirected, double null_value,
                         double *out /* n_live * n_live, row-major */);
 
+/* compute_distance_sum (src/shortest_path/average_length.rs:22-77), the kernel under
+ * graph_/digraph_unweighted_average_shortest_path_length (src/shortest_path/mod.rs:1657-1740):
+ * sum of all finite shortest-path lengths and the number of connected ordered pairs. */
+int rxc_distance_sums(rxc_graph *g, int as_undirected, uint64_t *total_distance,
+                      uint64_t *connected_pairs);
+
 /* ---- partial calls: a subset of sources (ORIGINAL node indices), no final scaling.  This is the
  * unit a rank runs when sources are sharded across GPUs; partial vectors are additive.
  * `out` is zero-initialised by the call. ----------------------------------------------------------- */

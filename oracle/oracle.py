@@ -86,6 +86,9 @@ def lib():
     L.rxo_betweenness_partial.argtypes = [vp, u32p, C.c_size_t, C.c_int, C.c_int, f64p, sp]
     L.rxo_edge_betweenness_partial.argtypes = [vp, u32p, C.c_size_t, C.c_int, f64p, sp]
     L.rxo_closeness_partial.argtypes = [vp, u32p, C.c_size_t, C.c_int, C.c_int, f64p, sp]
+    L.rxo_average_shortest_path_length.restype = C.c_double
+    L.rxo_average_shortest_path_length.argtypes = [vp, C.c_size_t, C.c_int, C.c_int]
+    L.rxo_distance_sum.argtypes = [vp, C.c_size_t, C.c_int, u64p, u64p]
     L.rxo_rescale.argtypes = [f64p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int]
     L.rxo_max_threads.restype = C.c_int
     _lib = L
@@ -241,6 +244,17 @@ class OracleGraph:
                 self._h, int(parallel_threshold), int(as_undirected), float(null_value),
                 _p(out, C.c_double), C.byref(st))
         return (out, st.as_dict()) if return_stats else out
+
+    def average_shortest_path_length(self, parallel_threshold=300, as_undirected=False,
+                                     disconnected=False):
+        return float(self._L.rxo_average_shortest_path_length(
+            self._h, int(parallel_threshold), int(as_undirected), int(disconnected)))
+
+    def distance_sum(self, parallel_threshold=300, as_undirected=False):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._L.rxo_distance_sum(self._h, int(parallel_threshold), int(as_undirected),
+                                 C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
 
     # -- partial (source subset, un-rescaled) --------------------------------------------------
     def betweenness_partial(self, sources, include_endpoints=False, threads=1):

@@ -671,6 +671,68 @@ void rxo_closeness_centrality(const rxo_graph *g, int wf_improved, size_t parall
     free(ids);
 }
 
+/* compute_distance_sum, src/shortest_path/average_length.rs:22-77: per source a level-by-level
+ * BFS over outgoing (and, for a directed graph with as_undirected, incoming) neighbours; returns
+ * (sum of distances, connected ordered pairs). */
+void rxo_distance_sum(const rxo_graph *g, size_t parallel_threshold, int as_undirected,
+                      uint64_t *sum_out, uint64_t *pairs_out) {
+    size_t bound = rxo_node_bound(g);
+    size_t k;
+    uint32_t *ids = rxo_live_nodes(g, &k);
+    int threads = (g->node_count >= parallel_threshold) ? rxo_max_threads() : 1;
+    uint64_t tot_sum = 0, tot_pairs = 0;
+    long kk = (long)k;
+    (void)threads;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads) if (threads > 1) \
+    reduction(+ : tot_sum, tot_pairs)
+    for (long i = 0; i < kk; i++) {
+        size_t *dist = (size_t *)malloc((bound ? bound : 1) * sizeof(size_t));
+        for (size_t j = 0; j < bound; j++) dist[j] = RXO_NONE;
+        uint32_t *Q = (uint32_t *)malloc((g->node_count ? g->node_count : 1) * sizeof(uint32_t));
+        size_t qh = 0, qt = 0;
+        uint64_t count = 0, found = 0;
+        dist[ids[i]] = 0;
+        Q[qt++] = ids[i];
+        while (qh < qt) {
+            uint32_t v = Q[qh++];
+            size_t d = dist[v];
+            count += d;
+            found++;
+            const rxo_node_t *vn = &g->nodes[v];
+            for (uint32_t e = vn->next[0]; e != RXO_END; e = g->edges[e].next[0]) {
+                uint32_t w = g->edges[e].node[1];
+                if (dist[w] == RXO_NONE) { dist[w] = d + 1; Q[qt++] = w; }
+            }
+            if (!g->directed || as_undirected) {
+                for (uint32_t e = vn->next[1]; e != RXO_END; e = g->edges[e].next[1]) {
+                    uint32_t w = g->edges[e].node[0];
+                    if (dist[w] == RXO_NONE) { dist[w] = d + 1; Q[qt++] = w; }
+                }
+            }
+        }
+        tot_sum += count;
+        tot_pairs += found - 1;
+        free(dist);
+        free(Q);
+    }
+    free(ids);
+    *sum_out = tot_sum;
+    *pairs_out = tot_pairs;
+}
+
+/* graph_/digraph_unweighted_average_shortest_path_length, src/shortest_path/mod.rs:1657-1740 */
+double rxo_average_shortest_path_length(const rxo_graph *g, size_t parallel_threshold,
+                                        int as_undirected, int disconnected) {
+    size_t n = g->node_count;
+    if (n <= 1) return NAN;
+    uint64_t sum, conn_pairs;
+    rxo_distance_sum(g, parallel_threshold, as_undirected, &sum, &conn_pairs);
+    uint64_t tot_pairs = (uint64_t)n * (n - 1);
+    if (disconnected && conn_pairs == 0) return NAN;
+    if (!disconnected && conn_pairs < tot_pairs) return INFINITY;
+    return (double)sum / (double)conn_pairs;
+}
+
 /* ------------------------------------------------------------------ */
 /* distance_matrix                                                     */
 /* ------------------------------------------------------------------ */

@@ -83,6 +83,12 @@ void rxo_closeness_centrality(const rxo_graph *g, int wf_improved, size_t parall
 void rxo_distance_matrix(const rxo_graph *g, size_t parallel_threshold, int as_undirected,
                          double null_value, double *out, rxo_stats *stats);
 
+/* src/shortest_path/average_length.rs:22-77 and src/shortest_path/mod.rs:1657-1740 */
+void rxo_distance_sum(const rxo_graph *g, size_t parallel_threshold, int as_undirected,
+                      uint64_t *sum_out, uint64_t *pairs_out);
+double rxo_average_shortest_path_length(const rxo_graph *g, size_t parallel_threshold,
+                                        int as_undirected, int disconnected);
+
 /* ---- partial (source-subset) variants used for sampled parity on large
  *      graphs and as the timed CPU baseline: same per-source code, no final
  *      _rescale; accumulate into `out` (caller zero-initialises). ---- */

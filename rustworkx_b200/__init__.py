@@ -192,6 +192,34 @@ def digraph_distance_matrix(graph, /, parallel_threshold=300, as_undirected=Fals
     return device_snapshot(graph).distance_matrix(as_undirected, null_value)
 
 
+def _average_length(graph, as_undirected, disconnected):
+    # src/shortest_path/mod.rs:1657-1740
+    n = graph.num_nodes()
+    if n <= 1:
+        return float("nan")
+    total, conn_pairs = device_snapshot(graph).distance_sums(as_undirected)
+    if disconnected and conn_pairs == 0:
+        return float("nan")
+    if not disconnected and conn_pairs < n * (n - 1):
+        return float("inf")
+    return float(total) / float(conn_pairs)
+
+
+def graph_unweighted_average_shortest_path_length(graph, /, parallel_threshold=300, disconnected=False):
+    """``rustworkx.graph_unweighted_average_shortest_path_length`` (``src/shortest_path/mod.rs:1706-1740``)."""
+    graph = _graph_arg(graph, PyGraph, "PyGraph")
+    _usize(parallel_threshold, "parallel_threshold")
+    return _average_length(graph, True, _bool(disconnected, "disconnected"))
+
+
+def digraph_unweighted_average_shortest_path_length(graph, /, parallel_threshold=300,
+                                                    as_undirected=False, disconnected=False):
+    """``rustworkx.digraph_unweighted_average_shortest_path_length`` (``src/shortest_path/mod.rs:1657-1690``)."""
+    graph = _graph_arg(graph, PyDiGraph, "PyDiGraph")
+    _usize(parallel_threshold, "parallel_threshold")
+    return _average_length(graph, _bool(as_undirected, "as_undirected"), _bool(disconnected, "disconnected"))
+
+
 # ---------------------------------------------------------------------------------------------
 # universal dispatchers (rustworkx/__init__.py:138-147)
 # ---------------------------------------------------------------------------------------------
@@ -207,6 +235,12 @@ def _rustworkx_dispatch(func):
 @_rustworkx_dispatch
 def distance_matrix(graph, parallel_threshold=300, as_undirected=False, null_value=0.0):
     """Get the distance matrix for a graph (``rustworkx/__init__.py:150-179``)."""
+    raise TypeError(f"Invalid Input Type {type(graph)} for graph")
+
+
+@_rustworkx_dispatch
+def unweighted_average_shortest_path_length(graph, parallel_threshold=300, disconnected=False):
+    """Average shortest path length with unweighted edges (``rustworkx/__init__.py:182-220``)."""
     raise TypeError(f"Invalid Input Type {type(graph)} for graph")
 
 

@@ -68,6 +68,7 @@ SYMBOLS = {
     "rxc_edge_betweenness": (C.c_int, [_vp, C.c_int, _f64p]),
     "rxc_closeness": (C.c_int, [_vp, C.c_int, _f64p]),
     "rxc_distance_matrix": (C.c_int, [_vp, C.c_int, C.c_double, _f64p]),
+    "rxc_distance_sums": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "rxc_betweenness_partial": (C.c_int, [_vp, _u32p, C.c_uint64, C.c_int, _f64p]),
     "rxc_edge_betweenness_partial": (C.c_int, [_vp, _u32p, C.c_uint64, _f64p]),
     "rxc_closeness_partial": (C.c_int, [_vp, _u32p, C.c_uint64, C.c_int, _f64p]),
@@ -215,6 +216,11 @@ class DeviceGraph:
         if self.n_live:
             check(lib().rxc_distance_matrix(self._h, int(as_undirected), float(null_value), p_f64(out)))
         return out
+
+    def distance_sums(self, as_undirected):
+        total, pairs = C.c_uint64(), C.c_uint64()
+        check(lib().rxc_distance_sums(self._h, int(as_undirected), C.byref(total), C.byref(pairs)))
+        return int(total.value), int(pairs.value)
 
     # ---- partial calls (source shards; un-rescaled) ---------------------------------------------
     def betweenness_partial(self, sources, include_endpoints=False):

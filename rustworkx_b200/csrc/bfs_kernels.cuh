@@ -307,6 +307,17 @@ __global__ void __launch_bounds__(1024, 1) bfs_smem_kernel(SmemBfsParams p) {
     }
 }
 
+// (reach, sum of distances) per source as exact doubles (both < 2^53) for
+// unweighted_average_shortest_path_length, src/shortest_path/average_length.rs:22-77
+__global__ void __launch_bounds__(BLOCK)
+    distance_sums_kernel(const unsigned long long *reach, const unsigned long long *dsum,
+                         uint32_t nslots, double *out /* [nslots][2] */) {
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= nslots) return;
+    out[2 * (size_t)i] = (double)reach[i];
+    out[2 * (size_t)i + 1] = (double)dsum[i];
+}
+
 // closeness_finalize for the CTA-per-source path (no NO_SOURCE padding)
 __global__ void __launch_bounds__(BLOCK)
     closeness_finalize_flat_kernel(const unsigned long long *reach, const unsigned long long *dsum,

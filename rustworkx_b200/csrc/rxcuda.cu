@@ -133,6 +133,7 @@ struct BcWorkspace {
         loff.release(); lvlcnt.release(); lvl_total.release(); src.release(); reach.release();
         hubv.release(); hubm.release(); hubcnt.release(); maybe.release();
         ng = 0;
+        wanted = 0;
     }
 };
 
@@ -147,6 +148,7 @@ struct BfsWorkspace {
         cnt.release(); lvl_total.release(); src.release(); reach.release(); dsum.release();
         vals.release(); rows.release();
         ng = ng_rows = 0;
+        wanted = 0;
     }
 };
 
@@ -483,7 +485,7 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
 
     BcWorkspace &ws = g->bc_ws;
     cudaStream_t st = g->stream;
-    if (ws.ng < ng && ws.wanted >= ng) ng = ws.ng;  // already clamped by memory for this request
+    if (ws.ng > 0 && ws.ng < ng && ws.wanted >= ng) ng = ws.ng;  // already clamped by memory for this request
     if (ws.ng < ng) {
         ws.release();
         g->bfs_ws.release();  // one scratch set at a time keeps the footprint predictable
@@ -685,7 +687,7 @@ static void bc_partial(rxc_graph *g, const std::vector<uint32_t> &sources, bool 
 // ------------------------------------------------------------------------------------------------
 // closeness / distance matrix
 // ------------------------------------------------------------------------------------------------
-enum class BfsMode { Closeness, Rows };
+enum class BfsMode { Closeness, Rows, Sums };  // Sums: out[i] = {reached, sum of distances}
 
 // sources: compact ids.  Closeness: out[i] = closeness of sources[i].  Rows: out = rows of the
 // distance matrix for sources[i] (n_live columns each).
@@ -729,7 +731,7 @@ static void bfs_run(rxc_graph *g, const DeviceCSR &csr, const std::vector<uint32
         ws.src.alloc((size_t)ng * GW);
         ws.reach.alloc((size_t)ng * GW);
         ws.dsum.alloc((size_t)ng * GW);
-        ws.vals.alloc((size_t)ng * GW);
+        ws.vals.alloc((size_t)ng * GW * 2);
         ws.ng = ng;
         ws.dirty_levels = lcap;
     }
@@ -757,7 +759,8 @@ static void bfs_run(rxc_graph *g, const DeviceCSR &csr, const std::vector<uint32
     p.n = n;
 
     std::vector<uint32_t> h_src((size_t)ng * GW), h_totals;
-    std::vector<double> h_vals((size_t)ng * GW);
+    const size_t vstride = mode == BfsMode::Sums ? 2 : 1;
+    std::vector<double> h_vals((size_t)ng * GW * 2);
     const uint32_t vblocks = (n + BLOCK - 1) / BLOCK;
     uint32_t &clear_levels = ws.dirty_levels;
 
@@ -803,7 +806,11 @@ static void bfs_run(rxc_graph *g, const DeviceCSR &csr, const std::vector<uint32
         g->stats.levels += L;
         for (uint32_t l = 0; l < L && l < h_totals.size(); l++) g->last_bfs_entries += h_totals[l];
         clear_levels = std::min<uint32_t>(lcap, launched_levels + 2);
-        if (!rows_mode) {
+        if (mode == BfsMode::Sums) {
+            distance_sums_kernel<<<(bg * GW + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(ws.reach.p, ws.dsum.p,
+                                                                                bg * GW, ws.vals.p);
+            g->stats.launches++;
+        } else if (!rows_mode) {
             closeness_finalize_kernel<<<(bg * GW + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(
                 ws.reach.p, ws.dsum.p, ws.src.p, bg * GW, wf_improved ? 1 : 0,
                 (unsigned long long)n, ws.vals.p);
@@ -815,12 +822,12 @@ static void bfs_run(rxc_graph *g, const DeviceCSR &csr, const std::vector<uint32
             RXC_CUDA(cudaMemcpyAsync(out + (size_t)s0 * n, ws.rows.p, (size_t)cnt * n * 8,
                                      cudaMemcpyDeviceToHost, st));
         } else {
-            RXC_CUDA(cudaMemcpyAsync(h_vals.data(), ws.vals.p, (size_t)cnt * 8,
+            RXC_CUDA(cudaMemcpyAsync(h_vals.data(), ws.vals.p, (size_t)cnt * 8 * vstride,
                                      cudaMemcpyDeviceToHost, st));
         }
         RXC_CUDA(cudaStreamSynchronize(st));
         RXC_CUDA(cudaGetLastError());
-        if (!rows_mode) std::copy(h_vals.begin(), h_vals.begin() + cnt, out + s0);
+        if (!rows_mode) std::copy(h_vals.begin(), h_vals.begin() + cnt * vstride, out + s0 * vstride);
         g->stats.ms_d2h += now_ms() - t0;
         float f = 0.f;
         RXC_CUDA(cudaEventElapsedTime(&f, g->ev[0], g->ev[1]));
@@ -881,8 +888,9 @@ static void bfs_smem_run(rxc_graph *g, const DeviceCSR &csr, const uint32_t *sou
     d_counter.alloc(1);
     d_reach.alloc(batch);
     d_dsum.alloc(batch);
+    const size_t vstride = mode == BfsMode::Sums ? 2 : 1;
     if (rows_mode) d_rows.alloc(batch * n);
-    else d_vals.alloc(batch);
+    else d_vals.alloc(batch * 2);
 
     SmemBfsParams p{};
     p.row = csr.row.p;
@@ -899,7 +907,7 @@ static void bfs_smem_run(rxc_graph *g, const DeviceCSR &csr, const uint32_t *sou
     p.n = n;
     p.words = (n + 31) / 32;
     p.qs = qs;
-    std::vector<double> h_vals(rows_mode ? 0 : batch);
+    std::vector<double> h_vals(rows_mode ? 0 : batch * 2);
     for (size_t s0 = 0; s0 < k; s0 += batch) {
         const size_t cnt = std::min(batch, k - s0);
         p.nsrc = (uint32_t)cnt;
@@ -914,9 +922,13 @@ static void bfs_smem_run(rxc_graph *g, const DeviceCSR &csr, const uint32_t *sou
             g->stats.launches += 2;
         } else {
             bfs_smem_kernel<false><<<grid, threads, smem, st>>>(p);
-            closeness_finalize_flat_kernel<<<((uint32_t)cnt + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(
-                d_reach.p, d_dsum.p, (uint32_t)cnt, wf_improved ? 1 : 0, (unsigned long long)n,
-                d_vals.p);
+            if (mode == BfsMode::Sums)
+                distance_sums_kernel<<<((uint32_t)cnt + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(
+                    d_reach.p, d_dsum.p, (uint32_t)cnt, d_vals.p);
+            else
+                closeness_finalize_flat_kernel<<<((uint32_t)cnt + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(
+                    d_reach.p, d_dsum.p, (uint32_t)cnt, wf_improved ? 1 : 0, (unsigned long long)n,
+                    d_vals.p);
             g->stats.launches += 2;
         }
         RXC_CUDA(cudaEventRecord(g->ev[1], st));
@@ -924,10 +936,10 @@ static void bfs_smem_run(rxc_graph *g, const DeviceCSR &csr, const uint32_t *sou
         if (rows_mode)
             RXC_CUDA(cudaMemcpyAsync(out + s0 * n, d_rows.p, cnt * (size_t)n * 8, cudaMemcpyDeviceToHost, st));
         else
-            RXC_CUDA(cudaMemcpyAsync(h_vals.data(), d_vals.p, cnt * 8, cudaMemcpyDeviceToHost, st));
+            RXC_CUDA(cudaMemcpyAsync(h_vals.data(), d_vals.p, cnt * 8 * vstride, cudaMemcpyDeviceToHost, st));
         RXC_CUDA(cudaStreamSynchronize(st));
         RXC_CUDA(cudaGetLastError());
-        if (!rows_mode) std::copy(h_vals.begin(), h_vals.begin() + cnt, out + s0);
+        if (!rows_mode) std::copy(h_vals.begin(), h_vals.begin() + cnt * vstride, out + s0 * vstride);
         if (max_depth_out) {
             std::vector<uint32_t> h_depth(cnt);
             RXC_CUDA(cudaMemcpy(h_depth.data(), d_depth.p, cnt * 4, cudaMemcpyDeviceToHost));
@@ -951,7 +963,7 @@ static void bfs_dispatch(rxc_graph *g, const DeviceCSR &csr, const std::vector<u
                          BfsMode mode, bool wf_improved, double null_value, double *out) {
     const uint32_t n = g->host.n_live;
     if (sources.empty() || n == 0) return;
-    const size_t stride = mode == BfsMode::Rows ? (size_t)n : 1;
+    const size_t stride = mode == BfsMode::Rows ? (size_t)n : (mode == BfsMode::Sums ? 2 : 1);
     const bool fits = smem_bfs_fits(n, nullptr, nullptr);
     int64_t regime = g_opt.bfs_mode;  // 0 auto, 1 bit-parallel, 2 CTA-per-source
     if (!fits) regime = 1;
@@ -1178,6 +1190,29 @@ int rxc_distance_matrix_rows(rxc_graph *g, int as_undirected, double null_value,
         bfs_dispatch(g, csr, src, BfsMode::Rows, false, null_value, out);
         end_call(g);
         fetch_stats(g);
+    });
+}
+
+int rxc_distance_sums(rxc_graph *g, int as_undirected, uint64_t *total_distance,
+                      uint64_t *connected_pairs) {
+    if (!g || !total_distance || !connected_pairs) return RXC_ERR_INVALID;
+    return guarded([&] {
+        std::lock_guard<std::mutex> lock(g->mu);
+        begin_call(g);
+        const uint32_t n = g->host.n_live;
+        std::vector<double> vals((size_t)n * 2);
+        // outgoing neighbours; both directions for an undirected graph or as_undirected
+        const DeviceCSR &csr = (as_undirected || !g->host.directed) ? symmetric_csr(g) : g->out;
+        bfs_dispatch(g, csr, all_sources(g), BfsMode::Sums, false, 0.0, vals.data());
+        end_call(g);
+        fetch_stats(g);
+        uint64_t sum = 0, pairs = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            pairs += (uint64_t)vals[2 * (size_t)i] - 1;
+            sum += (uint64_t)vals[2 * (size_t)i + 1];
+        }
+        *total_distance = sum;
+        *connected_pairs = pairs;
     });
 }
 

@@ -456,3 +456,68 @@ def test_device_and_host_csr_builders_agree(rx, oracle):
     with pytest.raises(_lib.RxCudaError):
         _lib.DeviceGraph(4, np.array([0, 1, 2], np.uint32), 1, np.array([0], np.uint32),
                          np.array([3], np.uint32), np.array([0], np.uint32), False)
+
+
+def test_full_size_invariant_ba_1m(rx):
+    """BASELINE.json configs[2] at full size (BA(10^6, 8)): size-independent property instead of the
+    oracle.  Every shortest s-t path of length d has d-1 interior vertices whose pair-dependencies
+    sum to d-1, so  sum_v partial_bc[v] = sum_{s in S} sum_t (d(s,t) - 1);  the right-hand side comes
+    from the (bit-exact) distance kernel via closeness = (r-1)/sum_d on a connected graph."""
+    from rustworkx_b200 import device_snapshot
+
+    n = 1_000_000
+    g = rx.barabasi_albert_graph(n, 8, seed=1)
+    dg = device_snapshot(g)
+    src = np.random.default_rng(5).choice(n, size=256, replace=False).astype(np.uint32)
+    partial = dg.betweenness_partial(src, False)
+    st = dg.stats()
+    assert st["v"] == 256 * n  # connected: every source reaches every vertex
+    assert st["te"] == 256 * 2 * g.num_edges()
+    cc = dg.closeness_partial(src, wf_improved=False)
+    dsum = np.rint((n - 1) / cc)  # integers well below 2^53
+    want = float(np.sum(dsum - (n - 1)))
+    got = float(np.sum(partial))
+    assert abs(got - want) <= 1e-9 * want
+    # endpoints add exactly (reached - 1) to the source and 1 to every other reached vertex
+    with_ep = dg.betweenness_partial(src[:128], True)
+    without = dg.betweenness_partial(src[:128], False)
+    assert abs(float(np.sum(with_ep - without)) - 2.0 * 128 * (n - 1)) <= 1e-6 * 128 * n
+    # edge betweenness: every s-t path of length d crosses d edges
+    epart = dg.edge_betweenness_partial(src[:128])
+    want_e = float(np.sum(dsum[:128]))
+    assert abs(float(np.sum(epart)) - want_e) <= 1e-9 * want_e
+
+
+def test_average_shortest_path_length(rx, oracle):
+    # SURVEY 8f #1: tests/graph/test_avg_shortest_path.py, tests/digraph/test_avg_shortest_path.py
+    gen = rx.generators
+    g = rx.PyGraph()
+    g.extend_from_edge_list([(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (3, 6), (6, 7)])
+    assert rx.graph_unweighted_average_shortest_path_length(g) == pytest.approx(2.5714285714285716, abs=1e-7)
+    assert rx.unweighted_average_shortest_path_length(gen.cycle_graph(7)) == pytest.approx(2, abs=1e-7)
+    assert rx.unweighted_average_shortest_path_length(gen.grid_graph(30, 11)) == pytest.approx(
+        13.666666666666666, abs=1e-7)
+    assert math.isnan(rx.unweighted_average_shortest_path_length(rx.PyGraph()))
+    iso = rx.PyGraph()
+    iso.add_nodes_from(range(32))
+    assert math.isinf(rx.unweighted_average_shortest_path_length(iso))
+    assert math.isnan(rx.unweighted_average_shortest_path_length(iso, disconnected=True))
+    part = gen.cycle_graph(32)
+    part.add_nodes_from(range(32))
+    assert math.isinf(rx.unweighted_average_shortest_path_length(part))
+    assert rx.unweighted_average_shortest_path_length(part, disconnected=True) == pytest.approx(8192 / 992, abs=1e-7)
+    assert math.isinf(rx.unweighted_average_shortest_path_length(gen.directed_path_graph(5)))
+    assert rx.digraph_unweighted_average_shortest_path_length(
+        gen.directed_path_graph(5), as_undirected=True) == pytest.approx(2, abs=1e-7)
+    # integer sums are exact, so the ratio is bit-identical to the oracle
+    for directed, seed in ((False, 31), (True, 32)):
+        g = random_graph(rx, directed, 800, 2500, seed, holes=15)
+        og = oracle_graph(oracle, g)
+        for disc in (False, True):
+            for und in ((False, True) if directed else (True,)):
+                want = og.average_shortest_path_length(300, und, disc)
+                if directed:
+                    got = rx.digraph_unweighted_average_shortest_path_length(g, as_undirected=und, disconnected=disc)
+                else:
+                    got = rx.unweighted_average_shortest_path_length(g, disconnected=disc)
+                assert (math.isnan(want) and math.isnan(got)) or want == got

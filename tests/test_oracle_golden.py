@@ -283,3 +283,38 @@ def test_grid_fixture(oracle):
                                    (4, 5), (5, 8), (6, 7), (7, 8)]
     g = gen.grid_graph(1000, 1000)
     assert g.num_nodes() == 10**6 and g.num_edges() == 1998000
+
+
+# ----------------------------------------------------------------------------- average path length
+def test_average_shortest_path_length_goldens(oracle):
+    # tests/graph/test_avg_shortest_path.py:20-100
+    import rustworkx_b200.generators as gen
+
+    def val(g, **kw):
+        return _gen(oracle, g).average_shortest_path_length(**kw)
+
+    g = oracle.OracleGraph.from_edges(False, [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (3, 6), (6, 7)])
+    assert g.average_shortest_path_length() == pytest.approx(2.5714285714285716, abs=1e-7)
+    assert val(gen.cycle_graph(7)) == pytest.approx(2, abs=1e-7)
+    assert val(gen.path_graph(5)) == pytest.approx(2, abs=1e-7)
+    assert val(gen.grid_graph(30, 11)) == pytest.approx(13.666666666666666, abs=1e-7)
+    assert math.isnan(oracle.OracleGraph(False).average_shortest_path_length())
+    one = oracle.OracleGraph(False)
+    a = one.add_node()
+    assert math.isnan(one.average_shortest_path_length())
+    one.add_edge(a, a)
+    assert math.isnan(one.average_shortest_path_length())
+    iso = oracle.OracleGraph(False)
+    for _ in range(32):
+        iso.add_node()
+    assert math.isinf(iso.average_shortest_path_length())
+    assert math.isnan(iso.average_shortest_path_length(disconnected=True))
+    part = gen.cycle_graph(32)
+    part.add_nodes_from(list(range(32)))
+    assert math.isinf(val(part))
+    assert val(part, disconnected=True) == pytest.approx(8192 / 992, abs=1e-7)
+    assert val(gen.cycle_graph(32)) == pytest.approx(8192 / 992, abs=1e-7)
+    # directed: tests/digraph/test_avg_shortest_path.py
+    assert val(gen.directed_cycle_graph(7)) == pytest.approx(3.5, abs=1e-7)
+    assert math.isinf(val(gen.directed_path_graph(5)))
+    assert val(gen.directed_path_graph(5), as_undirected=True) == pytest.approx(2, abs=1e-7)
