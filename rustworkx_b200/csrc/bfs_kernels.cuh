@@ -213,6 +213,7 @@ struct SmemBfsParams {
     const uint32_t *col;
     const uint32_t *sources;       // compact ids
     uint32_t *qspill;              // [gridDim.x][2][n] queue entries beyond SB_QS
+    uint32_t *gbitmap;             // [gridDim.x][words] visited bitmaps when they do not fit in smem
     uint32_t *next_source;         // dynamic source counter
     unsigned long long *reach;     // [nsrc]
     unsigned long long *dsum;      // [nsrc]
@@ -226,11 +227,13 @@ struct SmemBfsParams {
     uint32_t qs;                   // frontier entries per queue held in shared memory (<= SB_QS)
 };
 
-template <bool ROWS>
+template <bool ROWS, bool GLOBAL_BITMAP>
 __global__ void __launch_bounds__(1024, 1) bfs_smem_kernel(SmemBfsParams p) {
     extern __shared__ uint32_t sb_smem[];
-    uint32_t *vis = sb_smem;
-    uint32_t *q0 = vis + p.words;
+    // the bitmap lives in shared memory when it fits (n <= ~1.3 M), else in this CTA's slab of
+    // global memory (L2-resident: 148 slabs of n/8 bytes)
+    uint32_t *vis = GLOBAL_BITMAP ? p.gbitmap + (size_t)blockIdx.x * p.words : sb_smem;
+    uint32_t *q0 = GLOBAL_BITMAP ? sb_smem : sb_smem + p.words;
     uint32_t *q1 = q0 + p.qs;
     __shared__ uint32_t s_src, s_tail[2];
     __shared__ unsigned long long s_te;

@@ -840,13 +840,21 @@ static void bfs_run(rxc_graph *g, const DeviceCSR &csr, const std::vector<uint32
 // ------------------------------------------------------------------------------------------------
 // CTA-per-source BFS with the visited bitmap in shared memory (high-diameter graphs)
 // ------------------------------------------------------------------------------------------------
-static bool smem_bfs_fits(uint32_t n, uint32_t *qs_out, size_t *bytes_out) {
+// Shared-memory plan of the CTA-per-source kernel: the visited bitmap goes to shared memory when it
+// fits next to the frontier queues, otherwise to a per-CTA slab in global memory.
+static bool smem_bfs_fits(uint32_t n, uint32_t *qs_out, size_t *bytes_out, bool *global_bitmap = nullptr) {
     const uint32_t words = (n + 31) / 32;
     const uint32_t qs = std::min<uint32_t>(SB_QS, ((n + 31) / 32) * 32);
-    const size_t bytes = ((size_t)words + 2 * (size_t)qs) * 4;
+    size_t bytes = ((size_t)words + 2 * (size_t)qs) * 4;
+    bool global_bm = false;
+    if (bytes > 200 * 1024) {
+        global_bm = true;
+        bytes = 2 * (size_t)qs * 4;
+    }
     if (qs_out) *qs_out = qs;
     if (bytes_out) *bytes_out = bytes;
-    return bytes <= 200 * 1024;
+    if (global_bitmap) *global_bitmap = global_bm;
+    return true;
 }
 
 static void bfs_smem_run(rxc_graph *g, const DeviceCSR &csr, const uint32_t *sources, size_t k,
@@ -857,20 +865,23 @@ static void bfs_smem_run(rxc_graph *g, const DeviceCSR &csr, const uint32_t *sou
     const bool rows_mode = mode == BfsMode::Rows;
     uint32_t qs = 0;
     size_t smem = 0;
-    smem_bfs_fits(n, &qs, &smem);
+    bool gbm = false;
+    smem_bfs_fits(n, &qs, &smem, &gbm);
+    using KernelT = void (*)(SmemBfsParams);
+    const KernelT kernel = rows_mode ? (gbm ? bfs_smem_kernel<true, true> : bfs_smem_kernel<true, false>)
+                                     : (gbm ? bfs_smem_kernel<false, true> : bfs_smem_kernel<false, false>);
     static bool attr_done = false;
     if (!attr_done) {
-        RXC_CUDA(cudaFuncSetAttribute(bfs_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        RXC_CUDA(cudaFuncSetAttribute(bfs_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        const KernelT all[4] = {bfs_smem_kernel<false, false>, bfs_smem_kernel<false, true>,
+                                bfs_smem_kernel<true, false>, bfs_smem_kernel<true, true>};
+        for (KernelT k4 : all)
+            RXC_CUDA(cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_done = true;
     }
     const int threads = n >= (1u << 18) ? 1024 : 256;
     int per_sm = 1, sms = 148;
     RXC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device));
-    if (rows_mode)
-        RXC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_smem_kernel<true>, threads, smem));
-    else
-        RXC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_smem_kernel<false>, threads, smem));
+    RXC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
     per_sm = std::max(per_sm, 1);
     cudaStream_t st = g->stream;
 
@@ -878,13 +889,14 @@ static void bfs_smem_run(rxc_graph *g, const DeviceCSR &csr, const uint32_t *sou
     size_t batch = k;
     if (rows_mode) batch = std::max<size_t>(1, std::min<size_t>(k, (8ull << 30) / ((size_t)n * 8)));
     const uint32_t grid = (uint32_t)std::min<size_t>(batch, (size_t)sms * per_sm);
-    DevBuf<uint32_t> d_src, d_spill, d_counter;
+    DevBuf<uint32_t> d_src, d_spill, d_counter, d_bitmap;
     DevBuf<unsigned long long> d_reach, d_dsum;
     DevBuf<double> d_vals, d_rows;
     DevBuf<uint32_t> d_depth;
     if (max_depth_out) d_depth.alloc(batch);
     d_src.alloc(batch);
     d_spill.alloc((size_t)grid * 2 * n);
+    if (gbm) d_bitmap.alloc((size_t)grid * ((n + 31) / 32));
     d_counter.alloc(1);
     d_reach.alloc(batch);
     d_dsum.alloc(batch);
@@ -897,6 +909,7 @@ static void bfs_smem_run(rxc_graph *g, const DeviceCSR &csr, const uint32_t *sou
     p.col = csr.col.p;
     p.sources = d_src.p;
     p.qspill = d_spill.p;
+    p.gbitmap = gbm ? d_bitmap.p : nullptr;
     p.next_source = d_counter.p;
     p.reach = d_reach.p;
     p.dsum = d_dsum.p;
@@ -918,10 +931,10 @@ static void bfs_smem_run(rxc_graph *g, const DeviceCSR &csr, const uint32_t *sou
             const uint64_t len = (uint64_t)cnt * n;
             const uint32_t fb = (uint32_t)std::min<uint64_t>((len + BLOCK - 1) / BLOCK, 148 * 16);
             bfs_fill_f64_kernel<<<fb, BLOCK, 0, st>>>(d_rows.p, len, null_value);
-            bfs_smem_kernel<true><<<grid, threads, smem, st>>>(p);
+            kernel<<<grid, threads, smem, st>>>(p);
             g->stats.launches += 2;
         } else {
-            bfs_smem_kernel<false><<<grid, threads, smem, st>>>(p);
+            kernel<<<grid, threads, smem, st>>>(p);
             if (mode == BfsMode::Sums)
                 distance_sums_kernel<<<((uint32_t)cnt + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(
                     d_reach.p, d_dsum.p, (uint32_t)cnt, d_vals.p);
@@ -964,9 +977,7 @@ static void bfs_dispatch(rxc_graph *g, const DeviceCSR &csr, const std::vector<u
     const uint32_t n = g->host.n_live;
     if (sources.empty() || n == 0) return;
     const size_t stride = mode == BfsMode::Rows ? (size_t)n : (mode == BfsMode::Sums ? 2 : 1);
-    const bool fits = smem_bfs_fits(n, nullptr, nullptr);
     int64_t regime = g_opt.bfs_mode;  // 0 auto, 1 bit-parallel, 2 CTA-per-source
-    if (!fits) regime = 1;
     if (regime == 0) {
         const size_t k = sources.size(), np = std::min<size_t>(8, k);
         std::vector<uint32_t> pilot(np);

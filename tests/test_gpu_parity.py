@@ -521,3 +521,22 @@ def test_average_shortest_path_length(rx, oracle):
                 else:
                     got = rx.unweighted_average_shortest_path_length(g, disconnected=disc)
                 assert (math.isnan(want) and math.isnan(got)) or want == got
+
+
+def test_cta_per_source_with_global_bitmap(rx, oracle):
+    """n > 1.3 M: the visited bitmap no longer fits in shared memory and moves to a per-CTA slab in
+    global memory; results stay bit-exact (grid 1200 x 1200, a few sampled sources)."""
+    from rustworkx_b200 import _lib, device_snapshot
+
+    g = rx.generators.grid_graph(1200, 1200)
+    og = oracle_graph(oracle, g)
+    src = np.array([0, 7, 1199, 720600, 1439999, 333333], dtype=np.uint32)
+    want, _ = og.closeness_partial(src, True, threads=oracle.max_threads())
+    dg = device_snapshot(g)
+    for mode in (0, 2):
+        _lib.set_option("bfs_mode", mode)
+        try:
+            got = dg.closeness_partial(src, True)
+        finally:
+            _lib.set_option("bfs_mode", 0)
+        assert np.array_equal(got, want[src])
