@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librxcuda.so")
+LIB_PATH = os.environ.get("RXCUDA_LIB") or os.path.join(_HERE, "librxcuda.so")
 
 RXC_OK = 0
 RXC_ERR_INVALID = -1

@@ -231,9 +231,17 @@ __device__ __forceinline__ Row4 row_load(const double *rows, uint32_t v, int lan
 // (LDGSTS, 16-byte, L1-bypassing) fetches a lane's 32-byte sector into its own slice of the slot;
 // lanes none of whose four sources needs the arc zero-fill without touching memory.  A lane later
 // reads only bytes it copied itself, so cp.async.wait_all is the only synchronisation needed and
-// up to STAGE KB per warp are in flight without holding registers.
-constexpr int STAGE = 8;
-constexpr int BC_SMEM_BYTES = WARPS * STAGE * BG * 8;  // 64 KB per CTA
+// up to STAGE KB per warp are in flight without holding registers (32 warps/SM x 4 KB = 128 KB).
+// Measured on BA(1M,8), 1024 sources (GTEPS): STAGE 8 x 3 CTAs/SM 169, 4 x 4 176, 4 x 5 172, 4 x 6 162,
+// 2 x 6 165, 2 x 8 148 -- flat: the big launches sit at the random-sector DRAM ceiling (~5.4 TB/s).
+#ifndef RXC_STAGE
+#define RXC_STAGE 4
+#endif
+#ifndef RXC_MINBLOCKS
+#define RXC_MINBLOCKS 4
+#endif
+constexpr int STAGE = RXC_STAGE;
+constexpr int BC_SMEM_BYTES = WARPS * STAGE * BG * 8;  // 32 KB per CTA
 
 __device__ __forceinline__ void cp_async_sector(double *smem_dst, const double *gsrc, bool on) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -342,7 +350,7 @@ __device__ __forceinline__ void bc_fwd_scan(const BcParams &p, const double *row
 // One BFS level for every group of the batch: vertices not yet reached by all 128 sources scan
 // their in-arcs -- the bottom-up form of centrality.rs:427-437.  No early exit: every frontier
 // parent contributes to sigma.
-__global__ void __launch_bounds__(BLOCK) bc_forward_kernel(BcParams p, uint32_t level) {
+__global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) bc_forward_kernel(BcParams p, uint32_t level) {
     const uint32_t g = blockIdx.y;
     uint32_t *lc = p.lvlcnt + (size_t)g * p.lcap;
     uint32_t *lo = p.loff + (size_t)g * p.lcap;
@@ -575,7 +583,7 @@ __device__ __forceinline__ void bc_bwd_scan(const BcParams &p, const double *row
                         todo &= todo - 1;
                         const Mask128 mj = mask_shfl(m, a);
                         const uint32_t ej = __shfl_sync(FULL, ed, a);
-                        if ((lane >> 2) == i) my_e = ej;
+                        if (lane / (32 / STAGE) == i) my_e = ej;
                         const double2 *q = reinterpret_cast<const double2 *>(stage + i * BG + lane * BK);
                         const double2 x0 = q[0], x1 = q[1];
                         const double xs[BK] = {x0.x, x0.y, x1.x, x1.y};
@@ -590,11 +598,12 @@ __device__ __forceinline__ void bc_bwd_scan(const BcParams &p, const double *row
                         dag += mask_popc(mj);
                     }
                 }
-                // reduce the STAGE per-arc sums over the warp at once: after the three halving
-                // exchanges lane l holds arc (l >> 2) & 7, two more steps finish the sum
-                static_assert(STAGE == 8, "the exchange network below is written for 8 values");
+                // reduce the STAGE per-arc sums over the warp at once: log2(STAGE) halving exchanges
+                // leave lane l with arc l / (32/STAGE); the remaining butterfly steps finish the sum
+                static_assert(STAGE == 8 || STAGE == 4 || STAGE == 2, "exchange network: STAGE must be 2, 4 or 8");
+                int off = 16;
 #pragma unroll
-                for (int half = 4, off = 16; half >= 1; half >>= 1, off >>= 1) {
+                for (int half = STAGE / 2; half >= 1; half >>= 1, off >>= 1) {
                     const bool upper = lane & off;
 #pragma unroll
                     for (int j = 0; j < half; j++) {
@@ -604,9 +613,9 @@ __device__ __forceinline__ void bc_bwd_scan(const BcParams &p, const double *row
                     }
                 }
                 double tot = c[0];
-                tot += __shfl_xor_sync(FULL, tot, 2);
-                tot += __shfl_xor_sync(FULL, tot, 1);
-                if ((lane & 3) == 0 && (lane >> 2) < cnt) atomicAdd(&p.acc[my_e], tot);
+#pragma unroll
+                for (; off >= 1; off >>= 1) tot += __shfl_xor_sync(FULL, tot, off);
+                if (lane % (32 / STAGE) == 0 && lane / (32 / STAGE) < cnt) atomicAdd(&p.acc[my_e], tot);
             }
         }
     }
@@ -640,7 +649,7 @@ __device__ __forceinline__ void bc_bwd_finish(const BcParams &p, uint32_t v, con
 // which regroups centrality.rs:272-279 by predecessor (pull instead of push; no f64 atomics on the
 // rows).  The row of v is then overwritten with (1+delta)/sigma for the level above to pull.
 template <bool EDGE, bool ENDPOINTS>
-__global__ void __launch_bounds__(BLOCK) bc_backward_kernel(BcParams p, uint32_t level) {
+__global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) bc_backward_kernel(BcParams p, uint32_t level) {
     const uint32_t g = blockIdx.y;
     if (blockIdx.x == 0 && threadIdx.x == 0) *bc_hubcnt(p, level + 1, g) = 0;  // for the next launch
     const uint32_t cnt = p.lvlcnt[(size_t)g * p.lcap + level];

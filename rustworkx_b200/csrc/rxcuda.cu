@@ -479,7 +479,7 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
     // bytes per group: 1 KB row + worst-case queues + two tagged mask arrays + visited + level tables
     const double per_group = (double)n * (1024.0 + 20.0 * BG + 64.0 + 16.0) + (double)lcap * 8.0 + 4096.0;
     uint64_t ng = g_opt.bc_groups > 0 ? (uint64_t)g_opt.bc_groups
-                                      : std::max<uint64_t>(1, (2ull << 20) / std::max<uint32_t>(n, 1));
+                                      : std::max<uint64_t>(1, (8ull << 20) / std::max<uint32_t>(n, 1));
     ng = std::min<uint64_t>(ng, 64);
     ng = std::min<uint64_t>(ng, total_groups);
 
