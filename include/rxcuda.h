@@ -67,6 +67,10 @@ const char *rxc_last_error(void);
 int rxc_device_count(void);       /* 0 when no CUDA device is usable */
 int rxc_set_device(int device);   /* device used by subsequent rxc_graph_snapshot calls */
 int rxc_get_device(void);
+/* In-process multi-GPU: subsequent snapshots replicate the CSR on every listed device and the full
+ * calls (rxc_betweenness, ..._edge_betweenness, ..._closeness, ..._distance_matrix*, ..._distance_sums)
+ * shard the live sources over them, one host thread per device.  n = 0 returns to single-device. */
+int rxc_set_devices(const int *devices, int n);
 
 /* ---- snapshot: StableGraph -> compact int32 CSR/CSC in HBM ---------------------------------------
  * live_nodes[n_live]: ascending original indices of live nodes (PyGraph.node_indices()).

@@ -19,7 +19,7 @@ import functools
 import numpy as np
 
 from . import generators  # noqa: F401
-from ._lib import DeviceGraph, RxCudaError  # noqa: F401
+from ._lib import DeviceGraph, RxCudaError, set_devices  # noqa: F401
 from .graph import (  # noqa: F401
     EdgeIndices,
     EdgeList,

@@ -59,6 +59,7 @@ SYMBOLS = {
     "rxc_device_count": (C.c_int, []),
     "rxc_set_device": (C.c_int, [C.c_int]),
     "rxc_get_device": (C.c_int, []),
+    "rxc_set_devices": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
     "rxc_graph_snapshot": (C.c_int, [C.c_uint32, _u32p, C.c_uint32, C.c_uint32, _u32p, _u32p, _u32p,
                                      C.c_uint64, C.c_int, C.POINTER(_vp)]),
     "rxc_graph_free": (None, [_vp]),
@@ -108,6 +109,9 @@ def lib():
         fn.restype = restype
         fn.argtypes = argtypes
     _lib = L
+    env = os.environ.get("RXCUDA_DEVICES")
+    if env:
+        set_devices("all" if env.strip().lower() == "all" else [int(x) for x in env.split(",") if x.strip()])
     return L
 
 
@@ -138,6 +142,16 @@ def device_count():
 
 def set_device(device):
     check(lib().rxc_set_device(int(device)))
+
+
+def set_devices(devices):
+    """In-process multi-GPU: replicate later snapshots on these devices and shard full calls over
+    them ([] or None: back to the single current device; "all": every visible device)."""
+    if devices == "all":
+        devices = list(range(device_count()))
+    devices = list(devices or [])
+    arr = (C.c_int * max(len(devices), 1))(*devices)
+    check(lib().rxc_set_devices(arr, len(devices)))
 
 
 def set_option(name, value):

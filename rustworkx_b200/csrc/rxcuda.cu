@@ -11,7 +11,10 @@
 
 #include <algorithm>
 #include <chrono>
+#include <exception>
+#include <memory>
 #include <mutex>
+#include <thread>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -110,6 +113,7 @@ constexpr uint32_t HUB_CAP = 4096;  // deferred high-degree work items per group
 constexpr uint32_t HUB_CTAS = 32;   // CTAs per group in the hub kernels
 constexpr uint32_t MARK_CTAS = 64;  // CTAs per group in the frontier-marking kernel
 static int g_device = 0;
+static std::vector<int> g_devices;  // rxc_set_devices: replicas for in-process multi-GPU (empty: single)
 
 static double now_ms() {
     using namespace std::chrono;
@@ -172,6 +176,7 @@ struct rxc_graph {
     BcWorkspace bc_ws;
     BfsWorkspace bfs_ws;
     DevBuf<double> acc_buf;  // partial centrality vector of the current call
+    std::vector<std::unique_ptr<rxc_graph>> replicas;  // same snapshot on the other devices of rxc_set_devices
     std::mutex mu;
 
     const DeviceCSR &succ() const { return out; }
@@ -257,11 +262,13 @@ static void device_scan(const uint32_t *in, uint32_t *out_row, uint32_t n, DevBu
 static void device_sort_rows(DeviceCSR &csr, uint32_t n, DevBuf<uint32_t> &long_rows,
                              uint32_t *d_nlong, cudaStream_t st) {
     if (n == 0 || !csr.eid.p) return;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {false};  // function attributes are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_done[dev & 63]) {
         RXC_CUDA(cudaFuncSetAttribute(csr_sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(CSR_SORT_MAX * 8)));
-        attr_done = true;
+        attr_done[dev & 63] = true;
     }
     RXC_CUDA(cudaMemsetAsync(d_nlong, 0, 4, st));
     csr_sort_rows_kernel<<<(n + WARPS - 1) / WARPS, BLOCK, 0, st>>>(csr.row.p, n, csr.col.p, csr.eid.p,
@@ -454,7 +461,10 @@ static uint32_t run_levels(rxc_graph *g, uint32_t *d_lvl_total, uint32_t n, F &&
 // betweenness (node / edge)
 // ------------------------------------------------------------------------------------------------
 static void bc_enable_smem() {
-    static bool done = false;
+    static bool done_dev[64] = {false};  // function attributes are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool &done = done_dev[dev & 63];
     if (done) return;
     const int b = BC_SMEM_BYTES;
     RXC_CUDA(cudaFuncSetAttribute(bc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
@@ -870,7 +880,8 @@ static void bfs_smem_run(rxc_graph *g, const DeviceCSR &csr, const uint32_t *sou
     using KernelT = void (*)(SmemBfsParams);
     const KernelT kernel = rows_mode ? (gbm ? bfs_smem_kernel<true, true> : bfs_smem_kernel<true, false>)
                                      : (gbm ? bfs_smem_kernel<false, true> : bfs_smem_kernel<false, false>);
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {false};  // function attributes are per device
+    bool &attr_done = attr_done_dev[g->device & 63];
     if (!attr_done) {
         const KernelT all[4] = {bfs_smem_kernel<false, false>, bfs_smem_kernel<false, true>,
                                 bfs_smem_kernel<true, false>, bfs_smem_kernel<true, true>};
@@ -1021,6 +1032,80 @@ static const DeviceCSR &symmetric_csr(rxc_graph *g) {
     return g->sym;
 }
 
+// ------------------------------------------------------------------------------------------------
+// in-process multi-GPU: the handle carries one replica of the snapshot per extra device
+// (rxc_set_devices).  Full calls shard the live sources round-robin over the replicas, one host
+// thread per device; partial vectors are summed on the host (8 MB at config 3 -- the one-process-
+// per-GPU mode uses ncclReduce instead, comm.cpp).  Disjoint outputs need no reduction.
+// ------------------------------------------------------------------------------------------------
+static std::vector<rxc_graph *> shards_of(rxc_graph *g) {
+    std::vector<rxc_graph *> v{g};
+    for (auto &r : g->replicas) v.push_back(r.get());
+    return v;
+}
+
+template <class F>
+static void run_on_shards(rxc_graph *g, F &&fn) {
+    const std::vector<rxc_graph *> sh = shards_of(g);
+    if (sh.size() == 1) {
+        fn(sh[0], 0, 1);
+        return;
+    }
+    std::vector<std::exception_ptr> errs(sh.size());
+    std::vector<std::thread> threads;
+    for (size_t k = 0; k < sh.size(); k++)
+        threads.emplace_back([&, k] {
+            try {
+                RXC_CUDA(cudaSetDevice(sh[k]->device));
+                fn(sh[k], k, sh.size());
+            } catch (...) {
+                errs[k] = std::current_exception();
+            }
+        });
+    for (auto &t : threads) t.join();
+    cudaSetDevice(g->device);
+    // counters of the call: work adds up, device time is the slowest shard
+    for (size_t k = 1; k < sh.size(); k++) {
+        const rxc_stats &r = sh[k]->stats;
+        rxc_stats &a = g->stats;
+        a.te += r.te; a.te_dag += r.te_dag; a.v += r.v; a.sources += r.sources;
+        a.levels += r.levels; a.launches += r.launches; a.batches += r.batches;
+        a.ms_total = std::max(a.ms_total, r.ms_total);
+        a.ms_forward = std::max(a.ms_forward, r.ms_forward);
+        a.ms_backward = std::max(a.ms_backward, r.ms_backward);
+        a.ms_d2h = std::max(a.ms_d2h, r.ms_d2h);
+    }
+    for (auto &e : errs)
+        if (e) std::rethrow_exception(e);
+}
+
+static std::vector<uint32_t> shard_sources(uint32_t n_live, size_t k, size_t K) {
+    std::vector<uint32_t> s;
+    s.reserve(n_live / K + 1);
+    for (uint32_t i = (uint32_t)k; i < n_live; i += (uint32_t)K) s.push_back(i);
+    return s;
+}
+
+// all live sources, un-rescaled, into out (original indexing)
+static void bc_full(rxc_graph *g, bool endpoints, bool edge_mode, double *out) {
+    const size_t out_len = edge_mode ? g->host.e_bound : g->host.n_bound;
+    const size_t K = 1 + g->replicas.size();
+    if (K == 1) {
+        bc_partial(g, all_sources(g), endpoints, edge_mode, out);
+        return;
+    }
+    std::vector<std::vector<double>> parts(K);
+    run_on_shards(g, [&](rxc_graph *r, size_t k, size_t nk) {
+        parts[k].assign(std::max<size_t>(out_len, 1), 0.0);
+        bc_partial(r, shard_sources(r->host.n_live, k, nk), endpoints, edge_mode, parts[k].data());
+    });
+    for (size_t i = 0; i < out_len; i++) {
+        double sum = 0.0;
+        for (size_t k = 0; k < K; k++) sum += parts[k][i];  // fixed order: deterministic
+        out[i] = sum;
+    }
+}
+
 }  // namespace rxc
 
 // ================================================================================================
@@ -1050,6 +1135,57 @@ int rxc_set_device(int device) {
 
 int rxc_get_device(void) { return g_device; }
 
+int rxc_set_devices(const int *devices, int n) {
+    return guarded([&] {
+        require_device();
+        int cnt = 0;
+        RXC_CUDA(cudaGetDeviceCount(&cnt));
+        std::vector<int> v;
+        for (int i = 0; i < n; i++) {
+            if (!devices || devices[i] < 0 || devices[i] >= cnt)
+                throw std::invalid_argument("device id out of range");
+            if (std::find(v.begin(), v.end(), devices[i]) != v.end())
+                throw std::invalid_argument("duplicate device id");
+            v.push_back(devices[i]);
+        }
+        g_devices = v;
+        if (!v.empty()) {
+            RXC_CUDA(cudaSetDevice(v[0]));
+            g_device = v[0];
+        }
+    });
+}
+
+// one snapshot on one device
+static rxc_graph *snapshot_on(int device, uint32_t n_bound, const uint32_t *live_nodes, uint32_t n_live,
+                              uint32_t e_bound, const uint32_t *edge_src, const uint32_t *edge_dst,
+                              const uint32_t *edge_id, uint64_t n_edges, bool directed) {
+    const double t0 = now_ms();
+    std::unique_ptr<rxc_graph> g(new rxc_graph());
+    g->device = device;
+    RXC_CUDA(cudaSetDevice(device));
+    pool_setup(device);
+    RXC_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+    for (auto &e : g->ev) RXC_CUDA(cudaEventCreate(&e));
+    if (g_opt.device_csr) {
+        device_snapshot(g.get(), n_bound, live_nodes, n_live, e_bound, edge_src, edge_dst, edge_id,
+                        n_edges, directed);
+    } else {
+        g->host = make_snapshot(n_bound, live_nodes, n_live, e_bound, edge_src, edge_dst, edge_id,
+                                n_edges, directed);
+        g->out.upload(g->host.out, g->stream);
+        if (g->host.directed) g->in.upload(g->host.in, g->stream);
+        g->n_arcs = g->host.out.col.size();
+    }
+    g->d_stats.alloc(ST_COUNT);
+    RXC_CUDA(cudaMemsetAsync(g->d_stats.p, 0, g->d_stats.bytes(), g->stream));
+    RXC_CUDA(cudaStreamSynchronize(g->stream));
+    memset(&g->stats, 0, sizeof(g->stats));
+    g->ms_snapshot = now_ms() - t0;
+    g->stats.ms_snapshot = g->ms_snapshot;
+    return g.release();
+}
+
 int rxc_graph_snapshot(uint32_t n_bound, const uint32_t *live_nodes, uint32_t n_live,
                        uint32_t e_bound, const uint32_t *edge_src, const uint32_t *edge_dst,
                        const uint32_t *edge_id, uint64_t n_edges, int directed,
@@ -1062,26 +1198,14 @@ int rxc_graph_snapshot(uint32_t n_bound, const uint32_t *live_nodes, uint32_t n_
             throw std::invalid_argument("null array");
         require_device();
         const double t0 = now_ms();
-        g = new rxc_graph();
-        g->device = g_device;
+        // primary on the first device; with rxc_set_devices the CSR is replicated on the others
+        const std::vector<int> devs = g_devices.empty() ? std::vector<int>{g_device} : g_devices;
+        g = snapshot_on(devs[0], n_bound, live_nodes, n_live, e_bound, edge_src, edge_dst, edge_id,
+                        n_edges, directed != 0);
+        for (size_t d = 1; d < devs.size(); d++)
+            g->replicas.emplace_back(snapshot_on(devs[d], n_bound, live_nodes, n_live, e_bound, edge_src,
+                                                 edge_dst, edge_id, n_edges, directed != 0));
         RXC_CUDA(cudaSetDevice(g->device));
-        pool_setup(g->device);
-        RXC_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
-        for (auto &e : g->ev) RXC_CUDA(cudaEventCreate(&e));
-        if (g_opt.device_csr) {
-            device_snapshot(g, n_bound, live_nodes, n_live, e_bound, edge_src, edge_dst, edge_id,
-                            n_edges, directed != 0);
-        } else {
-            g->host = make_snapshot(n_bound, live_nodes, n_live, e_bound, edge_src, edge_dst, edge_id,
-                                    n_edges, directed != 0);
-            g->out.upload(g->host.out, g->stream);
-            if (g->host.directed) g->in.upload(g->host.in, g->stream);
-            g->n_arcs = g->host.out.col.size();
-        }
-        g->d_stats.alloc(ST_COUNT);
-        RXC_CUDA(cudaMemsetAsync(g->d_stats.p, 0, g->d_stats.bytes(), g->stream));
-        RXC_CUDA(cudaStreamSynchronize(g->stream));
-        memset(&g->stats, 0, sizeof(g->stats));
         g->ms_snapshot = now_ms() - t0;
         g->stats.ms_snapshot = g->ms_snapshot;
     });
@@ -1144,7 +1268,7 @@ int rxc_edge_betweenness_partial(rxc_graph *g, const uint32_t *sources, uint64_t
 int rxc_betweenness(rxc_graph *g, int include_endpoints, int normalized, double *out) {
     if (!g || !out) return RXC_ERR_INVALID;
     return guarded([&] {
-        bc_partial(g, all_sources(g), include_endpoints != 0, false, out);
+        bc_full(g, include_endpoints != 0, false, out);
         rxc_rescale(out, g->host.n_bound, g->host.n_live, normalized, g->host.directed ? 1 : 0,
                     include_endpoints);
     });
@@ -1153,7 +1277,7 @@ int rxc_betweenness(rxc_graph *g, int include_endpoints, int normalized, double 
 int rxc_edge_betweenness(rxc_graph *g, int normalized, double *out) {
     if (!g || !out) return RXC_ERR_INVALID;
     return guarded([&] {
-        bc_partial(g, all_sources(g), false, true, out);
+        bc_full(g, false, true, out);
         rxc_rescale(out, g->host.e_bound, g->host.n_live, normalized, g->host.directed ? 1 : 0, 1);
     });
 }
@@ -1175,14 +1299,18 @@ int rxc_closeness_partial(rxc_graph *g, const uint32_t *sources, uint64_t n_sour
 int rxc_closeness(rxc_graph *g, int wf_improved, double *out) {
     if (!g || !out) return RXC_ERR_INVALID;
     return guarded([&] {
-        std::lock_guard<std::mutex> lock(g->mu);
-        begin_call(g);
         std::fill(out, out + g->host.n_bound, 0.0);
-        std::vector<double> vals(g->host.n_live);
-        bfs_dispatch(g, g->pred(), all_sources(g), BfsMode::Closeness, wf_improved != 0, 0.0, vals.data());
-        end_call(g);
-        for (uint32_t i = 0; i < g->host.n_live; i++) out[g->host.orig_of_compact[i]] = vals[i];
-        fetch_stats(g);
+        run_on_shards(g, [&](rxc_graph *r, size_t k, size_t nk) {
+            std::lock_guard<std::mutex> lock(r->mu);
+            begin_call(r);
+            const std::vector<uint32_t> src = shard_sources(r->host.n_live, k, nk);
+            std::vector<double> vals(src.size());
+            // closeness follows incoming edges: BFS over Reversed(&graph), centrality.rs:1208
+            bfs_dispatch(r, r->pred(), src, BfsMode::Closeness, wf_improved != 0, 0.0, vals.data());
+            end_call(r);
+            for (size_t i = 0; i < src.size(); i++) out[r->host.orig_of_compact[src[i]]] = vals[i];
+            fetch_stats(r);
+        });
     });
 }
 
@@ -1192,15 +1320,21 @@ int rxc_distance_matrix_rows(rxc_graph *g, int as_undirected, double null_value,
     return guarded([&] {
         if (row_begin > row_end || row_end > g->host.n_live)
             throw std::invalid_argument("row range outside [0, n_live]");
-        std::lock_guard<std::mutex> lock(g->mu);
-        begin_call(g);
-        std::vector<uint32_t> src(row_end - row_begin);
-        for (uint32_t i = row_begin; i < row_end; i++) src[i - row_begin] = i;
-        // graph_distance_matrix always passes as_undirected=true (src/shortest_path/mod.rs:1610)
-        const DeviceCSR &csr = (as_undirected || !g->host.directed) ? symmetric_csr(g) : g->out;
-        bfs_dispatch(g, csr, src, BfsMode::Rows, false, null_value, out);
-        end_call(g);
-        fetch_stats(g);
+        // every shard fills a contiguous block of rows of the caller's matrix
+        run_on_shards(g, [&](rxc_graph *r, size_t k, size_t nk) {
+            const uint64_t rows = row_end - row_begin;
+            const uint32_t b = row_begin + (uint32_t)(rows * k / nk), e = row_begin + (uint32_t)(rows * (k + 1) / nk);
+            std::lock_guard<std::mutex> lock(r->mu);
+            begin_call(r);
+            std::vector<uint32_t> src(e - b);
+            for (uint32_t i = b; i < e; i++) src[i - b] = i;
+            // graph_distance_matrix always passes as_undirected=true (src/shortest_path/mod.rs:1610)
+            const DeviceCSR &csr = (as_undirected || !r->host.directed) ? symmetric_csr(r) : r->out;
+            bfs_dispatch(r, csr, src, BfsMode::Rows, false, null_value,
+                         out + (size_t)(b - row_begin) * r->host.n_live);
+            end_call(r);
+            fetch_stats(r);
+        });
     });
 }
 
@@ -1208,22 +1342,30 @@ int rxc_distance_sums(rxc_graph *g, int as_undirected, uint64_t *total_distance,
                       uint64_t *connected_pairs) {
     if (!g || !total_distance || !connected_pairs) return RXC_ERR_INVALID;
     return guarded([&] {
-        std::lock_guard<std::mutex> lock(g->mu);
-        begin_call(g);
-        const uint32_t n = g->host.n_live;
-        std::vector<double> vals((size_t)n * 2);
-        // outgoing neighbours; both directions for an undirected graph or as_undirected
-        const DeviceCSR &csr = (as_undirected || !g->host.directed) ? symmetric_csr(g) : g->out;
-        bfs_dispatch(g, csr, all_sources(g), BfsMode::Sums, false, 0.0, vals.data());
-        end_call(g);
-        fetch_stats(g);
-        uint64_t sum = 0, pairs = 0;
-        for (uint32_t i = 0; i < n; i++) {
-            pairs += (uint64_t)vals[2 * (size_t)i] - 1;
-            sum += (uint64_t)vals[2 * (size_t)i + 1];
+        const size_t K = 1 + g->replicas.size();
+        std::vector<uint64_t> sums(K, 0), pairs(K, 0);
+        run_on_shards(g, [&](rxc_graph *r, size_t k, size_t nk) {
+            std::lock_guard<std::mutex> lock(r->mu);
+            begin_call(r);
+            const std::vector<uint32_t> src = shard_sources(r->host.n_live, k, nk);
+            std::vector<double> vals(src.size() * 2);
+            // outgoing neighbours; both directions for an undirected graph or as_undirected
+            const DeviceCSR &csr = (as_undirected || !r->host.directed) ? symmetric_csr(r) : r->out;
+            bfs_dispatch(r, csr, src, BfsMode::Sums, false, 0.0, vals.data());
+            end_call(r);
+            fetch_stats(r);
+            for (size_t i = 0; i < src.size(); i++) {
+                pairs[k] += (uint64_t)vals[2 * i] - 1;
+                sums[k] += (uint64_t)vals[2 * i + 1];
+            }
+        });
+        uint64_t sum = 0, prs = 0;
+        for (size_t k = 0; k < K; k++) {
+            sum += sums[k];
+            prs += pairs[k];
         }
         *total_distance = sum;
-        *connected_pairs = pairs;
+        *connected_pairs = prs;
     });
 }
 

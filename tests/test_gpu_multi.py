@@ -53,3 +53,38 @@ def test_two_rank_nccl_betweenness(tmp_path):
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert proc.returncode == 0, proc.stdout[-3000:]
     assert "NCCL_OK" in proc.stdout
+
+
+def test_in_process_replicas(oracle):
+    """rxc_set_devices: one process, the snapshot replicated on two GPUs, full calls sharded over
+    them with one host thread per device -- same results as the single-device path / the oracle."""
+    import numpy as np
+
+    import rustworkx_b200 as rx
+    from rustworkx_b200 import _lib
+
+    if _lib.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rx.set_devices([0, 1])
+    try:
+        g = rx.barabasi_albert_graph(6000, 5, seed=4)
+        g.remove_node(11)
+        og = oracle.OracleGraph.from_graph(g)
+        want, _ = og.betweenness_centrality(True, True, 50, as_arrays=True)
+        got = rx.betweenness_centrality(g, endpoints=True)
+        keys = np.array(list(got.keys()))
+        assert np.allclose(np.array(list(got.values())), want[keys], rtol=1e-9, atol=1e-12)
+        st = rx.device_snapshot(g).stats()
+        assert st["sources"] == g.num_nodes() and st["batches"] >= 2  # both shards worked
+        want_e, _ = og.edge_betweenness_centrality(False, 50, as_arrays=True)
+        got_e = rx.edge_betweenness_centrality(g, normalized=False)
+        assert np.allclose(np.array(list(got_e.values())), want_e[np.array(list(got_e.keys()))],
+                           rtol=1e-9, atol=1e-12)
+        want_c, _ = og.closeness_centrality(True, 50, as_arrays=True)
+        assert np.array_equal(np.array(list(rx.closeness_centrality(g).values())), want_c[keys])
+        h = rx.generators.heavy_hex_graph(9)
+        oh = oracle.OracleGraph.from_graph(h)
+        assert np.array_equal(rx.distance_matrix(h, null_value=-1.0), oh.distance_matrix(300, True, -1.0))
+        assert rx.unweighted_average_shortest_path_length(h) == oh.average_shortest_path_length(300, True, False)
+    finally:
+        rx.set_devices([])
