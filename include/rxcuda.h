@@ -100,6 +100,19 @@ int rxc_distance_matrix(rxc_graph *g, int as_undirected, double null_value,
 int rxc_distance_sums(rxc_graph *g, int as_undirected, uint64_t *total_distance,
                       uint64_t *connected_pairs);
 
+/* group centralities.  `group` holds ORIGINAL indices of live nodes (anything else is
+ * RXC_ERR_INVALID -- the binding raises ValueError, src/centrality.rs:1216-1222,1263-1269,1318-1324,
+ * 1371-1377); duplicates count once.
+ *   rxc_group_betweenness <- rustworkx-core/src/centrality.rs:1963-2101 group_betweenness_centrality
+ *   rxc_group_closeness   <- rustworkx-core/src/centrality.rs:1860-1916 group_closeness_centrality */
+int rxc_group_betweenness(rxc_graph *g, const uint32_t *group, uint64_t n_group, int normalized,
+                          double *out /* 1 */);
+int rxc_group_closeness(rxc_graph *g, const uint32_t *group, uint64_t n_group, double *out /* 1 */);
+/* the per-source sums of centrality.rs:1985-2080 over a subset of sources (members of the group are
+ * skipped), before the /2 of undirected graphs and the normalisation; additive over source shards */
+int rxc_group_betweenness_partial(rxc_graph *g, const uint32_t *group, uint64_t n_group,
+                                  const uint32_t *sources, uint64_t n_sources, double *out_sum);
+
 /* ---- partial calls: a subset of sources (ORIGINAL node indices), no final scaling.  This is the
  * unit a rank runs when sources are sharded across GPUs; partial vectors are additive.
  * `out` is zero-initialised by the call. ----------------------------------------------------------- */

@@ -89,6 +89,12 @@ def lib():
     L.rxo_average_shortest_path_length.restype = C.c_double
     L.rxo_average_shortest_path_length.argtypes = [vp, C.c_size_t, C.c_int, C.c_int]
     L.rxo_distance_sum.argtypes = [vp, C.c_size_t, C.c_int, u64p, u64p]
+    L.rxo_group_closeness_centrality.restype = C.c_double
+    L.rxo_group_closeness_centrality.argtypes = [vp, u32p, C.c_size_t]
+    L.rxo_group_betweenness_centrality.restype = C.c_double
+    L.rxo_group_betweenness_centrality.argtypes = [vp, u32p, C.c_size_t, C.c_int, C.c_size_t]
+    L.rxo_group_betweenness_partial.restype = C.c_double
+    L.rxo_group_betweenness_partial.argtypes = [vp, u32p, C.c_size_t, u32p, C.c_size_t, C.c_int, sp]
     L.rxo_rescale.argtypes = [f64p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int]
     L.rxo_max_threads.restype = C.c_int
     _lib = L
@@ -255,6 +261,25 @@ class OracleGraph:
         self._L.rxo_distance_sum(self._h, int(parallel_threshold), int(as_undirected),
                                  C.byref(a), C.byref(b))
         return int(a.value), int(b.value)
+
+    # -- group centralities ------------------------------------------------------
+    def group_closeness_centrality(self, group):
+        grp = np.ascontiguousarray(group, dtype=np.uint32)
+        return float(self._L.rxo_group_closeness_centrality(self._h, _p(grp, C.c_uint32), grp.shape[0]))
+
+    def group_betweenness_centrality(self, group, normalized=True, parallel_threshold=50):
+        grp = np.ascontiguousarray(group, dtype=np.uint32)
+        return float(self._L.rxo_group_betweenness_centrality(
+            self._h, _p(grp, C.c_uint32), grp.shape[0], int(normalized), int(parallel_threshold)))
+
+    def group_betweenness_partial(self, group, sources, threads=1):
+        grp = np.ascontiguousarray(group, dtype=np.uint32)
+        src = np.ascontiguousarray(sources, dtype=np.uint32)
+        st = Stats()
+        val = float(self._L.rxo_group_betweenness_partial(
+            self._h, _p(grp, C.c_uint32), grp.shape[0], _p(src, C.c_uint32), src.shape[0],
+            int(threads), C.byref(st)))
+        return val, st.as_dict()
 
     # -- partial (source subset, un-rescaled) --------------------------------------------------
     def betweenness_partial(self, sources, include_endpoints=False, threads=1):

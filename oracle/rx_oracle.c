@@ -849,3 +849,222 @@ void rxo_distance_matrix(const rxo_graph *g, size_t parallel_threshold, int as_u
     free(node_map);
     free(node_map_inv);
 }
+
+/* ------------------------------------------------------------------ */
+/* group centralities                                   */
+/* ------------------------------------------------------------------ */
+
+/* Adjacency cursor.  rev=0: graph.neighbors(v) -- the outgoing list, then (undirected only) the
+ * incoming list with self-loops skipped.  rev=1: Reversed(&graph).edges(v) -- the incoming list of a
+ * directed graph; every incident edge of an undirected one. */
+typedef struct {
+    const rxo_graph *g;
+    uint32_t v, e;
+    int phase; /* 0: first list, 1: second list, 2: done */
+    int rev;
+} rxo_cursor;
+
+static void rxo_cursor_init(rxo_cursor *c, const rxo_graph *g, uint32_t v, int rev) {
+    c->g = g;
+    c->v = v;
+    c->rev = rev;
+    if (g->directed) {
+        c->phase = 1; /* a single list */
+        c->e = g->nodes[v].next[rev ? 1 : 0];
+    } else {
+        c->phase = 0;
+        c->e = g->nodes[v].next[0];
+    }
+}
+
+static int rxo_cursor_next(rxo_cursor *c, uint32_t *w) {
+    const rxo_graph *g = c->g;
+    for (;;) {
+        if (c->e == RXO_END) {
+            if (c->phase == 0) {
+                c->phase = 1;
+                c->e = g->nodes[c->v].next[1];
+                continue;
+            }
+            return 0;
+        }
+        const rxo_edge_t *ed = &g->edges[c->e];
+        if (g->directed) {
+            const int k = c->rev ? 1 : 0;
+            *w = ed->node[1 - k];
+            c->e = ed->next[k];
+            return 1;
+        }
+        if (c->phase == 0) {
+            *w = ed->node[1];
+            c->e = ed->next[0];
+            return 1;
+        }
+        c->e = ed->next[1];
+        if (ed->node[0] == c->v) continue; /* self-loop: already seen in the outgoing list */
+        *w = ed->node[0];
+        return 1;
+    }
+}
+
+/* group_set: HashSet<usize> of the group, as a dense flag array; returns its size */
+static size_t rxo_group_flags(const rxo_graph *g, const uint32_t *group, size_t k, uint8_t **flags) {
+    size_t max_index = rxo_node_bound(g);
+    size_t top = max_index;
+    for (size_t i = 0; i < k; i++)
+        if ((size_t)group[i] + 1 > top) top = (size_t)group[i] + 1;
+    uint8_t *f = (uint8_t *)calloc(top ? top : 1, 1);
+    size_t sz = 0;
+    for (size_t i = 0; i < k; i++)
+        if (!f[group[i]]) {
+            f[group[i]] = 1;
+            sz++;
+        }
+    *flags = f;
+    return sz;
+}
+
+/* group_closeness_centrality, centrality.rs:1860-1916: one multi-source BFS over Reversed(&graph) */
+double rxo_group_closeness_centrality(const rxo_graph *g, const uint32_t *group, size_t k) {
+    size_t node_count = g->node_count;
+    uint8_t *in_group;
+    size_t group_size = rxo_group_flags(g, group, k, &in_group);
+    if (group_size >= node_count) {
+        free(in_group);
+        return 0.0;
+    }
+    size_t max_index = rxo_node_bound(g);
+    size_t *distance = (size_t *)malloc((max_index ? max_index : 1) * sizeof(size_t));
+    for (size_t i = 0; i < max_index; i++) distance[i] = RXO_NONE;
+    uint32_t *Q = (uint32_t *)malloc((node_count ? node_count : 1) * sizeof(uint32_t));
+    size_t qh = 0, qt = 0;
+    for (size_t i = 0; i < max_index; i++) /* iteration order of the set does not affect distances */
+        if (in_group[i]) {
+            distance[i] = 0;
+            Q[qt++] = (uint32_t)i;
+        }
+    while (qh < qt) {
+        uint32_t v = Q[qh++];
+        size_t dist_v = distance[v];
+        rxo_cursor c;
+        uint32_t w;
+        rxo_cursor_init(&c, g, v, 1);
+        while (rxo_cursor_next(&c, &w)) {
+            if (distance[w] == RXO_NONE) {
+                distance[w] = dist_v + 1;
+                Q[qt++] = w;
+            }
+        }
+    }
+    size_t dist_sum = 0;
+    for (size_t i = 0; i < max_index; i++) {
+        if (!g->nodes[i].alive || in_group[i]) continue;
+        if (distance[i] != RXO_NONE) dist_sum += distance[i];
+    }
+    free(distance);
+    free(Q);
+    free(in_group);
+    if (dist_sum == 0) return 0.0;
+    return (double)(node_count - group_size) / (double)dist_sum;
+}
+
+/* BFS with path counts from s; `blocked` (may be NULL) removes vertices (centrality.rs:1994-2044) */
+static uint64_t rxo_group_bfs(const rxo_graph *g, uint32_t s, const uint8_t *blocked, double *sigma,
+                              size_t *dist, uint32_t *Q, size_t max_index, uint64_t *reached) {
+    for (size_t i = 0; i < max_index; i++) {
+        sigma[i] = 0.0;
+        dist[i] = RXO_NONE;
+    }
+    size_t qh = 0, qt = 0;
+    uint64_t te = 0;
+    sigma[s] = 1.0;
+    dist[s] = 0;
+    Q[qt++] = s;
+    while (qh < qt) {
+        uint32_t v = Q[qh++];
+        size_t dist_v = dist[v];
+        rxo_cursor c;
+        uint32_t w;
+        rxo_cursor_init(&c, g, v, 0);
+        while (rxo_cursor_next(&c, &w)) {
+            te++;
+            if (blocked && blocked[w]) continue;
+            if (dist[w] == RXO_NONE) {
+                dist[w] = dist_v + 1;
+                Q[qt++] = w;
+            }
+            if (dist[w] == dist_v + 1) sigma[w] += sigma[v];
+        }
+    }
+    *reached = qt;
+    return te;
+}
+
+/* Sum over the listed non-group sources of sum_t (sigma_full - paths_avoiding)/sigma_full
+ * (centrality.rs:1985-2080), before the /2 and the normalisation. */
+double rxo_group_betweenness_partial(const rxo_graph *g, const uint32_t *group, size_t k,
+                                     const uint32_t *sources, size_t n_sources, int threads,
+                                     rxo_stats *stats) {
+    size_t max_index = rxo_node_bound(g);
+    uint8_t *in_group;
+    (void)rxo_group_flags(g, group, k, &in_group);
+    if (stats) memset(stats, 0, sizeof(*stats));
+    double total = 0.0;
+    long kk = (long)n_sources;
+    (void)threads;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads) if (threads > 1) reduction(+ : total)
+    for (long i = 0; i < kk; i++) {
+        uint32_t s = sources[i];
+        if (in_group[s]) continue;
+        size_t m = max_index ? max_index : 1;
+        double *sigma_full = (double *)malloc(m * sizeof(double));
+        double *sigma_no_group = (double *)malloc(m * sizeof(double));
+        size_t *dist_full = (size_t *)malloc(m * sizeof(size_t));
+        size_t *dist_no_group = (size_t *)malloc(m * sizeof(size_t));
+        uint32_t *Q = (uint32_t *)malloc((g->node_count ? g->node_count : 1) * sizeof(uint32_t));
+        uint64_t r1, r2;
+        uint64_t te = rxo_group_bfs(g, s, NULL, sigma_full, dist_full, Q, max_index, &r1);
+        te += rxo_group_bfs(g, s, in_group, sigma_no_group, dist_no_group, Q, max_index, &r2);
+        double source_group_betweenness = 0.0;
+        for (size_t t = 0; t < max_index; t++) {
+            if (!g->nodes[t].alive || t == s || in_group[t]) continue;
+            if (sigma_full[t] == 0.0) continue;
+            double paths_avoiding = (dist_no_group[t] == dist_full[t]) ? sigma_no_group[t] : 0.0;
+            source_group_betweenness += (sigma_full[t] - paths_avoiding) / sigma_full[t];
+        }
+        total += source_group_betweenness;
+        rxo_stats_add(stats, te, 0, r1 + r2, 0);
+        free(sigma_full);
+        free(sigma_no_group);
+        free(dist_full);
+        free(dist_no_group);
+        free(Q);
+    }
+    free(in_group);
+    return total;
+}
+
+/* group_betweenness_centrality, centrality.rs:1963-2101 */
+double rxo_group_betweenness_centrality(const rxo_graph *g, const uint32_t *group, size_t k,
+                                        int normalized, size_t parallel_threshold) {
+    size_t node_count = g->node_count;
+    uint8_t *in_group;
+    size_t group_size = rxo_group_flags(g, group, k, &in_group);
+    free(in_group);
+    if (group_size == 0 || node_count <= 1) return 0.0;
+    size_t n;
+    uint32_t *ids = rxo_live_nodes(g, &n);
+    int threads = (node_count >= parallel_threshold) ? rxo_max_threads() : 1;
+    double gb = rxo_group_betweenness_partial(g, group, k, ids, n, threads, NULL);
+    free(ids);
+    if (!g->directed) gb /= 2.0;
+    if (normalized) {
+        size_t non_group = node_count - group_size;
+        if (non_group > 1) {
+            double norm = g->directed ? (double)(non_group * (non_group - 1))
+                                      : (double)((non_group * (non_group - 1)) / 2);
+            gb /= norm;
+        }
+    }
+    return gb;
+}

@@ -99,6 +99,18 @@ void rxo_edge_betweenness_partial(const rxo_graph *g, const uint32_t *sources, s
 void rxo_closeness_partial(const rxo_graph *g, const uint32_t *sources, size_t k,
                            int wf_improved, int threads, double *out, rxo_stats *stats);
 
+/* ---- group centralities.  `group` holds ORIGINAL node indices of live nodes
+ *      (the binding validates them, src/centrality.rs:1216-1222); duplicates count once. ---- */
+/* rustworkx-core/src/centrality.rs:1860-1916 */
+double rxo_group_closeness_centrality(const rxo_graph *g, const uint32_t *group, size_t k);
+/* rustworkx-core/src/centrality.rs:1963-2101 */
+double rxo_group_betweenness_centrality(const rxo_graph *g, const uint32_t *group, size_t k,
+                                        int normalized, size_t parallel_threshold);
+/* the per-source sums of :1985-2080 over a subset of sources, before /2 and normalisation */
+double rxo_group_betweenness_partial(const rxo_graph *g, const uint32_t *group, size_t k,
+                                     const uint32_t *sources, size_t n_sources, int threads,
+                                     rxo_stats *stats);
+
 /* _rescale, rustworkx-core/src/centrality.rs:221-252, on a dense vector */
 void rxo_rescale(double *x, size_t len, size_t node_count, int normalized, int directed,
                  int include_endpoints);

@@ -220,6 +220,51 @@ def digraph_unweighted_average_shortest_path_length(graph, /, parallel_threshold
     return _average_length(graph, _bool(as_undirected, "as_undirected"), _bool(disconnected, "disconnected"))
 
 
+def _group_arg(graph, group):
+    """pyo3 ``Vec<usize>`` extraction plus the binding's membership check
+    (``src/centrality.rs:1216-1222``): ``ValueError`` for an index that is not in the graph."""
+    if isinstance(group, (str, bytes)):
+        raise TypeError("argument 'group': Can't extract `str` to `Vec`")
+    idx = [_usize(x, "group") for x in group]
+    for i in idx:
+        if not graph.has_node(i):
+            raise ValueError(f"Node index {i} is not in the graph")
+    return np.asarray(idx, dtype=np.uint32)
+
+
+def graph_group_closeness_centrality(graph, group, /):
+    """``rustworkx.graph_group_closeness_centrality`` (``src/centrality.rs:1210-1224``)."""
+    graph = _graph_arg(graph, PyGraph, "PyGraph")
+    group = _group_arg(graph, group)
+    return device_snapshot(graph).group_closeness(group)
+
+
+def digraph_group_closeness_centrality(graph, group, /):
+    """``rustworkx.digraph_group_closeness_centrality`` (``src/centrality.rs:1250-1264``)."""
+    graph = _graph_arg(graph, PyDiGraph, "PyDiGraph")
+    group = _group_arg(graph, group)
+    return device_snapshot(graph).group_closeness(group)
+
+
+def _group_betweenness(graph, group, normalized, parallel_threshold):
+    group = _group_arg(graph, group)
+    normalized = _bool(normalized, "normalized")
+    _usize(parallel_threshold, "parallel_threshold")
+    return device_snapshot(graph).group_betweenness(group, normalized)
+
+
+def graph_group_betweenness_centrality(graph, group, /, normalized=True, parallel_threshold=50):
+    """``rustworkx.graph_group_betweenness_centrality`` (``src/centrality.rs:1304-1325``)."""
+    return _group_betweenness(_graph_arg(graph, PyGraph, "PyGraph"), group, normalized,
+                              parallel_threshold)
+
+
+def digraph_group_betweenness_centrality(graph, group, /, normalized=True, parallel_threshold=50):
+    """``rustworkx.digraph_group_betweenness_centrality`` (``src/centrality.rs:1363-1384``)."""
+    return _group_betweenness(_graph_arg(graph, PyDiGraph, "PyDiGraph"), group, normalized,
+                              parallel_threshold)
+
+
 # ---------------------------------------------------------------------------------------------
 # universal dispatchers (rustworkx/__init__.py:138-147)
 # ---------------------------------------------------------------------------------------------
@@ -259,4 +304,16 @@ def closeness_centrality(graph, wf_improved=True, parallel_threshold=50):
 @_rustworkx_dispatch
 def edge_betweenness_centrality(graph, normalized=True, parallel_threshold=50):
     """Edge betweenness centrality of each edge (``rustworkx/__init__.py:1438-1479``)."""
+    raise TypeError(f"Invalid Input Type {type(graph)} for graph")
+
+
+@_rustworkx_dispatch
+def group_closeness_centrality(graph, group):
+    """Group closeness centrality of a set of nodes (``rustworkx/__init__.py:1370-1396``)."""
+    raise TypeError(f"Invalid Input Type {type(graph)} for graph")
+
+
+@_rustworkx_dispatch
+def group_betweenness_centrality(graph, group, normalized=True, parallel_threshold=50):
+    """Group betweenness centrality of a set of nodes (``rustworkx/__init__.py:1398-1440``)."""
     raise TypeError(f"Invalid Input Type {type(graph)} for graph")

@@ -70,6 +70,9 @@ SYMBOLS = {
     "rxc_closeness": (C.c_int, [_vp, C.c_int, _f64p]),
     "rxc_distance_matrix": (C.c_int, [_vp, C.c_int, C.c_double, _f64p]),
     "rxc_distance_sums": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "rxc_group_betweenness": (C.c_int, [_vp, _u32p, C.c_uint64, C.c_int, _f64p]),
+    "rxc_group_closeness": (C.c_int, [_vp, _u32p, C.c_uint64, _f64p]),
+    "rxc_group_betweenness_partial": (C.c_int, [_vp, _u32p, C.c_uint64, _u32p, C.c_uint64, _f64p]),
     "rxc_betweenness_partial": (C.c_int, [_vp, _u32p, C.c_uint64, C.c_int, _f64p]),
     "rxc_edge_betweenness_partial": (C.c_int, [_vp, _u32p, C.c_uint64, _f64p]),
     "rxc_closeness_partial": (C.c_int, [_vp, _u32p, C.c_uint64, C.c_int, _f64p]),
@@ -235,6 +238,26 @@ class DeviceGraph:
         total, pairs = C.c_uint64(), C.c_uint64()
         check(lib().rxc_distance_sums(self._h, int(as_undirected), C.byref(total), C.byref(pairs)))
         return int(total.value), int(pairs.value)
+
+    def group_betweenness(self, group, normalized):
+        grp = np.ascontiguousarray(group, dtype=np.uint32)
+        out = C.c_double()
+        check(lib().rxc_group_betweenness(self._h, p_u32(grp), grp.shape[0], int(normalized), C.byref(out)))
+        return float(out.value)
+
+    def group_closeness(self, group):
+        grp = np.ascontiguousarray(group, dtype=np.uint32)
+        out = C.c_double()
+        check(lib().rxc_group_closeness(self._h, p_u32(grp), grp.shape[0], C.byref(out)))
+        return float(out.value)
+
+    def group_betweenness_partial(self, group, sources):
+        grp = np.ascontiguousarray(group, dtype=np.uint32)
+        src = np.ascontiguousarray(sources, dtype=np.uint32)
+        out = C.c_double()
+        check(lib().rxc_group_betweenness_partial(self._h, p_u32(grp), grp.shape[0], p_u32(src),
+                                                  src.shape[0], C.byref(out)))
+        return float(out.value)
 
     # ---- partial calls (source shards; un-rescaled) ---------------------------------------------
     def betweenness_partial(self, sources, include_endpoints=False):

@@ -94,6 +94,7 @@ struct BcParams {
     unsigned long long *stats;  // [ST_COUNT]
     double *acc;          // node mode: [n] by compact vertex; edge mode: [e_bound] by edge index
     const uint32_t *src;  // [NG][128] compact source ids, NO_SOURCE padded; slot 32k+l = lane l, k
+    const uint32_t *blocked;  // group betweenness: bitmap of the group's vertices, else nullptr
     uint64_t qcap;
     uint32_t n;
     uint32_t lcap;
@@ -750,6 +751,117 @@ __global__ void __launch_bounds__(BLOCK) bc_endpoint_sources_kernel(BcParams p, 
     if (i >= ngroups * BG) return;
     const uint32_t s = p.src[i];
     if (s != NO_SOURCE) atomicAdd(&p.acc[s], (double)p.reach[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// group betweenness (rustworkx-core/src/centrality.rs:1963-2101)
+//
+// The reference runs two sigma-BFSs per non-group source: one on the full graph and one on the
+// graph with the group's vertices removed.  Here both run in the SAME forward pass as a pair of
+// slots: slot j (< 64) of a group is the full BFS of source j, slot 64+j the BFS of the same source
+// with the group removed -- lane l holds the pairs (l, 64+l) and (32+l, 96+l) in ONE sector, elements
+// {0,2} and {1,3}.  "Removed" is a preset: the group's vertices start out visited in slots 64..127,
+// so they are never discovered there and never act as parents.  A queue entry (v, mask) of level L
+// holds bit j iff dist_full(s_j, v) = L and bit 64+j iff dist_no_group(s_j, v) = L, so the
+// reference's test `dist_no_group[t] == dist_full[t]` (:2066) is "both bits in the same entry".
+// ---------------------------------------------------------------------------------------------
+constexpr int BGP = BG / 2;  // sources per group in pair mode
+
+// visited[g][m] |= slots 64..127 for every member m of the group
+__global__ void __launch_bounds__(BLOCK)
+    bc_group_block_kernel(BcParams p, const uint32_t *members, uint32_t nmem) {
+    const uint32_t g = blockIdx.y;
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= nmem) return;
+    Mask128 *q = &p.visited[(size_t)g * p.n + members[i]];
+    Mask128 m = mask_load(q);
+    m.w[2] = m.w[3] = 0xFFFFFFFFu;
+    mask_store(q, m);
+}
+
+// Level 0 in pair mode: source j seeds slots j and 64+j with one queue entry carrying both bits.
+__global__ void __launch_bounds__(32) bc_seed_pair_kernel(BcParams p) {
+    const uint32_t g = blockIdx.x;
+    const int lane = lane_id();
+    const Mask128 valid = bc_valid_mask(p, g);
+    uint32_t base = 0;
+#pragma unroll
+    for (int k = 0; k < BK / 2; k++) {
+        const uint32_t s = p.src[(size_t)g * BG + k * 32 + lane];
+        if (s != NO_SOURCE) {
+            const size_t gv = (size_t)g * p.n + s;
+            Mask128 bit = mask_zero();
+            bit.w[k] = bit.w[k + 2] = 1u << lane;
+            Mask128 vis;
+#pragma unroll
+            for (int j = 0; j < BK; j++) vis.w[j] = ~valid.w[j] | bit.w[j];
+            mask_store(&p.visited[gv], vis);  // sources are distinct vertices outside the group
+            bc_store_level(p.P0 + (size_t)g * p.n, s, p.tagbase + 1, bit);
+            p.sc[gv * BG + lane * BK + k] = 1.0;
+            p.sc[gv * BG + lane * BK + k + 2] = 1.0;
+            const uint32_t i = base + __popc(valid.w[k] & lanemask_lt());
+            p.qv[(size_t)g * p.qcap + i] = s;
+            mask_store(&p.qm[(size_t)g * p.qcap + i], bit);
+        }
+        base += __popc(valid.w[k]);
+    }
+    if (lane == 0) {
+        p.loff[(size_t)g * p.lcap] = 0;
+        p.lvlcnt[(size_t)g * p.lcap] = base;
+        p.hubcnt[g] = 0;
+        p.hubcnt[p.ngroups + g] = 0;
+        atomicAdd(&p.lvl_total[0], base);
+    }
+}
+
+// After the forward pass: for every queue entry (t, mask) beyond level 0 with t outside the group,
+// add (sigma_full - paths_avoiding) / sigma_full for each source whose full BFS found t on this
+// level (centrality.rs:2054-2078).  One warp per entry; one atomicAdd per warp.
+__global__ void __launch_bounds__(BLOCK) bc_group_finalize_kernel(BcParams p, uint32_t nlevels) {
+    const uint32_t g = blockIdx.y;
+    const uint32_t *lc = p.lvlcnt + (size_t)g * p.lcap;
+    __shared__ uint32_t s_end;
+    if (threadIdx.x == 0) s_end = 0;
+    __syncthreads();
+    uint32_t part = 0;
+    for (uint32_t l = threadIdx.x; l < nlevels; l += BLOCK) part += lc[l];
+    part = (uint32_t)warp_sum_u64(part);
+    if (lane_id() == 0 && part) atomicAdd(&s_end, part);
+    __syncthreads();
+    const uint32_t end = s_end, first = lc[0];  // entries [0, first) are the sources themselves
+    const int lane = lane_id();
+    const double *rows = p.sc + (size_t)g * p.n * BG;
+    const uint32_t *qv = p.qv + (size_t)g * p.qcap;
+    const Mask128 *qm = p.qm + (size_t)g * p.qcap;
+    double sum = 0.0;
+    unsigned long long te = 0, vv = 0;
+    for (uint32_t i = blockIdx.x * WARPS + (threadIdx.x >> 5); i < end; i += gridDim.x * WARPS) {
+        const uint32_t t = qv[i];
+        const Mask128 fm = mask_load(&qm[i]);
+        if (lane == 0) {
+            te += (unsigned long long)mask_popc(fm) * (p.srow[t + 1] - p.srow[t]);
+            vv += mask_popc(fm);
+        }
+        if (i < first || ((p.blocked[t >> 5] >> (t & 31)) & 1u)) continue;
+        const uint32_t full = fm.w[0] | fm.w[1];
+        const Row4 r = row_load(rows, t, lane, (full >> lane) & 1u);
+#pragma unroll
+        for (int k = 0; k < BK / 2; k++) {
+            if ((fm.w[k] >> lane) & 1u) {
+                const double sf = r.x[k];
+                const double sa = ((fm.w[k + 2] >> lane) & 1u) ? r.x[k + 2] : 0.0;
+                sum += (sf - sa) / sf;
+            }
+        }
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) {
+        if (sum != 0.0) atomicAdd(&p.acc[0], sum);
+        if (te | vv) {
+            atomicAdd(&p.stats[ST_TE], te);
+            atomicAdd(&p.stats[ST_V], vv);
+        }
+    }
 }
 
 }  // namespace rxc

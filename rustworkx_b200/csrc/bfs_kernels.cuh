@@ -80,6 +80,27 @@ __global__ void __launch_bounds__(32) bfs_seed_kernel(BfsParams p) {
     }
 }
 
+// group closeness (rustworkx-core/src/centrality.rs:1860-1916): ONE multi-source BFS.
+// Slot 0 of group 0 is seeded at every member of the group; src[0] only marks the slot as valid.
+__global__ void __launch_bounds__(BLOCK)
+    bfs_seed_multi_kernel(BfsParams p, const uint32_t *members, uint32_t nmem) {
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i < nmem) {
+        p.next0[members[i]] = 1u;  // members are distinct
+        p.q0[i] = members[i];
+    }
+    if (i < GW) {
+        p.reach[i] = 0ull;
+        p.dsum[i] = 0ull;
+    }
+    if (i == 0) {
+        p.cnt[0] = nmem;
+        p.cnt[1] = 0;
+        p.cnt[2] = 0;
+        p.lvl_total[0] = nmem;
+    }
+}
+
 // One BFS level for every group of the batch (thread per queued vertex).
 template <bool ROWS>
 __global__ void __launch_bounds__(BLOCK) bfs_level_kernel(BfsParams p, uint32_t level) {

@@ -478,12 +478,20 @@ static void bc_enable_smem() {
     done = true;
 }
 
+// Group betweenness (bc_kernels.cuh, "pair mode"): the group's vertices on the device.
+struct GroupSpec {
+    const uint32_t *d_members;  // compact ids, distinct
+    uint32_t n_members;
+    const uint32_t *d_blocked;  // bitmap over compact ids
+};
+
 static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endpoints,
-                   bool edge_mode, double *d_acc) {
+                   bool edge_mode, double *d_acc, const GroupSpec *grp = nullptr) {
     bc_enable_smem();
     const uint32_t n = g->host.n_live;
     if (sources.empty() || n == 0) return;
-    const uint64_t total_groups = (sources.size() + BG - 1) / BG;
+    const uint32_t per = grp ? BGP : BG;  // sources per group (pair mode: two slots per source)
+    const uint64_t total_groups = (sources.size() + per - 1) / per;
     const uint32_t lcap = n + 2;
     const uint64_t qcap = (uint64_t)BG * n;  // worst case: a vertex sits on a different level per source
     // bytes per group: 1 KB row + worst-case queues + two tagged mask arrays + visited + level tables
@@ -548,6 +556,7 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
     p.srow = g->succ().row.p;
     p.scol = g->succ().col.p;
     p.hub_degree = (uint32_t)std::min<int64_t>(g_opt.hub_degree, 0x7FFFFFFF);
+    p.blocked = grp ? grp->d_blocked : nullptr;
     p.qcap = qcap;
     p.n = n;
     p.lcap = lcap;
@@ -560,9 +569,16 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
     for (uint64_t g0 = 0; g0 < total_groups; g0 += ng) {
         const uint32_t bg = (uint32_t)std::min<uint64_t>(ng, total_groups - g0);
         std::fill(h_src.begin(), h_src.end(), NO_SOURCE);
-        const size_t s0 = (size_t)g0 * BG;
-        const size_t cnt = std::min(sources.size() - s0, (size_t)bg * BG);
-        std::copy(sources.begin() + s0, sources.begin() + s0 + cnt, h_src.begin());
+        const size_t s0 = (size_t)g0 * per;
+        const size_t cnt = std::min(sources.size() - s0, (size_t)bg * per);
+        if (!grp) {
+            std::copy(sources.begin() + s0, sources.begin() + s0 + cnt, h_src.begin());
+        } else {  // slot j and slot 64+j of a group carry the same source
+            for (size_t i = 0; i < cnt; i++) {
+                const size_t slot = (i / BGP) * BG + i % BGP;
+                h_src[slot] = h_src[slot + BGP] = sources[s0 + i];
+            }
+        }
         if ((uint64_t)tagbase + lcap + 16 > 0xFFFFFFF0ull) {
             RXC_CUDA(cudaMemsetAsync(ws.P0.p, 0, ws.P0.bytes(), st));
             RXC_CUDA(cudaMemsetAsync(ws.P1.p, 0, ws.P1.bytes(), st));
@@ -576,7 +592,15 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
         RXC_CUDA(cudaMemset2DAsync(ws.lvlcnt.p, (size_t)lcap * 4, 0, (size_t)clear_levels * 4, ws.ng, st));
         RXC_CUDA(cudaMemsetAsync(ws.lvl_total.p, 0, (size_t)clear_levels * 4, st));
         bc_init_kernel<<<dim3(vblocks, bg), BLOCK, 0, st>>>(p);
-        bc_seed_kernel<<<bg, 32, 0, st>>>(p);
+        if (grp) {
+            if (grp->n_members)
+                bc_group_block_kernel<<<dim3((grp->n_members + BLOCK - 1) / BLOCK, bg), BLOCK, 0, st>>>(
+                    p, grp->d_members, grp->n_members);
+            bc_seed_pair_kernel<<<bg, 32, 0, st>>>(p);
+            g->stats.launches++;
+        } else {
+            bc_seed_kernel<<<bg, 32, 0, st>>>(p);
+        }
         g->stats.launches += 2;
 
         // forward: in-arcs (pull from predecessors)
@@ -598,6 +622,23 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
         clear_levels = std::min<uint32_t>(lcap, launched_levels + 2);
         RXC_CUDA(cudaMemsetAsync(ws.hubcnt.p, 0, ws.hubcnt.bytes(), st));
         RXC_CUDA(cudaEventRecord(g->ev[1], st));
+
+        if (grp) {  // no dependency sweep: the sums come straight from the two sigma rows
+            bc_group_finalize_kernel<<<dim3(148 * 2, bg), BLOCK, 0, st>>>(p, std::min(L + 1, lcap));
+            g->stats.launches++;
+            RXC_CUDA(cudaEventRecord(g->ev[2], st));
+            RXC_CUDA(cudaStreamSynchronize(st));
+            RXC_CUDA(cudaGetLastError());
+            float f = 0.f, b = 0.f;
+            RXC_CUDA(cudaEventElapsedTime(&f, g->ev[0], g->ev[1]));
+            RXC_CUDA(cudaEventElapsedTime(&b, g->ev[1], g->ev[2]));
+            g->stats.ms_forward += f;
+            g->stats.ms_backward += b;
+            g->stats.batches++;
+            g->stats.sources += cnt;
+            tagbase += launched_levels + 8;
+            continue;
+        }
 
         // backward: out-arcs (pull from successors), deepest level first
         h_lvlcnt.resize((size_t)bg * L);
@@ -692,6 +733,52 @@ static void bc_partial(rxc_graph *g, const std::vector<uint32_t> &sources, bool 
     }
     fetch_stats(g);
     g->stats.ms_d2h += now_ms() - t0;
+}
+
+// Distinct compact ids of a group given in ORIGINAL indices (the reference collects a HashSet,
+// centrality.rs:1869,1982); every index must name a live node (src/centrality.rs:1216-1222).
+static std::vector<uint32_t> group_members(const rxc_graph *g, const uint32_t *group, uint64_t k) {
+    std::vector<uint32_t> m = to_compact(g, group, k);
+    std::sort(m.begin(), m.end());
+    m.erase(std::unique(m.begin(), m.end()), m.end());
+    return m;
+}
+
+// sum over the listed sources (compact ids; members of the group are skipped, :1987-1989) of
+// sum_t (sigma_full - paths_avoiding) / sigma_full, before the /2 and the normalisation
+static double group_bc_partial(rxc_graph *g, const std::vector<uint32_t> &members,
+                               const std::vector<uint32_t> &sources) {
+    std::lock_guard<std::mutex> lock(g->mu);
+    begin_call(g);
+    const uint32_t n = g->host.n_live;
+    double total = 0.0;
+    if (n && !sources.empty()) {
+        cudaStream_t st = g->stream;
+        std::vector<uint32_t> h_blocked((n + 31) / 32, 0);
+        for (uint32_t m : members) h_blocked[m >> 5] |= 1u << (m & 31);
+        DevBuf<uint32_t> d_members, d_blocked;
+        d_members.alloc(std::max<size_t>(members.size(), 1));
+        d_blocked.alloc(h_blocked.size());
+        if (!members.empty())
+            RXC_CUDA(cudaMemcpyAsync(d_members.p, members.data(), members.size() * 4, cudaMemcpyHostToDevice, st));
+        RXC_CUDA(cudaMemcpyAsync(d_blocked.p, h_blocked.data(), h_blocked.size() * 4, cudaMemcpyHostToDevice, st));
+        std::vector<uint32_t> src;
+        src.reserve(sources.size());
+        for (uint32_t s : sources)
+            if (!((h_blocked[s >> 5] >> (s & 31)) & 1u)) src.push_back(s);
+        DevBuf<double> &acc = g->acc_buf;
+        if (acc.n < 1) acc.alloc(1);
+        RXC_CUDA(cudaMemsetAsync(acc.p, 0, sizeof(double), st));
+        const GroupSpec spec{d_members.p, (uint32_t)members.size(), d_blocked.p};
+        for (const auto &round : distinct_rounds(src, n)) bc_run(g, round, false, false, acc.p, &spec);
+        end_call(g);
+        RXC_CUDA(cudaMemcpyAsync(&total, acc.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+        RXC_CUDA(cudaStreamSynchronize(st));
+        fetch_stats(g);
+    } else {
+        end_call(g);
+    }
+    return total;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1007,6 +1094,77 @@ static void bfs_dispatch(rxc_graph *g, const DeviceCSR &csr, const std::vector<u
         bfs_run(g, csr, sources, mode, wf_improved, null_value, out);
 }
 
+// group closeness: one multi-source BFS over incoming arcs (Reversed(&graph), centrality.rs:1875-1899);
+// returns the sum of distances of the reached vertices (members contribute 0)
+static uint64_t group_closeness_dsum(rxc_graph *g, const std::vector<uint32_t> &members) {
+    std::lock_guard<std::mutex> lock(g->mu);
+    begin_call(g);
+    const uint32_t n = g->host.n_live;
+    uint64_t dsum = 0;
+    if (n && !members.empty()) {
+        cudaStream_t st = g->stream;
+        const uint32_t lcap = n + 2;
+        DevBuf<uint32_t> words, cnt, lvl_total, src, d_members;
+        DevBuf<unsigned long long> sums;
+        words.alloc((size_t)5 * n);  // visited, next0, next1, q0, q1
+        cnt.alloc(3);
+        lvl_total.alloc(lcap);
+        src.alloc(GW);
+        sums.alloc(2 * GW);
+        d_members.alloc(members.size());
+        std::vector<uint32_t> h_src(GW, NO_SOURCE);
+        h_src[0] = members[0];
+        RXC_CUDA(cudaMemcpyAsync(src.p, h_src.data(), GW * 4, cudaMemcpyHostToDevice, st));
+        RXC_CUDA(cudaMemcpyAsync(d_members.p, members.data(), members.size() * 4, cudaMemcpyHostToDevice, st));
+        RXC_CUDA(cudaMemsetAsync(lvl_total.p, 0, lvl_total.bytes(), st));
+        BfsParams p{};
+        p.row = g->pred().row.p;
+        p.col = g->pred().col.p;
+        p.visited = words.p;
+        p.next0 = words.p + (size_t)n;
+        p.next1 = words.p + (size_t)2 * n;
+        p.q0 = words.p + (size_t)3 * n;
+        p.q1 = words.p + (size_t)4 * n;
+        p.cnt = cnt.p;
+        p.lvl_total = lvl_total.p;
+        p.reach = sums.p;
+        p.dsum = sums.p + GW;
+        p.stats = g->d_stats.p;
+        p.src = src.p;
+        p.n = n;
+        p.n_cols = n;
+        p.ngroups = 1;
+        const uint32_t vblocks = (n + BLOCK - 1) / BLOCK;
+        bfs_init_kernel<<<dim3(vblocks, 1), BLOCK, 0, st>>>(p);
+        const uint32_t nmem = (uint32_t)members.size();
+        bfs_seed_multi_kernel<<<(std::max<uint32_t>(nmem, GW) + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(p, d_members.p, nmem);
+        std::vector<uint32_t> h_totals;
+        uint32_t launched = 0;
+        const uint32_t L = run_levels(
+            g, lvl_total.p, n,
+            [&](uint32_t level) {
+                uint32_t est = level < h_totals.size() && h_totals[level] ? h_totals[level] : nmem;
+                const uint32_t gx = std::max<uint32_t>(1, std::min((4 * est + BLOCK - 1) / BLOCK, vblocks));
+                bfs_level_kernel<false><<<dim3(gx, 1), BLOCK, 0, st>>>(p, level);
+                launched++;
+            },
+            h_totals);
+        g->stats.launches += 2 + launched;
+        g->stats.levels += L;
+        g->stats.sources += 1;
+        g->stats.batches += 1;
+        unsigned long long h = 0;
+        RXC_CUDA(cudaMemcpyAsync(&h, p.dsum, 8, cudaMemcpyDeviceToHost, st));
+        end_call(g);
+        RXC_CUDA(cudaStreamSynchronize(st));
+        fetch_stats(g);
+        dsum = h;
+    } else {
+        end_call(g);
+    }
+    return dsum;
+}
+
 static const DeviceCSR &symmetric_csr(rxc_graph *g) {
     if (!g->host.directed) return g->out;
     if (!g->has_sym) {
@@ -1279,6 +1437,57 @@ int rxc_edge_betweenness(rxc_graph *g, int normalized, double *out) {
     return guarded([&] {
         bc_full(g, false, true, out);
         rxc_rescale(out, g->host.e_bound, g->host.n_live, normalized, g->host.directed ? 1 : 0, 1);
+    });
+}
+
+int rxc_group_betweenness_partial(rxc_graph *g, const uint32_t *group, uint64_t n_group,
+                                  const uint32_t *sources, uint64_t n_sources, double *out_sum) {
+    if (!g || !out_sum || (n_group && !group) || (n_sources && !sources)) return RXC_ERR_INVALID;
+    return guarded([&] {
+        *out_sum = group_bc_partial(g, group_members(g, group, n_group), to_compact(g, sources, n_sources));
+    });
+}
+
+int rxc_group_betweenness(rxc_graph *g, const uint32_t *group, uint64_t n_group, int normalized,
+                          double *out) {
+    if (!g || !out || (n_group && !group)) return RXC_ERR_INVALID;
+    return guarded([&] {
+        // group_betweenness_centrality, rustworkx-core/src/centrality.rs:1963-2101
+        const std::vector<uint32_t> members = group_members(g, group, n_group);
+        const uint64_t node_count = g->host.n_live, group_size = members.size();
+        *out = 0.0;
+        if (group_size == 0 || node_count <= 1) return;
+        const size_t K = 1 + g->replicas.size();
+        std::vector<double> parts(K, 0.0);
+        run_on_shards(g, [&](rxc_graph *r, size_t k, size_t nk) {
+            parts[k] = group_bc_partial(r, members, shard_sources(r->host.n_live, k, nk));
+        });
+        double gb = 0.0;
+        for (double x : parts) gb += x;
+        if (!g->host.directed) gb /= 2.0;
+        if (normalized) {
+            const uint64_t non_group = node_count - group_size;
+            if (non_group > 1) {
+                const double norm = g->host.directed ? (double)(non_group * (non_group - 1))
+                                                     : (double)((non_group * (non_group - 1)) / 2);
+                gb /= norm;
+            }
+        }
+        *out = gb;
+    });
+}
+
+int rxc_group_closeness(rxc_graph *g, const uint32_t *group, uint64_t n_group, double *out) {
+    if (!g || !out || (n_group && !group)) return RXC_ERR_INVALID;
+    return guarded([&] {
+        // group_closeness_centrality, rustworkx-core/src/centrality.rs:1860-1916
+        const std::vector<uint32_t> members = group_members(g, group, n_group);
+        const uint64_t node_count = g->host.n_live, group_size = members.size();
+        *out = 0.0;
+        if (group_size >= node_count) return;
+        const uint64_t dist_sum = group_closeness_dsum(g, members);
+        if (dist_sum == 0) return;
+        *out = (double)(node_count - group_size) / (double)dist_sum;
     });
 }
 

@@ -540,3 +540,92 @@ def test_cta_per_source_with_global_bitmap(rx, oracle):
         finally:
             _lib.set_option("bfs_mode", 0)
         assert np.array_equal(got, want[src])
+
+
+# ------------------------------------------------------------------------------------ group centralities (8f #2)
+def _graph_from_case(rx, directed, n, edges):
+    g = rx.PyDiGraph() if directed else rx.PyGraph()
+    g.add_nodes_from(range(n))
+    g.add_edges_from_no_data(edges)
+    return g
+
+
+def test_reference_goldens_group_closeness(rx):
+    from group_cases import CLOSENESS
+
+    for name, directed, n, edges, group, expected in CLOSENESS:
+        g = _graph_from_case(rx, directed, n, edges)
+        typed = rx.digraph_group_closeness_centrality if directed else rx.graph_group_closeness_centrality
+        assert abs(typed(g, group) - expected) < 1e-10, name
+        assert rx.group_closeness_centrality(g, group) == typed(g, group)
+
+
+def test_reference_goldens_group_betweenness(rx):
+    from group_cases import BETWEENNESS
+
+    for name, directed, n, edges, group, normalized, expected in BETWEENNESS:
+        g = _graph_from_case(rx, directed, n, edges)
+        typed = rx.digraph_group_betweenness_centrality if directed else rx.graph_group_betweenness_centrality
+        for threshold in (50, 1):
+            got = typed(g, group, normalized=normalized, parallel_threshold=threshold)
+            assert abs(got - expected) < 1e-10, name
+        assert abs(rx.group_betweenness_centrality(g, group, normalized) - expected) < 1e-10, name
+    # rustworkx-core/src/centrality.rs:2338-2360: a one-node group equals that node's betweenness
+    g = _graph_from_case(rx, True, 4, [(0, 1), (1, 2), (2, 3)])
+    for normalized in (False, True):
+        per_node = rx.betweenness_centrality(g, normalized=normalized)
+        for v in range(4):
+            assert abs(rx.group_betweenness_centrality(g, [v], normalized) - per_node[v]) < 1e-10
+
+
+def test_group_errors(rx):
+    # tests/graph/test_centrality.py:362-365,407-410; src/centrality.rs:1216-1222
+    g = rx.generators.path_graph(3)
+    with pytest.raises(ValueError):
+        rx.graph_group_closeness_centrality(g, [10])
+    with pytest.raises(ValueError):
+        rx.graph_group_betweenness_centrality(g, [10])
+    g.remove_node(1)
+    with pytest.raises(ValueError):
+        rx.group_betweenness_centrality(g, [1])
+    with pytest.raises(TypeError):
+        rx.graph_group_betweenness_centrality(rx.PyDiGraph(), [0])
+    with pytest.raises(OverflowError):
+        rx.group_closeness_centrality(g, [-1])
+    assert rx.group_betweenness_centrality(g, [], normalized=False) == 0.0
+    assert rx.group_closeness_centrality(g, [0, 2]) == 0.0  # group covers every node
+
+
+@pytest.mark.parametrize("directed,n,m,seed,holes", CASES)
+def test_group_centralities_vs_oracle(rx, oracle, directed, n, m, seed, holes):
+    g = random_graph(rx, directed, n, m, seed, holes)
+    og = oracle_graph(oracle, g)
+    live = np.asarray(g.node_indices())
+    rng = np.random.default_rng(seed + 100)
+    for size in (1, 2, 5, max(2, len(live) // 3)):
+        group = rng.choice(live, size=size, replace=False).tolist()
+        group = group + group[:1]  # a duplicate counts once
+        assert rx.group_closeness_centrality(g, group) == og.group_closeness_centrality(group)  # bit exact
+        for normalized in (False, True):
+            want = og.group_betweenness_centrality(group, normalized, 1 << 30)
+            got = rx.group_betweenness_centrality(g, group, normalized=normalized)
+            assert abs(got - want) <= ATOL + RTOL * abs(want), (size, normalized, got, want)
+
+
+def test_group_betweenness_sampled_sources_ba(rx, oracle):
+    """BA(100k, 8): un-normalised partial sums over 200 sampled sources against the oracle, work
+    counters included (TE and V count both BFSs of every source)."""
+    from rustworkx_b200 import device_snapshot
+
+    g = rx.barabasi_albert_graph(100_000, 8, seed=3)
+    og = oracle_graph(oracle, g)
+    rng = np.random.default_rng(5)
+    group = rng.choice(100_000, size=50, replace=False).astype(np.uint32)
+    group[:3] = [0, 1, 2]  # include the oldest hubs
+    sources = rng.choice(100_000, size=200, replace=False).astype(np.uint32)
+    want, wst = og.group_betweenness_partial(group, sources, threads=oracle.max_threads())
+    dg = device_snapshot(g)
+    got = dg.group_betweenness_partial(group, sources)
+    assert abs(got - want) <= RTOL * abs(want)
+    st = dg.stats()
+    assert st["te"] == wst["te"] and st["v"] == wst["v"]

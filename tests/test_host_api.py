@@ -251,3 +251,18 @@ def test_shard_sources_partition(rx):
         assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
     with pytest.raises(ValueError):
         shard_sources(src, 2, 2)
+
+
+def test_group_argument_validation_happens_before_any_device_work():
+    # src/centrality.rs:1216-1222: the binding checks the group first -> ValueError even without a GPU
+    import rustworkx_b200 as rx
+
+    g = rx.generators.path_graph(3)
+    with pytest.raises(ValueError, match="Node index 10 is not in the graph"):
+        rx.graph_group_closeness_centrality(g, [10])
+    with pytest.raises(ValueError):
+        rx.group_betweenness_centrality(g, [0, 7])
+    with pytest.raises(TypeError):
+        rx.group_betweenness_centrality(g, "01")
+    with pytest.raises(TypeError):
+        rx.digraph_group_closeness_centrality(g, [0])

@@ -318,3 +318,34 @@ def test_average_shortest_path_length_goldens(oracle):
     assert val(gen.directed_cycle_graph(7)) == pytest.approx(3.5, abs=1e-7)
     assert math.isinf(val(gen.directed_path_graph(5)))
     assert val(gen.directed_path_graph(5), as_undirected=True) == pytest.approx(2, abs=1e-7)
+
+
+# ----------------------------------------------------------------------------- group centralities
+def test_group_closeness_goldens(oracle):
+    # rustworkx-core/src/centrality.rs:2155-2211; tests/graph/test_centrality.py:341-497;
+    # tests/digraph/test_centrality.py:374-495
+    from group_cases import CLOSENESS
+
+    for name, directed, n, edges, group, expected in CLOSENESS:
+        g = oracle.OracleGraph.from_edges(directed, edges, num_nodes=n)
+        assert abs(g.group_closeness_centrality(group) - expected) < 1e-10, name
+
+
+@pytest.mark.parametrize("threshold", [50, 1])
+def test_group_betweenness_goldens(oracle, threshold):
+    # rustworkx-core/src/centrality.rs:2213-2360; tests/graph/test_centrality.py:366-567;
+    # tests/digraph/test_centrality.py:396-565
+    from group_cases import BETWEENNESS
+
+    for name, directed, n, edges, group, normalized, expected in BETWEENNESS:
+        g = oracle.OracleGraph.from_edges(directed, edges, num_nodes=n)
+        got = g.group_betweenness_centrality(group, normalized, threshold)
+        assert abs(got - expected) < 1e-10, name
+
+
+def test_group_betweenness_singleton_matches_betweenness(oracle):
+    # rustworkx-core/src/centrality.rs:2342-2360: a one-node group equals that node's betweenness
+    g = oracle.OracleGraph.from_edges(True, [(0, 1), (1, 2), (2, 3)])
+    per_node = g.betweenness_centrality(False, False, 200)
+    for v in range(4):
+        assert abs(g.group_betweenness_centrality([v], False, 200) - per_node[v]) < 1e-10
