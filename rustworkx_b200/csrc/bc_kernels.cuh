@@ -244,21 +244,29 @@ __device__ __forceinline__ Row4 row_load(const double *rows, uint32_t v, int lan
 constexpr int STAGE = RXC_STAGE;
 constexpr int BC_SMEM_BYTES = WARPS * STAGE * BG * 8;  // 32 KB per CTA
 
-// Shared-memory layout of a staged row: the two 16-byte halves of lane l's sector sit at
-// slot + 16 l and slot + 512 + 16 l, so that every warp-wide 16-byte access (the LDGSTS writes and the
-// LDS.128 reads) covers 512 contiguous bytes = 4 conflict-free wavefronts.  The sector-contiguous
-// layout (32 l) was 2-way bank conflicted and ncu showed the shared-memory data pipe at 85 % of peak
-// (l1tex__data_pipe_lsu_wavefronts_mem_shared) in all four big launches.
-__device__ __forceinline__ double *stage_half(double *slot, int lane, int h) {
-    return slot + h * (BG / 2) + lane * 2;
+// Staging a row (1 KB = 64 chunks of 16 bytes) without shared-memory bank conflicts on either side.
+// Copy: instruction 1 moves chunk `lane`, instruction 2 chunk `32 + lane`, so the global side of each
+// warp-wide LDGSTS is 512 contiguous bytes (ncu: the sector-per-lane form, lane l copying chunks 2l
+// and 2l+1, cost 12.4 shared wavefronts per LDGSTS against an ideal of 4-5, and the shared-memory
+// data pipe sat at 65-85 % of peak in all four big launches).  Read: lane l owns sector l = chunks 2l
+// and 2l+1.  Chunk c is stored at position (c & ~7) | ((c + (c >> 3)) & 7) -- a rotation inside its
+// 128-byte line by the line number -- which makes the 8 lanes of every quarter warp hit 8 different
+// 16-byte bank groups for the writes (8 consecutive chunks) and for both reads (8 even or 8 odd
+// chunks of two neighbouring lines).  A chunk is only fetched when its sector is needed (`any` bit
+// of the sector); the others are zero-filled without touching memory.
+__device__ __forceinline__ int stage_pos(int c) { return (c & ~7) | ((c + (c >> 3)) & 7); }
+__device__ __forceinline__ const double2 *stage_chunk(const double *slot, int c) {
+    return reinterpret_cast<const double2 *>(slot) + stage_pos(c);
 }
-__device__ __forceinline__ void cp_async_sector(double *slot, int lane, const double *gsrc, bool on) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(slot + lane * 2);
-    const int sz = on ? 16 : 0;  // src-size 0: zero-fill, no global access
+__device__ __forceinline__ void cp_async_row(double *slot, int lane, const double *grow, uint32_t any) {
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(slot);
+    const uint32_t d1 = base + 16u * stage_pos(lane), d2 = base + 16u * stage_pos(32 + lane);
+    const int sz1 = ((any >> (lane >> 1)) & 1u) ? 16 : 0;  // src-size 0: zero-fill, no global access
+    const int sz2 = ((any >> (16 + (lane >> 1))) & 1u) ? 16 : 0;
     asm volatile(
         "cp.async.cg.shared.global [%0], [%1], 16, %2;\n"
-        "cp.async.cg.shared.global [%3], [%4], 16, %2;\n" ::"r"(d),
-        "l"(gsrc), "r"(sz), "r"(d + 512), "l"(gsrc + 2)
+        "cp.async.cg.shared.global [%3], [%4], 16, %5;\n" ::"r"(d1),
+        "l"(grow + 2 * lane), "r"(sz1), "r"(d2), "l"(grow + 64 + 2 * lane), "r"(sz2)
         : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
@@ -280,8 +288,7 @@ __device__ __forceinline__ void bc_gather(const double *rows, uint32_t v_lane, c
                 nz &= nz - 1;
                 const uint32_t vj = __shfl_sync(FULL, v_lane, a);
                 const uint32_t any = __shfl_sync(FULL, mask_or(m_lane), a);
-                cp_async_sector(stage + i * BG, lane, rows + (size_t)vj * BG + lane * BK,
-                                (any >> lane) & 1u);
+                cp_async_row(stage + i * BG, lane, rows + (size_t)vj * BG, any);
                 cnt = i + 1;
             }
         }
@@ -292,8 +299,8 @@ __device__ __forceinline__ void bc_gather(const double *rows, uint32_t v_lane, c
                 const int a = __ffs(todo) - 1;
                 todo &= todo - 1;
                 const Mask128 mj = mask_shfl(m_lane, a);
-                const double2 x0 = *reinterpret_cast<const double2 *>(stage_half(stage + i * BG, lane, 0));
-                const double2 x1 = *reinterpret_cast<const double2 *>(stage_half(stage + i * BG, lane, 1));
+                const double2 x0 = *stage_chunk(stage + i * BG, 2 * lane);
+                const double2 x1 = *stage_chunk(stage + i * BG, 2 * lane + 1);
                 if ((mj.w[0] >> lane) & 1u) acc[0] += x0.x;
                 if ((mj.w[1] >> lane) & 1u) acc[1] += x0.y;
                 if ((mj.w[2] >> lane) & 1u) acc[2] += x1.x;
@@ -576,8 +583,7 @@ __device__ __forceinline__ void bc_bwd_scan(const BcParams &p, const double *row
                         nz &= nz - 1;
                         const uint32_t wj = __shfl_sync(FULL, w, a);
                         const uint32_t any = __shfl_sync(FULL, mask_or(m), a);
-                        cp_async_sector(stage + i * BG, lane, rows + (size_t)wj * BG + lane * BK,
-                                        (any >> lane) & 1u);
+                        cp_async_row(stage + i * BG, lane, rows + (size_t)wj * BG, any);
                         cnt = i + 1;
                     }
                 }
@@ -593,8 +599,8 @@ __device__ __forceinline__ void bc_bwd_scan(const BcParams &p, const double *row
                         const Mask128 mj = mask_shfl(m, a);
                         const uint32_t ej = __shfl_sync(FULL, ed, a);
                         if (lane / (32 / STAGE) == i) my_e = ej;
-                        const double2 x0 = *reinterpret_cast<const double2 *>(stage_half(stage + i * BG, lane, 0));
-                        const double2 x1 = *reinterpret_cast<const double2 *>(stage_half(stage + i * BG, lane, 1));
+                        const double2 x0 = *stage_chunk(stage + i * BG, 2 * lane);
+                        const double2 x1 = *stage_chunk(stage + i * BG, 2 * lane + 1);
                         const double xs[BK] = {x0.x, x0.y, x1.x, x1.y};
 #pragma unroll
                         for (int k = 0; k < BK; k++) {
