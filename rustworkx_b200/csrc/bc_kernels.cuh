@@ -261,12 +261,18 @@ __device__ __forceinline__ const double2 *stage_chunk(const double *slot, int c)
 __device__ __forceinline__ void cp_async_row(double *slot, int lane, const double *grow, uint32_t any) {
     const uint32_t base = (uint32_t)__cvta_generic_to_shared(slot);
     const uint32_t d1 = base + 16u * stage_pos(lane), d2 = base + 16u * stage_pos(32 + lane);
-    const int sz1 = ((any >> (lane >> 1)) & 1u) ? 16 : 0;  // src-size 0: zero-fill, no global access
-    const int sz2 = ((any >> (16 + (lane >> 1))) & 1u) ? 16 : 0;
+    // chunks of sectors nobody needs are not copied at all (their stale bytes are never used:
+    // a lane only adds values whose mask bit is set, and those sectors were fetched)
+    const uint32_t on1 = (any >> (lane >> 1)) & 1u, on2 = (any >> (16 + (lane >> 1))) & 1u;
     asm volatile(
-        "cp.async.cg.shared.global [%0], [%1], 16, %2;\n"
-        "cp.async.cg.shared.global [%3], [%4], 16, %5;\n" ::"r"(d1),
-        "l"(grow + 2 * lane), "r"(sz1), "r"(d2), "l"(grow + 64 + 2 * lane), "r"(sz2)
+        "{\n"
+        ".reg .pred p1, p2;\n"
+        "setp.ne.u32 p1, %2, 0;\n"
+        "setp.ne.u32 p2, %5, 0;\n"
+        "@p1 cp.async.cg.shared.global [%0], [%1], 16;\n"
+        "@p2 cp.async.cg.shared.global [%3], [%4], 16;\n"
+        "}\n" ::"r"(d1),
+        "l"(grow + 2 * lane), "r"(on1), "r"(d2), "l"(grow + 64 + 2 * lane), "r"(on2)
         : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
