@@ -113,6 +113,26 @@ int rxc_group_closeness(rxc_graph *g, const uint32_t *group, uint64_t n_group, d
 int rxc_group_betweenness_partial(rxc_graph *g, const uint32_t *group, uint64_t n_group,
                                   const uint32_t *sources, uint64_t n_sources, double *out_sum);
 
+/* weighted all-sources shortest path lengths.  `edge_weight` holds e_bound doubles by
+ * ORIGINAL edge index (slots of removed edges are ignored); weights must be non-negative and not NaN
+ * (the bindings reject them: is_valid_weight, src/lib.rs:303-313).  Distances are bit-identical to
+ * the reference's binary-heap Dijkstra (min over paths of the left-to-right f64 sum).
+ *   rxc_newman_weighted_closeness       <- rustworkx-core/src/centrality.rs:1297-1357 (cost = 1/weight
+ *                                          over Reversed(&graph); per-source sum in vertex order)
+ *   rxc_all_pairs_dijkstra_lengths_rows <- src/shortest_path/all_pairs_dijkstra.rs:36-105: rows
+ *                                          [row_begin, row_end) of the n_live x n_live length matrix in
+ *                                          compacted order; `unreachable_value` where there is no path */
+int rxc_newman_weighted_closeness(rxc_graph *g, const double *edge_weight, int wf_improved,
+                                  double *out /* n_bound */);
+int rxc_all_pairs_dijkstra_lengths_rows(rxc_graph *g, const double *edge_weight, double unreachable_value,
+                                        uint32_t row_begin, uint32_t row_end,
+                                        double *out /* (row_end-row_begin) * n_live */);
+/* closeness of the listed nodes from weighted distances; invert: cost = 1/weight; reversed: follow
+ * incoming edges.  (invert=1, reversed=1) is Newman's closeness; out[i] for sources[i]. */
+int rxc_weighted_closeness_partial(rxc_graph *g, const double *edge_weight, int invert, int reversed,
+                                   const uint32_t *sources, uint64_t n_sources, int wf_improved,
+                                   double *out /* n_sources */);
+
 /* ---- partial calls: a subset of sources (ORIGINAL node indices), no final scaling.  This is the
  * unit a rank runs when sources are sharded across GPUs; partial vectors are additive.
  * `out` is zero-initialised by the call. ----------------------------------------------------------- */

@@ -95,6 +95,10 @@ def lib():
     L.rxo_group_betweenness_centrality.argtypes = [vp, u32p, C.c_size_t, C.c_int, C.c_size_t]
     L.rxo_group_betweenness_partial.restype = C.c_double
     L.rxo_group_betweenness_partial.argtypes = [vp, u32p, C.c_size_t, u32p, C.c_size_t, C.c_int, sp]
+    L.rxo_newman_weighted_closeness_centrality.argtypes = [vp, f64p, C.c_int, C.c_size_t, f64p, u8p, sp]
+    L.rxo_weighted_closeness_partial.argtypes = [vp, f64p, C.c_int, C.c_int, u32p, C.c_size_t, C.c_int,
+                                                 C.c_int, f64p, sp]
+    L.rxo_dijkstra_lengths_rows.argtypes = [vp, f64p, u32p, C.c_size_t, C.c_int, f64p, sp]
     L.rxo_rescale.argtypes = [f64p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int]
     L.rxo_max_threads.restype = C.c_int
     _lib = L
@@ -280,6 +284,46 @@ class OracleGraph:
             self._h, _p(grp, C.c_uint32), grp.shape[0], _p(src, C.c_uint32), src.shape[0],
             int(threads), C.byref(st)))
         return val, st.as_dict()
+
+    # -- weighted shortest path lengths -------------------------------------------
+    def _edge_array(self, weight_by_edge):
+        w = np.zeros(max(self.edge_bound(), 1), dtype=np.float64)
+        w[: self.edge_bound()] = np.asarray(weight_by_edge, dtype=np.float64)[: self.edge_bound()]
+        return w
+
+    def newman_weighted_closeness_centrality(self, weight_by_edge, wf_improved=True,
+                                             parallel_threshold=50, as_arrays=False):
+        nb = self.node_bound()
+        w = self._edge_array(weight_by_edge)
+        out = np.zeros(max(nb, 1), dtype=np.float64)
+        present = np.zeros(max(nb, 1), dtype=np.uint8)
+        st = Stats()
+        self._L.rxo_newman_weighted_closeness_centrality(
+            self._h, _p(w, C.c_double), int(wf_improved), int(parallel_threshold),
+            _p(out, C.c_double), _p(present, C.c_uint8), C.byref(st))
+        return (out[:nb], present[:nb]) if as_arrays else self._opt(out[:nb], present[:nb])
+
+    def weighted_closeness_partial(self, weight_by_edge, sources, invert=True, reversed_=True,
+                                   wf_improved=True, threads=1):
+        w = self._edge_array(weight_by_edge)
+        src = np.ascontiguousarray(sources, dtype=np.uint32)
+        out = np.zeros(max(self.node_bound(), 1), dtype=np.float64)
+        st = Stats()
+        self._L.rxo_weighted_closeness_partial(
+            self._h, _p(w, C.c_double), int(invert), int(reversed_), _p(src, C.c_uint32), src.shape[0],
+            int(wf_improved), int(threads), _p(out, C.c_double), C.byref(st))
+        return out[: self.node_bound()], st.as_dict()
+
+    def dijkstra_lengths_rows(self, cost_by_edge, sources, threads=1):
+        """rows[i, v] = length sources[i] -> v by ORIGINAL node index, NaN where there is no entry."""
+        w = self._edge_array(cost_by_edge)
+        src = np.ascontiguousarray(sources, dtype=np.uint32)
+        nb = self.node_bound()
+        out = np.zeros((src.shape[0], max(nb, 1)), dtype=np.float64)
+        st = Stats()
+        self._L.rxo_dijkstra_lengths_rows(self._h, _p(w, C.c_double), _p(src, C.c_uint32), src.shape[0],
+                                          int(threads), _p(out, C.c_double), C.byref(st))
+        return out[:, :nb]
 
     # -- partial (source subset, un-rescaled) --------------------------------------------------
     def betweenness_partial(self, sources, include_endpoints=False, threads=1):

@@ -860,6 +860,7 @@ void rxo_distance_matrix(const rxo_graph *g, size_t parallel_threshold, int as_u
 typedef struct {
     const rxo_graph *g;
     uint32_t v, e;
+    uint32_t last_e; /* edge index of the arc returned last */
     int phase; /* 0: first list, 1: second list, 2: done */
     int rev;
 } rxo_cursor;
@@ -889,6 +890,7 @@ static int rxo_cursor_next(rxo_cursor *c, uint32_t *w) {
             return 0;
         }
         const rxo_edge_t *ed = &g->edges[c->e];
+        c->last_e = c->e;
         if (g->directed) {
             const int k = c->rev ? 1 : 0;
             *w = ed->node[1 - k];
@@ -1067,4 +1069,160 @@ double rxo_group_betweenness_centrality(const rxo_graph *g, const uint32_t *grou
         }
     }
     return gb;
+}
+
+
+/* ------------------------------------------------------------------ */
+/* weighted shortest path lengths                       */
+/* ------------------------------------------------------------------ */
+
+typedef struct {
+    double score;
+    uint32_t node;
+} rxo_scored;
+
+/* BinaryHeap<MinScored<f64, NodeId>>: a binary min-heap on the score (ties do not affect the
+ * distances) */
+static void rxo_heap_push(rxo_scored **h, size_t *len, size_t *cap, rxo_scored x) {
+    if (*len == *cap) {
+        *cap = *cap ? *cap * 2 : 64;
+        *h = (rxo_scored *)realloc(*h, *cap * sizeof(rxo_scored));
+    }
+    size_t i = (*len)++;
+    while (i > 0) {
+        size_t parent = (i - 1) / 2;
+        if ((*h)[parent].score <= x.score) break;
+        (*h)[i] = (*h)[parent];
+        i = parent;
+    }
+    (*h)[i] = x;
+}
+
+static rxo_scored rxo_heap_pop(rxo_scored *h, size_t *len) {
+    rxo_scored top = h[0];
+    rxo_scored last = h[--(*len)];
+    size_t i = 0, n = *len;
+    for (;;) {
+        size_t c = 2 * i + 1;
+        if (c >= n) break;
+        if (c + 1 < n && h[c + 1].score < h[c].score) c++;
+        if (last.score <= h[c].score) break;
+        h[i] = h[c];
+        i = c;
+    }
+    if (n) h[i] = last;
+    return top;
+}
+
+/* dijkstra without a goal: rustworkx-core/src/shortest_path/dijkstra.rs:100-160 (all_pairs) and
+ * petgraph 0.8.3 algo::dijkstra (Newman; same loop, published algorithm -- petgraph is not in the
+ * tree).  cost[e] by edge index; rev: Reversed(&graph).  score[i] = NAN marks "not in the map". */
+static uint64_t rxo_dijkstra(const rxo_graph *g, uint32_t start, const double *cost, int rev,
+                             double *score, uint8_t *visited, size_t max_index) {
+    for (size_t i = 0; i < max_index; i++) {
+        score[i] = NAN;
+        visited[i] = 0;
+    }
+    rxo_scored *heap = NULL;
+    size_t len = 0, cap = 0;
+    uint64_t te = 0;
+    score[start] = 0.0;
+    rxo_heap_push(&heap, &len, &cap, (rxo_scored){0.0, start});
+    while (len) {
+        rxo_scored top = rxo_heap_pop(heap, &len);
+        uint32_t node = top.node;
+        if (visited[node]) continue;
+        rxo_cursor c;
+        uint32_t next;
+        rxo_cursor_init(&c, g, node, rev);
+        while (rxo_cursor_next(&c, &next)) {
+            te++;
+            if (visited[next]) continue;
+            double next_score = top.score + cost[c.last_e];
+            if (score[next] == score[next]) { /* Some(current_score) */
+                if (next_score < score[next]) {
+                    score[next] = next_score;
+                    rxo_heap_push(&heap, &len, &cap, (rxo_scored){next_score, next});
+                }
+            } else {
+                score[next] = next_score;
+                rxo_heap_push(&heap, &len, &cap, (rxo_scored){next_score, next});
+            }
+        }
+        visited[node] = 1;
+    }
+    free(heap);
+    return te;
+}
+
+/* closeness from weighted distances for a subset of sources: out[sources[i]].  invert: cost = 1/w
+ * (centrality.rs:1319-1320).  The reference sums a HashMap's values (:1343, hash order); here the
+ * sum runs in ascending node index. */
+void rxo_weighted_closeness_partial(const rxo_graph *g, const double *weight_by_edge, int invert,
+                                    int rev, const uint32_t *sources, size_t k, int wf_improved,
+                                    int threads, double *out, rxo_stats *stats) {
+    size_t max_index = rxo_node_bound(g), eb = rxo_edge_bound(g);
+    double *cost = (double *)malloc((eb ? eb : 1) * sizeof(double));
+    for (size_t e = 0; e < eb; e++) cost[e] = invert ? 1.0 / weight_by_edge[e] : weight_by_edge[e];
+    if (stats) memset(stats, 0, sizeof(*stats));
+    long kk = (long)k;
+    (void)threads;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads) if (threads > 1)
+    for (long i = 0; i < kk; i++) {
+        uint32_t s = sources[i];
+        double *score = (double *)malloc((max_index ? max_index : 1) * sizeof(double));
+        uint8_t *visited = (uint8_t *)malloc(max_index ? max_index : 1);
+        uint64_t te = rxo_dijkstra(g, s, cost, rev, score, visited, max_index);
+        size_t reachable = 0;
+        double dists_sum = 0.0;
+        for (size_t v = 0; v < max_index; v++)
+            if (score[v] == score[v]) {
+                reachable++;
+                dists_sum += score[v];
+            }
+        double c = 0.0;
+        if (reachable != 1) {
+            c = (double)(reachable - 1) / dists_sum;
+            if (wf_improved) c = c * (double)(reachable - 1) / (double)(g->node_count - 1);
+        }
+        out[s] = c;
+        rxo_stats_add(stats, te, 0, reachable, 0);
+        free(score);
+        free(visited);
+    }
+    free(cost);
+}
+
+/* newman_weighted_closeness_centrality, centrality.rs:1297-1357 */
+void rxo_newman_weighted_closeness_centrality(const rxo_graph *g, const double *weight_by_edge,
+                                              int wf_improved, size_t parallel_threshold,
+                                              double *out, uint8_t *present, rxo_stats *stats) {
+    size_t max_index = rxo_node_bound(g);
+    for (size_t i = 0; i < max_index; i++) {
+        out[i] = 0.0;
+        present[i] = g->nodes[i].alive;
+    }
+    size_t k;
+    uint32_t *ids = rxo_live_nodes(g, &k);
+    int threads = (g->node_count >= parallel_threshold) ? rxo_max_threads() : 1;
+    rxo_weighted_closeness_partial(g, weight_by_edge, 1, 1, ids, k, wf_improved, threads, out, stats);
+    free(ids);
+}
+
+/* all_pairs_dijkstra_path_lengths, src/shortest_path/all_pairs_dijkstra.rs:36-105, for a subset of
+ * sources: out[i * node_bound + v] = length sources[i] -> v, NAN where the map has no entry. */
+void rxo_dijkstra_lengths_rows(const rxo_graph *g, const double *cost_by_edge, const uint32_t *sources,
+                               size_t k, int threads, double *out, rxo_stats *stats) {
+    size_t max_index = rxo_node_bound(g);
+    if (stats) memset(stats, 0, sizeof(*stats));
+    long kk = (long)k;
+    (void)threads;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads) if (threads > 1)
+    for (long i = 0; i < kk; i++) {
+        uint8_t *visited = (uint8_t *)malloc(max_index ? max_index : 1);
+        uint64_t te = rxo_dijkstra(g, sources[i], cost_by_edge, 0, out + (size_t)i * max_index, visited,
+                                   max_index);
+        rxo_stats_add(stats, te, 0, 0, 0);
+        free(visited);
+    }
 }

@@ -111,6 +111,20 @@ double rxo_group_betweenness_partial(const rxo_graph *g, const uint32_t *group, 
                                      const uint32_t *sources, size_t n_sources, int threads,
                                      rxo_stats *stats);
 
+/* ---- weighted shortest path lengths.  Weights / costs are dense over the edge
+ *      bound by ORIGINAL edge index; non-negative, not NaN. ---- */
+/* rustworkx-core/src/centrality.rs:1297-1357 */
+void rxo_newman_weighted_closeness_centrality(const rxo_graph *g, const double *weight_by_edge,
+                                              int wf_improved, size_t parallel_threshold,
+                                              double *out, uint8_t *present, rxo_stats *stats);
+void rxo_weighted_closeness_partial(const rxo_graph *g, const double *weight_by_edge, int invert,
+                                    int rev, const uint32_t *sources, size_t k, int wf_improved,
+                                    int threads, double *out, rxo_stats *stats);
+/* src/shortest_path/all_pairs_dijkstra.rs:36-105 + rustworkx-core/src/shortest_path/dijkstra.rs:100-160;
+ * out[i * node_bound + v], NAN where the reference's map has no entry */
+void rxo_dijkstra_lengths_rows(const rxo_graph *g, const double *cost_by_edge, const uint32_t *sources,
+                               size_t k, int threads, double *out, rxo_stats *stats);
+
 /* _rescale, rustworkx-core/src/centrality.rs:221-252, on a dense vector */
 void rxo_rescale(double *x, size_t len, size_t node_count, int normalized, int directed,
                  int include_endpoints);

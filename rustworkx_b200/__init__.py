@@ -30,7 +30,12 @@ from .graph import (  # noqa: F401
     PyDiGraph,
     PyGraph,
 )
-from .iterators import CentralityMapping, EdgeCentralityMapping  # noqa: F401
+from .iterators import (  # noqa: F401
+    AllPairsPathLengthMapping,
+    CentralityMapping,
+    EdgeCentralityMapping,
+    PathLengthMapping,
+)
 from .random_graph import (  # noqa: F401
     barabasi_albert_graph,
     directed_gnm_random_graph,
@@ -220,6 +225,79 @@ def digraph_unweighted_average_shortest_path_length(graph, /, parallel_threshold
     return _average_length(graph, _bool(as_undirected, "as_undirected"), _bool(disconnected, "disconnected"))
 
 
+def _valid_weight(val):
+    """``is_valid_weight`` (``src/lib.rs:303-313``) after pyo3's ``f64`` extraction."""
+    if isinstance(val, (str, bytes)) or not hasattr(val, "__float__") and not hasattr(val, "__index__"):
+        raise TypeError(f"'{type(val).__name__}' object cannot be interpreted as a float")
+    val = float(val)
+    if np.signbit(val):
+        raise ValueError("Negative weights not supported.")
+    if val != val:
+        raise ValueError("NaN weights not supported.")
+    return val
+
+
+def _edge_weight_vector(graph, weight_fn, default_weight, validate_default):
+    """Dense ``e_bound`` vector of edge weights by ORIGINAL edge index: ``weight_fn(payload)`` per
+    live edge through ``CostFn::call`` (``src/lib.rs:347-358``), or ``default_weight`` everywhere."""
+    _, e_bound = graph._bounds()
+    if weight_fn is None:
+        dw = _valid_weight(default_weight) if validate_default else float(default_weight)
+        return np.full(max(e_bound, 1), dw, dtype=np.float64)
+    if not callable(weight_fn):
+        raise TypeError(f"'{type(weight_fn).__name__}' object is not callable")
+    w = np.zeros(max(e_bound, 1), dtype=np.float64)
+    for e in graph._live_edges():
+        w[int(e)] = _valid_weight(weight_fn(graph._edata.get(int(e))))
+    return w
+
+
+def _newman(graph, weight_fn, wf_improved, default_weight, parallel_threshold):
+    wf_improved = _bool(wf_improved, "wf_improved")
+    default_weight = _f64(default_weight, "default_weight")
+    _usize(parallel_threshold, "parallel_threshold")
+    w = _edge_weight_vector(graph, weight_fn, default_weight, validate_default=False)
+    dg = device_snapshot(graph)
+    return _node_mapping(dg, dg.newman_weighted_closeness(w, wf_improved))
+
+
+def graph_newman_weighted_closeness_centrality(graph, weight_fn=None, wf_improved=True,
+                                               default_weight=1.0, parallel_threshold=50):
+    """``rustworkx.graph_newman_weighted_closeness_centrality`` (``src/centrality.rs:432-466``)."""
+    return _newman(_graph_arg(graph, PyGraph, "PyGraph"), weight_fn, wf_improved, default_weight,
+                   parallel_threshold)
+
+
+def digraph_newman_weighted_closeness_centrality(graph, weight_fn=None, wf_improved=True,
+                                                 default_weight=1.0, parallel_threshold=50):
+    """``rustworkx.digraph_newman_weighted_closeness_centrality`` (``src/centrality.rs:512-546``)."""
+    return _newman(_graph_arg(graph, PyDiGraph, "PyDiGraph"), weight_fn, wf_improved, default_weight,
+                   parallel_threshold)
+
+
+def _all_pairs_lengths(graph, edge_cost_fn):
+    # src/shortest_path/all_pairs_dijkstra.rs:36-105
+    keys = np.asarray(graph.node_indices(), dtype=np.int64)
+    if keys.size == 0:
+        return AllPairsPathLengthMapping()
+    if graph.num_edges() == 0:
+        return AllPairsPathLengthMapping(keys, None)
+    w = _edge_weight_vector(graph, edge_cost_fn, 1.0, validate_default=True)
+    rows = device_snapshot(graph).all_pairs_dijkstra_lengths_rows(w)
+    return AllPairsPathLengthMapping(keys, rows)
+
+
+def graph_all_pairs_dijkstra_path_lengths(graph, edge_cost_fn, /):
+    """``rustworkx.graph_all_pairs_dijkstra_path_lengths`` (``src/shortest_path/mod.rs``; core of
+    the call: ``src/shortest_path/all_pairs_dijkstra.rs:36-105``)."""
+    return _all_pairs_lengths(_graph_arg(graph, PyGraph, "PyGraph"), edge_cost_fn)
+
+
+def digraph_all_pairs_dijkstra_path_lengths(graph, edge_cost_fn, /):
+    """``rustworkx.digraph_all_pairs_dijkstra_path_lengths``."""
+    return _all_pairs_lengths(_graph_arg(graph, PyDiGraph, "PyDiGraph"), edge_cost_fn)
+
+
 def _group_arg(graph, group):
     """pyo3 ``Vec<usize>`` extraction plus the binding's membership check
     (``src/centrality.rs:1216-1222``): ``ValueError`` for an index that is not in the graph."""
@@ -316,4 +394,18 @@ def group_closeness_centrality(graph, group):
 @_rustworkx_dispatch
 def group_betweenness_centrality(graph, group, normalized=True, parallel_threshold=50):
     """Group betweenness centrality of a set of nodes (``rustworkx/__init__.py:1398-1440``)."""
+    raise TypeError(f"Invalid Input Type {type(graph)} for graph")
+
+
+@_rustworkx_dispatch
+def newman_weighted_closeness_centrality(graph, weight_fn=None, wf_improved=True, default_weight=1.0,
+                                         parallel_threshold=50):
+    """Newman's weighted closeness centrality (``rustworkx/__init__.py``; core
+    ``rustworkx-core/src/centrality.rs:1297-1357``)."""
+    raise TypeError(f"Invalid Input Type {type(graph)} for graph")
+
+
+@_rustworkx_dispatch
+def all_pairs_dijkstra_path_lengths(graph, edge_cost_fn):
+    """Shortest path lengths between all pairs of nodes (``rustworkx/__init__.py``)."""
     raise TypeError(f"Invalid Input Type {type(graph)} for graph")

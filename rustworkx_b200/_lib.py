@@ -73,6 +73,10 @@ SYMBOLS = {
     "rxc_group_betweenness": (C.c_int, [_vp, _u32p, C.c_uint64, C.c_int, _f64p]),
     "rxc_group_closeness": (C.c_int, [_vp, _u32p, C.c_uint64, _f64p]),
     "rxc_group_betweenness_partial": (C.c_int, [_vp, _u32p, C.c_uint64, _u32p, C.c_uint64, _f64p]),
+    "rxc_newman_weighted_closeness": (C.c_int, [_vp, _f64p, C.c_int, _f64p]),
+    "rxc_all_pairs_dijkstra_lengths_rows": (C.c_int, [_vp, _f64p, C.c_double, C.c_uint32, C.c_uint32, _f64p]),
+    "rxc_weighted_closeness_partial": (C.c_int, [_vp, _f64p, C.c_int, C.c_int, _u32p, C.c_uint64, C.c_int,
+                                                 _f64p]),
     "rxc_betweenness_partial": (C.c_int, [_vp, _u32p, C.c_uint64, C.c_int, _f64p]),
     "rxc_edge_betweenness_partial": (C.c_int, [_vp, _u32p, C.c_uint64, _f64p]),
     "rxc_closeness_partial": (C.c_int, [_vp, _u32p, C.c_uint64, C.c_int, _f64p]),
@@ -258,6 +262,36 @@ class DeviceGraph:
         check(lib().rxc_group_betweenness_partial(self._h, p_u32(grp), grp.shape[0], p_u32(src),
                                                   src.shape[0], C.byref(out)))
         return float(out.value)
+
+    # ---- weighted shortest path lengths (edge_weight: e_bound doubles by original edge index) ----
+    def _edge_weights(self, edge_weight):
+        w = np.zeros(max(self.e_bound, 1), dtype=np.float64)
+        w[: self.e_bound] = np.asarray(edge_weight, dtype=np.float64)[: self.e_bound]
+        return w
+
+    def newman_weighted_closeness(self, edge_weight, wf_improved):
+        w = self._edge_weights(edge_weight)
+        out = np.zeros(max(self.n_bound, 1), dtype=np.float64)
+        check(lib().rxc_newman_weighted_closeness(self._h, p_f64(w), int(wf_improved), p_f64(out)))
+        return out[: self.n_bound]
+
+    def weighted_closeness_partial(self, edge_weight, sources, invert=True, reversed_=True, wf_improved=True):
+        w = self._edge_weights(edge_weight)
+        src = np.ascontiguousarray(sources, dtype=np.uint32)
+        out = np.zeros(max(src.shape[0], 1), dtype=np.float64)
+        check(lib().rxc_weighted_closeness_partial(self._h, p_f64(w), int(invert), int(reversed_), p_u32(src),
+                                                   src.shape[0], int(wf_improved), p_f64(out)))
+        return out[: src.shape[0]]
+
+    def all_pairs_dijkstra_lengths_rows(self, edge_weight, row_begin=0, row_end=None,
+                                        unreachable_value=float("nan")):
+        w = self._edge_weights(edge_weight)
+        row_end = self.n_live if row_end is None else row_end
+        out = np.empty((row_end - row_begin, self.n_live), dtype=np.float64)
+        if out.size:
+            check(lib().rxc_all_pairs_dijkstra_lengths_rows(self._h, p_f64(w), float(unreachable_value),
+                                                            int(row_begin), int(row_end), p_f64(out)))
+        return out
 
     # ---- partial calls (source shards; un-rescaled) ---------------------------------------------
     def betweenness_partial(self, sources, include_endpoints=False):

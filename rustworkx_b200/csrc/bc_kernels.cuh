@@ -278,12 +278,31 @@ __device__ __forceinline__ void cp_async_row(double *slot, int lane, const doubl
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.wait_all;\n" ::: "memory");
 }
+__device__ __forceinline__ void cp_async_commit() {
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+// wait until at most n (warp-uniform, < 8) of this thread's cp.async groups are still pending
+__device__ __forceinline__ void cp_async_wait_pending(int n) {
+    switch (n) {
+        case 0: asm volatile("cp.async.wait_group 0;\n" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;\n" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;\n" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;\n" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;\n" ::: "memory"); break;
+        case 5: asm volatile("cp.async.wait_group 5;\n" ::: "memory"); break;
+        case 6: asm volatile("cp.async.wait_group 6;\n" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 7;\n" ::: "memory"); break;
+    }
+}
 
 // acc[k] += rows[v][lane][k] over the arcs in nz (lanes of v_lane / m_lane with a non-empty mask)
 // for the sources the arc's mask names, arc order preserved; up to STAGE rows in flight per warp.
 __device__ __forceinline__ void bc_gather(const double *rows, uint32_t v_lane, const Mask128 &m_lane,
                                           uint32_t nz, int lane, double *stage, double (&acc)[BK],
                                           Mask128 &seen, unsigned long long &dag) {
+    // Batches of STAGE rows.  (A ring that tops itself up row by row, so that STAGE rows stay in
+    // flight for the whole arc list, was measured: 80 -> 86 ms per 1024 sources -- its bookkeeping
+    // costs more issue slots than the shorter waits give back.)
     while (nz) {
         uint32_t todo = nz;
         int cnt = 0;
@@ -299,6 +318,7 @@ __device__ __forceinline__ void bc_gather(const double *rows, uint32_t v_lane, c
             }
         }
         cp_async_wait_all();
+        __syncwarp();  // the chunks a lane reads were copied by other lanes
 #pragma unroll
         for (int i = 0; i < STAGE; i++) {
             if (i < cnt) {
@@ -316,6 +336,7 @@ __device__ __forceinline__ void bc_gather(const double *rows, uint32_t v_lane, c
                 dag += mask_popc(mj);
             }
         }
+        __syncwarp();  // the slots may be refilled by other lanes from here on
     }
 }
 

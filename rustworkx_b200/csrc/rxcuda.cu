@@ -10,8 +10,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <chrono>
 #include <exception>
+#include <limits>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -24,6 +26,7 @@
 #include "bfs_kernels.cuh"
 #include "common.cuh"
 #include "csr_build.cuh"
+#include "wsp_kernels.cuh"
 #include "snapshot.hpp"
 
 namespace rxc {
@@ -478,29 +481,18 @@ static void bc_enable_smem() {
     done = true;
 }
 
-// Group betweenness (bc_kernels.cuh, "pair mode"): the group's vertices on the device.
-struct GroupSpec {
-    const uint32_t *d_members;  // compact ids, distinct
-    uint32_t n_members;
-    const uint32_t *d_blocked;  // bitmap over compact ids
-};
-
-static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endpoints,
-                   bool edge_mode, double *d_acc, const GroupSpec *grp = nullptr) {
-    bc_enable_smem();
+// Size (or re-use) the handle's betweenness scratch for up to `total_groups` groups of 128 sources;
+// returns the number of groups a batch can hold.  Shared by the weighted shortest-path driver.
+static uint64_t bc_ws_ensure(rxc_graph *g, uint64_t total_groups) {
     const uint32_t n = g->host.n_live;
-    if (sources.empty() || n == 0) return;
-    const uint32_t per = grp ? BGP : BG;  // sources per group (pair mode: two slots per source)
-    const uint64_t total_groups = (sources.size() + per - 1) / per;
     const uint32_t lcap = n + 2;
-    const uint64_t qcap = (uint64_t)BG * n;  // worst case: a vertex sits on a different level per source
+    const uint64_t qcap = (uint64_t)BG * n;
     // bytes per group: 1 KB row + worst-case queues + two tagged mask arrays + visited + level tables
     const double per_group = (double)n * (1024.0 + 20.0 * BG + 64.0 + 16.0) + (double)lcap * 8.0 + 4096.0;
     uint64_t ng = g_opt.bc_groups > 0 ? (uint64_t)g_opt.bc_groups
                                       : std::max<uint64_t>(1, (8ull << 20) / std::max<uint32_t>(n, 1));
     ng = std::min<uint64_t>(ng, 64);
     ng = std::min<uint64_t>(ng, total_groups);
-
     BcWorkspace &ws = g->bc_ws;
     cudaStream_t st = g->stream;
     if (ws.ng > 0 && ws.ng < ng && ws.wanted >= ng) ng = ws.ng;  // already clamped by memory for this request
@@ -531,6 +523,28 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
         RXC_CUDA(cudaMemsetAsync(ws.P0.p, 0, ws.P0.bytes(), st));
         RXC_CUDA(cudaMemsetAsync(ws.P1.p, 0, ws.P1.bytes(), st));
     }
+    return std::min<uint64_t>(ng, ws.ng);
+}
+
+// Group betweenness (bc_kernels.cuh, "pair mode"): the group's vertices on the device.
+struct GroupSpec {
+    const uint32_t *d_members;  // compact ids, distinct
+    uint32_t n_members;
+    const uint32_t *d_blocked;  // bitmap over compact ids
+};
+
+static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endpoints,
+                   bool edge_mode, double *d_acc, const GroupSpec *grp = nullptr) {
+    bc_enable_smem();
+    const uint32_t n = g->host.n_live;
+    if (sources.empty() || n == 0) return;
+    const uint32_t per = grp ? BGP : BG;  // sources per group (pair mode: two slots per source)
+    const uint64_t total_groups = (sources.size() + per - 1) / per;
+    const uint32_t lcap = n + 2;
+    const uint64_t qcap = (uint64_t)BG * n;  // worst case: a vertex sits on a different level per source
+    const uint64_t ng = bc_ws_ensure(g, total_groups);
+    BcWorkspace &ws = g->bc_ws;
+    cudaStream_t st = g->stream;
 
     BcParams p{};
     p.sc = ws.sc.p;
@@ -1165,6 +1179,193 @@ static uint64_t group_closeness_dsum(rxc_graph *g, const std::vector<uint32_t> &
     return dsum;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// weighted all-sources shortest path lengths (wsp_kernels.cuh)
+// ------------------------------------------------------------------------------------------------
+enum class WspMode { Closeness, Rows };
+
+struct WspCosts {
+    DevBuf<double> pull;  // cost of every arc of the pull adjacency
+    bool has_inf = false; // some cost is +inf: "reached" and "finite distance" may differ
+};
+
+// edge_weight: e_bound doubles by ORIGINAL edge index (dead slots ignored).  reversed: the search
+// follows incoming edges (Reversed(&graph), centrality.rs:1341), so a vertex pulls over its OUT-arcs.
+static void wsp_costs(rxc_graph *g, const double *edge_weight, bool invert, bool reversed, WspCosts &c) {
+    const DeviceCSR &pull = reversed ? g->succ() : g->pred();
+    if (!pull.eid.p && pull.arcs) throw std::invalid_argument("snapshot has no edge ids");
+    const size_t eb = g->host.e_bound;
+    DevBuf<double> d_w;
+    d_w.alloc(std::max<size_t>(eb, 1));
+    if (eb) RXC_CUDA(cudaMemcpyAsync(d_w.p, edge_weight, eb * 8, cudaMemcpyHostToDevice, g->stream));
+    c.pull.alloc(std::max<uint64_t>(pull.arcs, 1));
+    if (pull.arcs) {
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>((pull.arcs + BLOCK - 1) / BLOCK, 148 * 16);
+        wsp_arc_costs_kernel<<<blocks, BLOCK, 0, g->stream>>>(pull.eid.p, d_w.p, pull.arcs, invert ? 1 : 0, c.pull.p);
+    }
+    RXC_CUDA(cudaStreamSynchronize(g->stream));
+}
+
+// sources: compact ids, pairwise distinct.  Closeness: out[i] = closeness of sources[i] and, when
+// pairs != nullptr, pairs[2i], pairs[2i+1] = (vertices at finite distance, sum of distances).
+// Rows: out[i * n + v] = length of the shortest path sources[i] -> v, +inf where there is none.
+static void wsp_run(rxc_graph *g, bool reversed, const double *d_cost, const std::vector<uint32_t> &sources,
+                    WspMode mode, bool wf_improved, double *out, double *pairs) {
+    const uint32_t n = g->host.n_live;
+    if (sources.empty() || n == 0) return;
+    static bool attr_done[64] = {false};
+    if (!attr_done[g->device & 63]) {
+        RXC_CUDA(cudaFuncSetAttribute(wsp_relax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM_BYTES));
+        attr_done[g->device & 63] = true;
+    }
+    const uint64_t total_groups = (sources.size() + BG - 1) / BG;
+    const uint32_t lcap = n + 2;
+    uint64_t ng = bc_ws_ensure(g, total_groups);
+    if (mode == WspMode::Rows)  // keep one batch of output rows under 4 GiB
+        ng = std::min<uint64_t>(ng, std::max<uint64_t>(1, (4ull << 30) / ((uint64_t)n * BG * 8)));
+    BcWorkspace &ws = g->bc_ws;
+    cudaStream_t st = g->stream;
+    const DeviceCSR &pull = reversed ? g->succ() : g->pred();
+    const DeviceCSR &push = reversed ? g->pred() : g->succ();
+
+    WspParams p{};
+    p.row = pull.row.p;
+    p.col = pull.col.p;
+    p.cost = d_cost;
+    p.srow = push.row.p;
+    p.scol = push.col.p;
+    p.dist = ws.sc.p;
+    p.C0 = ws.P0.p;
+    p.C1 = ws.P1.p;
+    p.maybe = ws.maybe.p;
+    p.qv = ws.qv.p;
+    p.lvlcnt = ws.lvlcnt.p;
+    p.lvl_total = ws.lvl_total.p;
+    p.stats = g->d_stats.p;
+    p.src = ws.src.p;
+    p.qstride = (uint64_t)BG * n;
+    p.n = n;
+    p.lcap = lcap;
+    p.mwords = (n + 31) / 32;
+
+    const uint32_t vblocks = (n + BLOCK - 1) / BLOCK;
+    const uint32_t ntiles = (n + WSP_TILE - 1) / WSP_TILE;
+    DevBuf<double> part_sum, d_vals, d_rows;
+    DevBuf<unsigned long long> part_cnt;
+    if (mode == WspMode::Closeness) {
+        part_sum.alloc((size_t)ng * ntiles * BG);
+        part_cnt.alloc((size_t)ng * ntiles * BG);
+        d_vals.alloc((size_t)ng * BG * 3);
+    } else {
+        d_rows.alloc((size_t)ng * BG * n);
+    }
+    std::vector<uint32_t> h_src((size_t)ng * BG), h_totals;
+    std::vector<double> h_vals((size_t)ng * BG * 3);
+    uint32_t &clear_levels = ws.dirty_levels;
+    uint32_t &tagbase = ws.tagbase;
+
+    for (uint64_t g0 = 0; g0 < total_groups; g0 += ng) {
+        const uint32_t bg = (uint32_t)std::min<uint64_t>(ng, total_groups - g0);
+        std::fill(h_src.begin(), h_src.end(), NO_SOURCE);
+        const size_t s0 = (size_t)g0 * BG;
+        const size_t cnt = std::min(sources.size() - s0, (size_t)bg * BG);
+        std::copy(sources.begin() + s0, sources.begin() + s0 + cnt, h_src.begin());
+        if ((uint64_t)tagbase + lcap + 16 > 0xFFFFFFF0ull) {
+            RXC_CUDA(cudaMemsetAsync(ws.P0.p, 0, ws.P0.bytes(), st));
+            RXC_CUDA(cudaMemsetAsync(ws.P1.p, 0, ws.P1.bytes(), st));
+            tagbase = 0;
+        }
+        p.tagbase = tagbase;
+        p.ngroups = bg;
+        RXC_CUDA(cudaEventRecord(g->ev[0], st));
+        RXC_CUDA(cudaMemcpyAsync(ws.src.p, h_src.data(), (size_t)bg * BG * 4, cudaMemcpyHostToDevice, st));
+        RXC_CUDA(cudaMemset2DAsync(ws.lvlcnt.p, (size_t)lcap * 4, 0, (size_t)clear_levels * 4, ws.ng, st));
+        RXC_CUDA(cudaMemsetAsync(ws.lvl_total.p, 0, (size_t)clear_levels * 4, st));
+        wsp_fill_kernel<<<148 * 8, BLOCK, 0, st>>>(ws.sc.p, (uint64_t)bg * n * BG);
+        wsp_seed_kernel<<<bg, 32, 0, st>>>(p);
+        g->stats.launches += 2;
+        uint32_t launched = 0;
+        const uint32_t R = run_levels(
+            g, ws.lvl_total.p, n + 1,
+            [&](uint32_t round) {
+                wsp_mark_kernel<<<dim3(MARK_CTAS * 4, bg), BLOCK, 0, st>>>(p, round);
+                wsp_relax_kernel<<<dim3(vblocks, bg), BLOCK, BC_SMEM_BYTES, st>>>(p, round);
+                launched++;
+            },
+            h_totals);
+        g->stats.launches += 2 * launched;
+        g->stats.levels += R;
+        clear_levels = std::min<uint32_t>(lcap, launched + 2);
+        RXC_CUDA(cudaEventRecord(g->ev[1], st));
+        if (mode == WspMode::Closeness) {
+            wsp_sums_tile_kernel<<<dim3(ntiles, bg), BG, 0, st>>>(p, part_sum.p, part_cnt.p);
+            wsp_sums_finish_kernel<<<bg, BG, 0, st>>>(p, part_sum.p, part_cnt.p, ntiles, wf_improved ? 1 : 0,
+                                                       (unsigned long long)n, d_vals.p);
+            g->stats.launches += 2;
+            RXC_CUDA(cudaEventRecord(g->ev[2], st));
+            const double t0 = now_ms();
+            RXC_CUDA(cudaMemcpyAsync(h_vals.data(), d_vals.p, (size_t)bg * BG * 3 * 8, cudaMemcpyDeviceToHost, st));
+            RXC_CUDA(cudaStreamSynchronize(st));
+            RXC_CUDA(cudaGetLastError());
+            std::copy(h_vals.begin(), h_vals.begin() + cnt, out + s0);
+            if (pairs) std::copy(h_vals.begin() + (size_t)bg * BG, h_vals.begin() + (size_t)bg * BG + 2 * cnt, pairs + 2 * s0);
+            g->stats.ms_d2h += now_ms() - t0;
+        } else {
+            wsp_rows_kernel<<<dim3((n + 31) / 32, BG / 32, bg), BLOCK, 0, st>>>(p, d_rows.p, n);
+            g->stats.launches++;
+            // te / v counters come from the tile pass; run it for the counters only when cheap
+            RXC_CUDA(cudaEventRecord(g->ev[2], st));
+            const double t0 = now_ms();
+            RXC_CUDA(cudaMemcpyAsync(out + s0 * n, d_rows.p, cnt * (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+            RXC_CUDA(cudaStreamSynchronize(st));
+            RXC_CUDA(cudaGetLastError());
+            g->stats.ms_d2h += now_ms() - t0;
+        }
+        float f = 0.f, b = 0.f;
+        RXC_CUDA(cudaEventElapsedTime(&f, g->ev[0], g->ev[1]));
+        RXC_CUDA(cudaEventElapsedTime(&b, g->ev[1], g->ev[2]));
+        g->stats.ms_forward += f;
+        g->stats.ms_backward += b;
+        g->stats.batches++;
+        g->stats.sources += cnt;
+        tagbase += launched + 8;
+    }
+}
+
+static bool has_inf_cost(const rxc_graph *g, const double *edge_weight, const uint8_t *alive, bool invert) {
+    for (size_t e = 0; e < g->host.e_bound; e++) {
+        if (alive && !alive[e]) continue;
+        const double w = edge_weight[e];
+        if (invert ? (w == 0.0) : std::isinf(w)) return true;
+    }
+    return false;
+}
+
+// closeness of the listed sources (compact ids, distinct) from weighted distances
+static void wsp_closeness(rxc_graph *g, const double *edge_weight, bool invert, bool reversed,
+                          const std::vector<uint32_t> &sources, bool wf_improved, double *out) {
+    std::lock_guard<std::mutex> lock(g->mu);
+    begin_call(g);
+    if (!sources.empty() && g->host.n_live) {
+        WspCosts c;
+        wsp_costs(g, edge_weight, invert, reversed, c);
+        std::vector<double> pairs(sources.size() * 2);
+        wsp_run(g, reversed, c.pull.p, sources, WspMode::Closeness, wf_improved, out, pairs.data());
+        if (has_inf_cost(g, edge_weight, nullptr, invert)) {
+            // A vertex reached only through +inf-cost edges is "reachable" with an infinite distance
+            // (dijkstra.rs:139-141 inserts the first score unconditionally): the sum is +inf and the
+            // closeness 0.  Count the reachable vertices with the unweighted kernel.
+            std::vector<double> rs(sources.size() * 2);
+            bfs_dispatch(g, reversed ? g->pred() : g->succ(), sources, BfsMode::Sums, false, 0.0, rs.data());
+            for (size_t i = 0; i < sources.size(); i++)
+                if (rs[2 * i] > pairs[2 * i]) out[i] = 0.0;
+        }
+    }
+    end_call(g);
+    fetch_stats(g);
+}
+
 static const DeviceCSR &symmetric_csr(rxc_graph *g) {
     if (!g->host.directed) return g->out;
     if (!g->has_sym) {
@@ -1488,6 +1689,78 @@ int rxc_group_closeness(rxc_graph *g, const uint32_t *group, uint64_t n_group, d
         const uint64_t dist_sum = group_closeness_dsum(g, members);
         if (dist_sum == 0) return;
         *out = (double)(node_count - group_size) / (double)dist_sum;
+    });
+}
+
+
+int rxc_weighted_closeness_partial(rxc_graph *g, const double *edge_weight, int invert, int reversed,
+                                   const uint32_t *sources, uint64_t n_sources, int wf_improved,
+                                   double *out) {
+    if (!g || !out || (n_sources && !sources) || (g->host.e_bound && !edge_weight)) return RXC_ERR_INVALID;
+    return guarded([&] {
+        const std::vector<uint32_t> src = to_compact(g, sources, n_sources);
+        // duplicates: closeness is per source, so compute each distinct source once
+        std::vector<uint32_t> uniq = src;
+        std::sort(uniq.begin(), uniq.end());
+        uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+        std::vector<double> vals(uniq.size());
+        wsp_closeness(g, edge_weight, invert != 0, reversed != 0, uniq, wf_improved != 0, vals.data());
+        for (size_t i = 0; i < src.size(); i++)
+            out[i] = vals[std::lower_bound(uniq.begin(), uniq.end(), src[i]) - uniq.begin()];
+    });
+}
+
+int rxc_newman_weighted_closeness(rxc_graph *g, const double *edge_weight, int wf_improved, double *out) {
+    if (!g || !out || (g->host.e_bound && !edge_weight)) return RXC_ERR_INVALID;
+    return guarded([&] {
+        // newman_weighted_closeness_centrality, rustworkx-core/src/centrality.rs:1297-1357:
+        // dijkstra over Reversed(&graph) with cost 1 / weight
+        std::fill(out, out + g->host.n_bound, 0.0);
+        run_on_shards(g, [&](rxc_graph *r, size_t k, size_t nk) {
+            const std::vector<uint32_t> src = shard_sources(r->host.n_live, k, nk);
+            std::vector<double> vals(src.size());
+            wsp_closeness(r, edge_weight, true, true, src, wf_improved != 0, vals.data());
+            for (size_t i = 0; i < src.size(); i++) out[r->host.orig_of_compact[src[i]]] = vals[i];
+        });
+    });
+}
+
+int rxc_all_pairs_dijkstra_lengths_rows(rxc_graph *g, const double *edge_weight, double unreachable_value,
+                                        uint32_t row_begin, uint32_t row_end, double *out) {
+    if (!g || (!out && row_end > row_begin) || (g->host.e_bound && !edge_weight)) return RXC_ERR_INVALID;
+    return guarded([&] {
+        if (row_begin > row_end || row_end > g->host.n_live)
+            throw std::invalid_argument("row range outside [0, n_live]");
+        // all_pairs_dijkstra_path_lengths, src/shortest_path/all_pairs_dijkstra.rs:36-105: dijkstra
+        // along outgoing edges from every node
+        run_on_shards(g, [&](rxc_graph *r, size_t k, size_t nk) {
+            const uint64_t rows = row_end - row_begin;
+            const uint32_t b = row_begin + (uint32_t)(rows * k / nk), e = row_begin + (uint32_t)(rows * (k + 1) / nk);
+            if (b == e) return;
+            std::lock_guard<std::mutex> lock(r->mu);
+            begin_call(r);
+            const uint32_t n = r->host.n_live;
+            std::vector<uint32_t> src(e - b);
+            for (uint32_t i = b; i < e; i++) src[i - b] = i;
+            double *dst = out + (size_t)(b - row_begin) * n;
+            WspCosts c;
+            wsp_costs(r, edge_weight, false, false, c);
+            wsp_run(r, false, c.pull.p, src, WspMode::Rows, false, dst, nullptr);
+            const size_t len = (size_t)(e - b) * n;
+            const double inf = std::numeric_limits<double>::infinity();
+            if (has_inf_cost(r, edge_weight, nullptr, false)) {
+                // reached through +inf-cost edges only: keep +inf; never reached: unreachable_value
+                std::vector<double> hops(len);
+                bfs_dispatch(r, r->succ(), src, BfsMode::Rows, false, -1.0, hops.data());
+                for (size_t i = 0; i < len; i++)
+                    if (hops[i] < 0.0) dst[i] = unreachable_value;
+            } else if (!(unreachable_value == inf)) {
+                for (size_t i = 0; i < len; i++)
+                    if (dst[i] == inf) dst[i] = unreachable_value;
+            }
+            end_call(r);
+            fetch_stats(r);
+        });
     });
 }
 

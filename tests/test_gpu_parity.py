@@ -629,3 +629,133 @@ def test_group_betweenness_sampled_sources_ba(rx, oracle):
     assert abs(got - want) <= RTOL * abs(want)
     st = dg.stats()
     assert st["te"] == wst["te"] and st["v"] == wst["v"]
+
+
+# ------------------------------------------------------------------------------------ weighted shortest paths (8f #4)
+def _weighted_graph(rx, directed, edges, remove=None):
+    g = rx.PyDiGraph() if directed else rx.PyGraph()
+    n = max(max(a, b) for a, b, _ in edges) + 1
+    g.add_nodes_from(range(n))
+    g.add_edges_from([(a, b, w) for a, b, w in edges])
+    if remove is not None:
+        g.remove_node(remove)
+    return g
+
+
+def test_reference_goldens_newman_weighted_closeness(rx):
+    from weighted_cases import NEWMAN, NEWMAN_UNIT
+
+    for name, directed, edges, wf, expected in NEWMAN:
+        g = _weighted_graph(rx, directed, edges)
+        for threshold in (200, 1):
+            got = rx.newman_weighted_closeness_centrality(g, weight_fn=float, wf_improved=wf,
+                                                          parallel_threshold=threshold)
+            assert list(got.keys()) == list(range(len(expected))), name
+            for a, b in zip(got.values(), expected):
+                assert abs(a - b) < 1e-4, (name, list(got.values()))
+    for name, directed, edges in NEWMAN_UNIT:
+        g = _weighted_graph(rx, directed, edges)
+        for wf in (False, True):
+            assert rx.newman_weighted_closeness_centrality(g, float, wf) == rx.closeness_centrality(g, wf), name
+    # tests/graph/test_centrality.py:122-130, tests/digraph/test_centrality.py:151-158
+    for directed in (False, True):
+        g = rx.PyDiGraph() if directed else rx.PyGraph()
+        a, b, c = g.add_node("A"), g.add_node("B"), g.add_node("C")
+        c0 = g.add_node("C0")
+        d = g.add_node("D")
+        g.add_edges_from([(a, b, 1), (b, c, 1), (c, d, 1)])
+        g.remove_node(c0)
+        assert rx.closeness_centrality(g, parallel_threshold=1) == rx.newman_weighted_closeness_centrality(
+            g, default_weight=1.0, parallel_threshold=1)
+
+
+def test_reference_goldens_all_pairs_dijkstra(rx):
+    from weighted_cases import ALL_PAIRS, DIJKSTRA_EDGES
+
+    for name, directed, remove, expected in ALL_PAIRS:
+        g = _weighted_graph(rx, directed, DIJKSTRA_EDGES, remove)
+        typed = rx.digraph_all_pairs_dijkstra_path_lengths if directed else rx.graph_all_pairs_dijkstra_path_lengths
+        got = typed(g, float)
+        assert got == expected, (name, got)
+        assert rx.all_pairs_dijkstra_path_lengths(g, float) == expected
+        assert list(got.keys()) == sorted(expected)
+    # tests/graph/test_dijkstra.py:189-205, :262-270; tests/test_dispatch.py:88-90
+    assert rx.graph_all_pairs_dijkstra_path_lengths(rx.PyGraph(), float) == {}
+    g = rx.PyGraph()
+    g.add_nodes_from(list(range(1000)))
+    assert rx.graph_all_pairs_dijkstra_path_lengths(g, float) == {x: {} for x in range(1000)}
+    g = rx.generators.path_graph(2)
+    for bad in (float("nan"), -1):
+        with pytest.raises(ValueError):
+            rx.graph_all_pairs_dijkstra_path_lengths(g, lambda _: bad)
+    assert rx.all_pairs_dijkstra_path_lengths(g, lambda _: 1) == {0: {1: 1.0}, 1: {0: 1.0}}
+
+
+def _random_weights(g, seed, kind):
+    rng = np.random.default_rng(seed)
+    _, eb = g._bounds()
+    if kind == "uniform":
+        w = rng.uniform(0.05, 2.0, size=max(eb, 1))
+    elif kind == "ints":  # many ties between different paths
+        w = rng.integers(1, 4, size=max(eb, 1)).astype(np.float64)
+    else:  # wide dynamic range: rounding of the left-to-right sums matters
+        w = np.exp(rng.uniform(-12, 12, size=max(eb, 1)))
+    return w
+
+
+@pytest.mark.parametrize("kind", ["uniform", "ints", "wide"])
+@pytest.mark.parametrize("directed,n,m,seed,holes", CASES)
+def test_weighted_vs_oracle(rx, oracle, directed, n, m, seed, holes, kind):
+    from rustworkx_b200 import device_snapshot
+
+    g = random_graph(rx, directed, n, m, seed, holes)
+    og = oracle_graph(oracle, g)
+    w = _random_weights(g, seed, kind)
+    dg = device_snapshot(g)
+    live = np.asarray(g.node_indices(), dtype=np.uint32)
+    # all-pairs Dijkstra lengths: bit exact, same reachability
+    want = og.dijkstra_lengths_rows(w, live, threads=oracle.max_threads())[:, live]
+    got = dg.all_pairs_dijkstra_lengths_rows(w)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.array_equal(got[~np.isnan(got)], want[~np.isnan(want)])
+    # Newman closeness: distances are exact, the per-source sum is tiled -> a few ulp
+    for wf in (True, False):
+        cw, present = og.newman_weighted_closeness_centrality(w, wf, 1 << 30, as_arrays=True)
+        cg = dg.newman_weighted_closeness(w, wf)
+        assert np.allclose(cg, cw, rtol=1e-12, atol=0.0)
+        assert np.array_equal(cg == 0.0, cw == 0.0)
+
+
+def test_weighted_infinite_costs(rx, oracle):
+    """Newman weight 0 -> cost +inf; an infinite edge cost for Dijkstra: the vertex behind it is in the
+    map with distance +inf (dijkstra.rs:139-141), an unreachable one is not."""
+    from rustworkx_b200 import device_snapshot
+
+    for directed in (False, True):
+        g = rx.PyDiGraph() if directed else rx.PyGraph()
+        g.add_nodes_from(range(6))
+        g.add_edges_from([(0, 1, 1.0), (1, 2, 0.0), (2, 3, 2.0), (4, 0, 0.5)])  # node 5 isolated
+        og = oracle_graph(oracle, g)
+        w = np.array([1.0, 0.0, 2.0, 0.5])
+        dg = device_snapshot(g)
+        for wf in (True, False):
+            cw, _ = og.newman_weighted_closeness_centrality(w, wf, 1 << 30, as_arrays=True)
+            assert np.array_equal(dg.newman_weighted_closeness(w, wf), cw)
+        cost = np.array([1.0, np.inf, 2.0, 0.5])
+        want = og.dijkstra_lengths_rows(cost, np.arange(6, dtype=np.uint32))
+        got = dg.all_pairs_dijkstra_lengths_rows(cost)
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        assert np.array_equal(got[~np.isnan(got)], want[~np.isnan(want)])
+
+
+def test_weighted_closeness_sampled_sources_ba(rx, oracle):
+    """BA(100k, 8) with random weights: Newman closeness of 256 sampled sources against the oracle."""
+    from rustworkx_b200 import device_snapshot
+
+    g = rx.barabasi_albert_graph(100_000, 8, seed=4)
+    og = oracle_graph(oracle, g)
+    w = _random_weights(g, 9, "uniform")
+    sources = np.random.default_rng(2).choice(100_000, size=256, replace=False).astype(np.uint32)
+    want, _ = og.weighted_closeness_partial(w, sources, threads=oracle.max_threads())
+    got = device_snapshot(g).weighted_closeness_partial(w, sources)
+    assert np.allclose(got, want[sources], rtol=1e-12, atol=0.0)

@@ -349,3 +349,42 @@ def test_group_betweenness_singleton_matches_betweenness(oracle):
     per_node = g.betweenness_centrality(False, False, 200)
     for v in range(4):
         assert abs(g.group_betweenness_centrality([v], False, 200) - per_node[v]) < 1e-10
+
+
+# ----------------------------------------------------------------------------- weighted shortest paths
+def _weighted_oracle_graph(oracle, directed, edges, remove=None):
+    g = oracle.OracleGraph.from_edges(directed, [(a, b) for a, b, _ in edges])
+    w = [float(x) for _, _, x in edges]
+    if remove is not None:
+        g.remove_node(remove)
+    return g, w
+
+
+def test_newman_weighted_closeness_goldens(oracle):
+    # rustworkx-core/src/centrality.rs:1382-1760
+    from weighted_cases import NEWMAN, NEWMAN_UNIT
+
+    for name, directed, edges, wf, expected in NEWMAN:
+        g, w = _weighted_oracle_graph(oracle, directed, edges)
+        for threshold in (200, 1):
+            got = g.newman_weighted_closeness_centrality(w, wf, threshold)
+            assert len(got) == len(expected), name
+            for a, b in zip(got, expected):
+                assert abs(a - b) < 1e-4, (name, got)
+    for name, directed, edges in NEWMAN_UNIT:
+        g, w = _weighted_oracle_graph(oracle, directed, edges)
+        for wf in (False, True):
+            assert g.newman_weighted_closeness_centrality(w, wf, 200) == g.closeness_centrality(wf, 200), name
+
+
+def test_all_pairs_dijkstra_goldens(oracle):
+    # tests/graph/test_dijkstra.py:129-176, tests/digraph/test_dijkstra.py:198-258
+    from weighted_cases import ALL_PAIRS, DIJKSTRA_EDGES
+
+    for name, directed, remove, expected in ALL_PAIRS:
+        g, w = _weighted_oracle_graph(oracle, directed, DIJKSTRA_EDGES, remove)
+        live = sorted(expected)
+        rows = g.dijkstra_lengths_rows(w, live)
+        got = {s: {t: rows[i, t] for t in range(rows.shape[1]) if t != s and not math.isnan(rows[i, t])}
+               for i, s in enumerate(live)}
+        assert got == expected, name
