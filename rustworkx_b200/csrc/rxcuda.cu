@@ -144,6 +144,68 @@ struct BcWorkspace {
     }
 };
 
+// Large device-to-host results (distance-matrix rows, path-length rows) go through two pinned staging
+// buffers: the DMA engine fills one at PCIe speed while host threads copy the other into the
+// caller's pageable buffer.  A plain cudaMemcpyAsync into pageable memory ran at ~4.5 GB/s here and
+// was 98 % of distance_matrix's end-to-end time on heavy_hex(51) (333 MB).
+struct PinnedStage {
+    static constexpr size_t SLOT = 32u << 20;
+    char *buf[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    ~PinnedStage() {
+        for (int i = 0; i < 2; i++) {
+            if (buf[i]) cudaFreeHost(buf[i]);
+            if (ev[i]) cudaEventDestroy(ev[i]);
+        }
+    }
+    void ensure() {
+        for (int i = 0; i < 2; i++) {
+            if (!buf[i]) RXC_CUDA(cudaHostAlloc((void **)&buf[i], SLOT, cudaHostAllocDefault));
+            if (!ev[i]) RXC_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        }
+    }
+};
+
+static void host_copy_parallel(char *dst, const char *src, size_t bytes) {
+    const size_t T = bytes >= (8u << 20) ? 4 : 1;
+    if (T == 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t part = (bytes / T + 4095) & ~(size_t)4095;
+    for (size_t t = 0; t < T; t++) {
+        const size_t b = t * part, e = std::min(bytes, b + part);
+        if (b < e) th.emplace_back([=] { memcpy(dst + b, src + b, e - b); });
+    }
+    for (auto &x : th) x.join();
+}
+
+// dst: pageable host memory; src: device memory; everything queued on `st` before the call is
+// complete when it returns
+static void d2h_staged(PinnedStage &ps, void *dst, const void *src, size_t bytes, cudaStream_t st) {
+    if (bytes < (4u << 20)) {
+        RXC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+        RXC_CUDA(cudaStreamSynchronize(st));
+        return;
+    }
+    ps.ensure();
+    const size_t nchunks = (bytes + PinnedStage::SLOT - 1) / PinnedStage::SLOT;
+    auto issue = [&](size_t c) {
+        const size_t off = c * PinnedStage::SLOT, len = std::min(PinnedStage::SLOT, bytes - off);
+        RXC_CUDA(cudaMemcpyAsync(ps.buf[c & 1], (const char *)src + off, len, cudaMemcpyDeviceToHost, st));
+        RXC_CUDA(cudaEventRecord(ps.ev[c & 1], st));
+    };
+    issue(0);
+    for (size_t c = 0; c < nchunks; c++) {
+        if (c + 1 < nchunks) issue(c + 1);  // slot (c+1)&1 was drained in the previous iteration
+        RXC_CUDA(cudaEventSynchronize(ps.ev[c & 1]));
+        const size_t off = c * PinnedStage::SLOT, len = std::min(PinnedStage::SLOT, bytes - off);
+        host_copy_parallel((char *)dst + off, ps.buf[c & 1], len);
+    }
+    RXC_CUDA(cudaStreamSynchronize(st));
+}
+
 struct BfsWorkspace {
     DevBuf<uint32_t> visited, next0, next1, q0, q1, cnt, lvl_total, src;
     DevBuf<unsigned long long> reach, dsum;
@@ -179,6 +241,7 @@ struct rxc_graph {
     BcWorkspace bc_ws;
     BfsWorkspace bfs_ws;
     DevBuf<double> acc_buf;  // partial centrality vector of the current call
+    PinnedStage pinned;      // staging for large device-to-host results
     std::vector<std::unique_ptr<rxc_graph>> replicas;  // same snapshot on the other devices of rxc_set_devices
     std::mutex mu;
 
@@ -930,8 +993,7 @@ static void bfs_run(rxc_graph *g, const DeviceCSR &csr, const std::vector<uint32
         RXC_CUDA(cudaEventRecord(g->ev[1], st));
         const double t0 = now_ms();
         if (rows_mode) {
-            RXC_CUDA(cudaMemcpyAsync(out + (size_t)s0 * n, ws.rows.p, (size_t)cnt * n * 8,
-                                     cudaMemcpyDeviceToHost, st));
+            d2h_staged(g->pinned, out + (size_t)s0 * n, ws.rows.p, (size_t)cnt * n * 8, st);
         } else {
             RXC_CUDA(cudaMemcpyAsync(h_vals.data(), ws.vals.p, (size_t)cnt * 8 * vstride,
                                      cudaMemcpyDeviceToHost, st));
@@ -1059,7 +1121,7 @@ static void bfs_smem_run(rxc_graph *g, const DeviceCSR &csr, const uint32_t *sou
         RXC_CUDA(cudaEventRecord(g->ev[1], st));
         const double t0 = now_ms();
         if (rows_mode)
-            RXC_CUDA(cudaMemcpyAsync(out + s0 * n, d_rows.p, cnt * (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+            d2h_staged(g->pinned, out + s0 * n, d_rows.p, cnt * (size_t)n * 8, st);
         else
             RXC_CUDA(cudaMemcpyAsync(h_vals.data(), d_vals.p, cnt * 8 * vstride, cudaMemcpyDeviceToHost, st));
         RXC_CUDA(cudaStreamSynchronize(st));
@@ -1317,8 +1379,7 @@ static void wsp_run(rxc_graph *g, bool reversed, const double *d_cost, const std
             // te / v counters come from the tile pass; run it for the counters only when cheap
             RXC_CUDA(cudaEventRecord(g->ev[2], st));
             const double t0 = now_ms();
-            RXC_CUDA(cudaMemcpyAsync(out + s0 * n, d_rows.p, cnt * (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-            RXC_CUDA(cudaStreamSynchronize(st));
+            d2h_staged(g->pinned, out + s0 * n, d_rows.p, cnt * (size_t)n * 8, st);
             RXC_CUDA(cudaGetLastError());
             g->stats.ms_d2h += now_ms() - t0;
         }
