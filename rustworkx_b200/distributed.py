@@ -126,3 +126,66 @@ def edge_betweenness_centrality(graph, normalized=True, *, rank=None, world=None
         return None
     # edge betweenness always rescales with include_endpoints=true (centrality.rs:211-217)
     return _lib.rescale(total.copy(), snap["live_nodes"].shape[0], normalized, snap["directed"], True)
+
+
+def _world(rank, world):
+    dist = _dist()
+    if rank is None:
+        rank = dist.get_rank() if dist else 0
+    if world is None:
+        world = dist.get_world_size() if dist else 1
+    return rank, world
+
+
+def group_betweenness_centrality(graph, group, normalized=True, *, rank=None, world=None,
+                                 compute_partial=None):
+    """Group betweenness (``rustworkx-core/src/centrality.rs:1963-2101``) with the non-group sources
+    sharded over the process group: the per-source sums are additive, so one scalar is reduced.
+    ``compute_partial(group, sources) -> float`` defaults to ``rxc_group_betweenness_partial``.
+    Returns the value on rank 0 and ``None`` elsewhere."""
+    rank, world = _world(rank, world)
+    snap = graph._snapshot_arrays()
+    members = sorted(set(int(x) for x in group))
+    node_count = int(snap["live_nodes"].shape[0])
+    if not members or node_count <= 1:
+        return 0.0 if rank == 0 else None
+    mine = shard_sources(snap["live_nodes"], rank, world)
+    if compute_partial is None:
+        from . import device_snapshot
+
+        dg = device_snapshot(graph)
+        compute_partial = dg.group_betweenness_partial
+    part = np.array([compute_partial(np.asarray(members, dtype=np.uint32), mine)], dtype=np.float64)
+    total = float(reduce_partial(part)[0])
+    if rank != 0:
+        return None
+    if not snap["directed"]:
+        total /= 2.0
+    if normalized:
+        non_group = node_count - len(members)
+        if non_group > 1:
+            norm = non_group * (non_group - 1) if snap["directed"] else (non_group * (non_group - 1)) // 2
+            total /= float(norm)
+    return total
+
+
+def newman_weighted_closeness_centrality(graph, edge_weight, wf_improved=True, *, rank=None, world=None,
+                                         compute_partial=None):
+    """Newman's weighted closeness (``centrality.rs:1297-1357``), sources sharded: every rank fills the
+    entries of its own sources in a zero vector, one sum-reduce assembles them (entries are disjoint).
+    ``edge_weight``: dense vector by original edge index.  ``compute_partial(edge_weight, sources) ->
+    f64[len(sources)]`` defaults to ``rxc_weighted_closeness_partial``.  Dense vector over original
+    node indices on rank 0, ``None`` elsewhere."""
+    rank, world = _world(rank, world)
+    snap = graph._snapshot_arrays()
+    mine = shard_sources(snap["live_nodes"], rank, world)
+    if compute_partial is None:
+        from . import device_snapshot
+
+        dg = device_snapshot(graph)
+        compute_partial = lambda w, s: dg.weighted_closeness_partial(w, s, True, True, wf_improved)  # noqa: E731
+    dense = np.zeros(max(int(snap["n_bound"]), 1), dtype=np.float64)
+    if mine.size:
+        dense[mine.astype(np.int64)] = compute_partial(edge_weight, mine)
+    total = reduce_partial(dense)
+    return total[: int(snap["n_bound"])] if rank == 0 else None

@@ -22,6 +22,11 @@ g = rx.barabasi_albert_graph(5000, 4, seed=9)
 g.remove_node(17)
 node = rxd.betweenness_centrality(g, True, True)
 edge = rxd.edge_betweenness_centrality(g, False)
+group = [0, 5, 1234]
+gb = rxd.group_betweenness_centrality(g, group, True)
+_, eb = g._bounds()
+w = np.random.default_rng(3).uniform(0.1, 2.0, size=eb)
+nw = rxd.newman_weighted_closeness_centrality(g, w, True)
 if rank == 0:
     import oracle
     og = oracle.OracleGraph.from_graph(g)
@@ -29,6 +34,9 @@ if rank == 0:
     want_e, _ = og.edge_betweenness_centrality(False, 50, as_arrays=True)
     assert np.allclose(node, want, rtol=1e-9, atol=1e-12)
     assert np.allclose(edge, want_e, rtol=1e-9, atol=1e-12)
+    assert abs(gb - og.group_betweenness_centrality(group, True, 50)) <= 1e-9 * abs(gb)
+    want_nw, _ = og.newman_weighted_closeness_centrality(w, True, 50, as_arrays=True)
+    assert np.allclose(nw, want_nw, rtol=1e-12, atol=0.0)
     print("NCCL_OK")
 else:
     assert node is None and edge is None
@@ -86,5 +94,19 @@ def test_in_process_replicas(oracle):
         oh = oracle.OracleGraph.from_graph(h)
         assert np.array_equal(rx.distance_matrix(h, null_value=-1.0), oh.distance_matrix(300, True, -1.0))
         assert rx.unweighted_average_shortest_path_length(h) == oh.average_shortest_path_length(300, True, False)
+        # 8f #2 / #4 through the sharded full calls
+        group = [3, 77, 4000]
+        assert abs(rx.group_betweenness_centrality(g, group) - og.group_betweenness_centrality(group, True, 50)) \
+            <= 1e-9 * og.group_betweenness_centrality(group, True, 50)
+        _, eb = g._bounds()
+        w = np.random.default_rng(1).uniform(0.1, 2.0, size=eb)
+        dg = rx.device_snapshot(g)
+        want_nw, _ = og.newman_weighted_closeness_centrality(w, True, 50, as_arrays=True)
+        assert np.allclose(dg.newman_weighted_closeness(w, True), want_nw, rtol=1e-12, atol=0.0)
+        live = np.asarray(g.node_indices(), dtype=np.uint32)
+        want_rows = og.dijkstra_lengths_rows(w, live[:300], threads=4)[:, live]
+        got_rows = dg.all_pairs_dijkstra_lengths_rows(w, 0, 300)
+        assert np.array_equal(np.isnan(got_rows), np.isnan(want_rows))
+        assert np.array_equal(got_rows[~np.isnan(got_rows)], want_rows[~np.isnan(want_rows)])
     finally:
         rx.set_devices([])

@@ -211,14 +211,24 @@ node = rxd.betweenness_centrality(g, True, True,
         compute_partial=lambda s, ep: og.betweenness_partial(s, ep)[0])
 edge = rxd.edge_betweenness_centrality(g, False,
         compute_partial=lambda s, ep: og.edge_betweenness_partial(s)[0])
+group = [3, 50, 50, 211]
+gb = rxd.group_betweenness_centrality(g, group, True,
+        compute_partial=lambda grp, s: og.group_betweenness_partial(grp, s)[0])
+_, eb = g._bounds()
+w = np.random.default_rng(3).uniform(0.1, 2.0, size=eb)
+nw = rxd.newman_weighted_closeness_centrality(g, w, True,
+        compute_partial=lambda ww, s: og.weighted_closeness_partial(ww, s)[0][s])
 if dist.get_rank() == 0:
+    assert abs(gb - og.group_betweenness_centrality(group, True, 1 << 30)) <= 1e-12 * abs(gb)
+    want_nw, _ = og.newman_weighted_closeness_centrality(w, True, 1 << 30, as_arrays=True)
+    assert np.array_equal(nw, want_nw)
     want, _ = og.betweenness_centrality(True, True, 1 << 30, as_arrays=True)
     want_e, _ = og.edge_betweenness_centrality(False, 1 << 30, as_arrays=True)
     assert np.allclose(node, want, rtol=1e-12, atol=1e-15), np.abs(node - want).max()
     assert np.allclose(edge, want_e, rtol=1e-12, atol=1e-15)
     print("GLOO_OK")
 else:
-    assert node is None and edge is None
+    assert node is None and edge is None and gb is None and nw is None
 dist.destroy_process_group()
 """
 
