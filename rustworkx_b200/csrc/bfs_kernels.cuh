@@ -232,6 +232,7 @@ constexpr uint32_t SB_QS = 8192;  // most frontier entries kept in shared memory
 struct SmemBfsParams {
     const uint32_t *row;
     const uint32_t *col;
+    const uint4 *ell;              // [n] adjacency when every vertex has <= 4 arcs, else nullptr
     const uint32_t *sources;       // compact ids
     uint32_t *qspill;              // [gridDim.x][2][n] queue entries beyond SB_QS
     uint32_t *gbitmap;             // [gridDim.x][words] visited bitmaps when they do not fit in smem
@@ -248,7 +249,10 @@ struct SmemBfsParams {
     uint32_t qs;                   // frontier entries per queue held in shared memory (<= SB_QS)
 };
 
-template <bool ROWS, bool GLOBAL_BITMAP>
+// ELL: every vertex has at most 4 arcs (grids, heavy-hex and the other coupling-map lattices) and
+// the adjacency is one uint4 per vertex (0xFFFFFFFF padded): one dependent load per level instead
+// of two (CSR offsets, then targets).
+template <bool ROWS, bool GLOBAL_BITMAP, bool ELL>
 __global__ void __launch_bounds__(1024, 1) bfs_smem_kernel(SmemBfsParams p) {
     extern __shared__ uint32_t sb_smem[];
     // the bitmap lives in shared memory when it fits (n <= ~1.3 M), else in this CTA's slab of
@@ -286,33 +290,63 @@ __global__ void __launch_bounds__(1024, 1) bfs_smem_kernel(SmemBfsParams p) {
         while (size) {
             reach += size;
             dsum += (unsigned long long)size * level;
+            uint32_t *tail = &s_tail[level & 1];
             for (uint32_t i = tid; i < size; i += nthr) {
-                const uint32_t v = (i < p.qs) ? qc[i] : sc[i];
-                if (ROWS) p.rows[(size_t)si * p.n_cols + v] = (double)level;
-                const uint32_t e0 = p.row[v], e1 = p.row[v + 1];
-                te += e1 - e0;
-                for (uint32_t e = e0; e < e1; e += 4) {
-                    // four independent target loads in flight before any is used
-                    uint32_t w[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) w[u] = (e + u < e1) ? p.col[e + u] : 0xFFFFFFFFu;
+                const bool active = true;
+                uint32_t v = 0;
+                if (active) {
+                    v = (i < p.qs) ? qc[i] : sc[i];
+                    if (ROWS) p.rows[(size_t)si * p.n_cols + v] = (double)level;
+                }
+                if (ELL) {
+                    uint4 nb = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                    if (active) nb = p.ell[v];
+                    const uint32_t w[4] = {nb.x, nb.y, nb.z, nb.w};
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         if (w[u] == 0xFFFFFFFFu) continue;
+                        te++;
                         const uint32_t bit = 1u << (w[u] & 31);
                         if (!(vis[w[u] >> 5] & bit)) {
                             const uint32_t old = atomicOr(&vis[w[u] >> 5], bit);
                             if (!(old & bit)) {
-                                const uint32_t pos = atomicAdd(&s_tail[level & 1], 1u);
+                                // per-thread append: a warp-aggregated one (scan + one atomic per
+                                // warp) was measured slower, 235 vs 287 GTEPS on the grid
+                                const uint32_t pos = atomicAdd(tail, 1u);
                                 if (pos < p.qs) qn[pos] = w[u];
                                 else sn[pos] = w[u];
+                            }
+                        }
+                    }
+                } else if (active) {
+                    // general degrees: per-thread appends (measured: making this loop a warp
+                    // collective for an aggregated append costs more than the atomics it saves,
+                    // 173 -> 150 GTEPS on the grid)
+                    const uint32_t e0 = p.row[v], e1 = p.row[v + 1];
+                    te += e1 - e0;
+                    for (uint32_t e = e0; e < e1; e += 4) {
+                        // four independent target loads in flight before any is used
+                        uint32_t w[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) w[u] = (e + u < e1) ? p.col[e + u] : 0xFFFFFFFFu;
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            if (w[u] == 0xFFFFFFFFu) continue;
+                            const uint32_t bit = 1u << (w[u] & 31);
+                            if (!(vis[w[u] >> 5] & bit)) {
+                                const uint32_t old = atomicOr(&vis[w[u] >> 5], bit);
+                                if (!(old & bit)) {
+                                    const uint32_t pos = atomicAdd(tail, 1u);
+                                    if (pos < p.qs) qn[pos] = w[u];
+                                    else sn[pos] = w[u];
+                                }
                             }
                         }
                     }
                 }
             }
             __syncthreads();
-            size = s_tail[level & 1];
+            size = *tail;
             if (tid == 0) s_tail[(level + 1) & 1] = 0;  // the counter the next level appends to
             __syncthreads();
             uint32_t *t = qc; qc = qn; qn = t;
@@ -329,6 +363,27 @@ __global__ void __launch_bounds__(1024, 1) bfs_smem_kernel(SmemBfsParams p) {
             atomicAdd(&p.stats[ST_V], reach);
         }
     }
+}
+
+// ELL adjacency of a CSR whose rows have at most 4 arcs
+__global__ void __launch_bounds__(BLOCK) csr_to_ell4_kernel(const uint32_t *row, const uint32_t *col,
+                                                            uint32_t n, uint4 *ell) {
+    const uint32_t v = blockIdx.x * BLOCK + threadIdx.x;
+    if (v >= n) return;
+    const uint32_t e0 = row[v], e1 = row[v + 1];
+    uint32_t w[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) w[u] = (e0 + u < e1) ? col[e0 + u] : 0xFFFFFFFFu;
+    ell[v] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__global__ void __launch_bounds__(BLOCK) csr_max_degree_kernel(const uint32_t *row, uint32_t n,
+                                                               uint32_t *out) {
+    const uint32_t v = blockIdx.x * BLOCK + threadIdx.x;
+    uint32_t d = (v < n) ? row[v + 1] - row[v] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d = max(d, __shfl_xor_sync(FULL, d, o));
+    if (lane_id() == 0 && d) atomicMax(out, d);
 }
 
 // (reach, sum of distances) per source as exact doubles (both < 2^53) for

@@ -86,6 +86,8 @@ struct DevBuf {
 
 struct DeviceCSR {
     DevBuf<uint32_t> row, col, eid;
+    DevBuf<uint4> ell;      // one uint4 per vertex when max_degree <= 4 (built on first use)
+    int64_t max_degree = -1;  // -1: not computed yet
     uint64_t arcs = 0;
     void upload(const HostCSR &h, cudaStream_t s) {
         row.alloc(h.row.size());
@@ -110,6 +112,8 @@ struct Options {
     int64_t bc_sparse_div = 16;  // forward levels with <= n/this queue entries use the frontier filter (0: off)
     int64_t device_csr = 1;      // build the CSR on the device (0: host counting sort)
     int64_t bfs_depth_switch = 48;  // auto: pilot BFS deeper than this many levels -> mode 2
+    int64_t bfs_threads = 0;        // CTA-per-source BFS: threads per CTA (0: 1024 for n >= 2^18, else 256)
+    int64_t bfs_ell = 1;            // CTA-per-source BFS: ELL adjacency when every vertex has <= 4 arcs
 };
 static Options g_opt;
 constexpr uint32_t HUB_CAP = 4096;  // deferred high-degree work items per group and level
@@ -1040,19 +1044,37 @@ static void bfs_smem_run(rxc_graph *g, const DeviceCSR &csr, const uint32_t *sou
     size_t smem = 0;
     bool gbm = false;
     smem_bfs_fits(n, &qs, &smem, &gbm);
+    // lattices (grid, heavy-hex: at most 4 arcs per vertex) get the ELL adjacency
+    DeviceCSR &mcsr = const_cast<DeviceCSR &>(csr);
+    if (mcsr.max_degree < 0) {
+        DevBuf<uint32_t> d_max;
+        d_max.alloc(1);
+        RXC_CUDA(cudaMemsetAsync(d_max.p, 0, 4, g->stream));
+        csr_max_degree_kernel<<<(n + BLOCK - 1) / BLOCK, BLOCK, 0, g->stream>>>(csr.row.p, n, d_max.p);
+        uint32_t h_max = 0;
+        RXC_CUDA(cudaMemcpyAsync(&h_max, d_max.p, 4, cudaMemcpyDeviceToHost, g->stream));
+        RXC_CUDA(cudaStreamSynchronize(g->stream));
+        mcsr.max_degree = h_max;
+    }
+    if (mcsr.max_degree <= 4 && g_opt.bfs_ell && !mcsr.ell.p) {
+        mcsr.ell.alloc(n);
+        csr_to_ell4_kernel<<<(n + BLOCK - 1) / BLOCK, BLOCK, 0, g->stream>>>(csr.row.p, csr.col.p, n, mcsr.ell.p);
+    }
+    const bool ell = mcsr.ell.p != nullptr && g_opt.bfs_ell;
     using KernelT = void (*)(SmemBfsParams);
-    const KernelT kernel = rows_mode ? (gbm ? bfs_smem_kernel<true, true> : bfs_smem_kernel<true, false>)
-                                     : (gbm ? bfs_smem_kernel<false, true> : bfs_smem_kernel<false, false>);
+    const KernelT table[8] = {bfs_smem_kernel<false, false, false>, bfs_smem_kernel<false, false, true>,
+                              bfs_smem_kernel<false, true, false>,  bfs_smem_kernel<false, true, true>,
+                              bfs_smem_kernel<true, false, false>,  bfs_smem_kernel<true, false, true>,
+                              bfs_smem_kernel<true, true, false>,   bfs_smem_kernel<true, true, true>};
+    const KernelT kernel = table[(rows_mode ? 4 : 0) + (gbm ? 2 : 0) + (ell ? 1 : 0)];
     static bool attr_done_dev[64] = {false};  // function attributes are per device
     bool &attr_done = attr_done_dev[g->device & 63];
     if (!attr_done) {
-        const KernelT all[4] = {bfs_smem_kernel<false, false>, bfs_smem_kernel<false, true>,
-                                bfs_smem_kernel<true, false>, bfs_smem_kernel<true, true>};
-        for (KernelT k4 : all)
+        for (KernelT k4 : table)
             RXC_CUDA(cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_done = true;
     }
-    const int threads = n >= (1u << 18) ? 1024 : 256;
+    const int threads = g_opt.bfs_threads > 0 ? (int)g_opt.bfs_threads : (n >= (1u << 18) ? 1024 : 256);
     int per_sm = 1, sms = 148;
     RXC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device));
     RXC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
@@ -1081,6 +1103,7 @@ static void bfs_smem_run(rxc_graph *g, const DeviceCSR &csr, const uint32_t *sou
     SmemBfsParams p{};
     p.row = csr.row.p;
     p.col = csr.col.p;
+    p.ell = ell ? mcsr.ell.p : nullptr;
     p.sources = d_src.p;
     p.qspill = d_spill.p;
     p.gbitmap = gbm ? d_bitmap.p : nullptr;
@@ -1931,6 +1954,8 @@ int rxc_set_option(const char *name, int64_t value) {
     else if (k == "hub_degree" && value > 0) g_opt.hub_degree = value;
     else if (k == "bfs_mode" && value >= 0 && value <= 2) g_opt.bfs_mode = value;
     else if (k == "bfs_depth_switch" && value >= 0) g_opt.bfs_depth_switch = value;
+    else if (k == "bfs_threads" && (value == 0 || value == 128 || value == 256 || value == 512 || value == 1024)) g_opt.bfs_threads = value;
+    else if (k == "bfs_ell" && (value == 0 || value == 1)) g_opt.bfs_ell = value;
     else if (k == "device_csr" && (value == 0 || value == 1)) g_opt.device_csr = value;
     else if (k == "bc_sparse_div" && value >= 0) g_opt.bc_sparse_div = value;
     else if (k == "mem_fraction_pct" && value > 0 && value <= 95) g_opt.mem_fraction_pct = value;

@@ -14,6 +14,9 @@ def timed(label, fn, dg, te_bytes=None):
                       "launches": st["launches"], "batches": st["batches"], "d2h_ms": round(st["ms_d2h"], 2)}), flush=True)
     return out
 
+for kv in os.environ.get("OPT", "").split(","):
+    if "=" in kv:
+        _lib.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 which = sys.argv[1:] or ["hh", "grid", "gnm"]
 if "hh" in which:
     g = rx.generators.heavy_hex_graph(51)
