@@ -83,13 +83,16 @@ def hbm_peak():
 
 
 def ncu_traffic(kernel, sources_per_step):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed
-    `ncu --set full` capture of one 256-source batch of this same workload (profiles/)."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic_batch256.json")
+    """dram__bytes_read.sum + dram__bytes_write.sum per (non-empty) launch of `kernel`, from the
+    committed `ncu --set full` capture of one 1024-source batch of this same workload (profiles/,
+    made with scripts/ncu_traffic.py)."""
+    name = "r01_traffic_batch1024.json"
+    path = os.path.join(ROOT, "profiles", name)
     try:
         with open(path) as f:
             rec = json.load(f)[kernel]
-        return rec["dram_bytes"] / rec["launches"], "profiles/r01_traffic_batch256.json (ncu --set full, per launch)"
+        return (rec["dram_bytes"] / max(1, rec["launches_nonempty"]),
+                f"profiles/{name} (ncu --set full, per non-empty launch of a 1024-source batch)")
     except Exception:
         return None, "no ncu capture committed"
 
