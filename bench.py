@@ -249,8 +249,12 @@ def run_b200(args):
         dist.broadcast(t, 0)
         ident = t.cpu().numpy().copy()
         _lib.check(_lib.lib().rxc_comm_init(rank, world, _lib.p_u8(ident)))
-        warm = np.zeros(1024, dtype=np.float64)  # first collective pays NCCL's lazy connection setup
-        _lib.check(_lib.lib().rxc_comm_reduce_sum_f64(_lib.p_f64(warm), warm.shape[0], 0))
+        # The first collective of a given size class pays NCCL's lazy connection set-up (hundreds of
+        # ms; a small warm-up does not cover the protocol the 8 MB reduce uses): warm the communicator
+        # with a vector of the real length, before the timed region.
+        warm = np.zeros(max(int(snap["n_bound"]), 1), dtype=np.float64)
+        for _ in range(2):
+            _lib.check(_lib.lib().rxc_comm_reduce_sum_f64(_lib.p_f64(warm), warm.shape[0], 0))
 
     dg = make_device_graph()  # inputs resident in HBM before the timed region
     partial = np.zeros(snap["n_bound"], dtype=np.float64)

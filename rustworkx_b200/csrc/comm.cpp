@@ -42,6 +42,8 @@ struct NcclApi {
 NcclApi g_nccl;
 nccl_comm_t g_comm = nullptr;
 cudaStream_t g_comm_stream = nullptr;
+double *g_red_buf = nullptr;  // device staging of rxc_comm_reduce_sum_f64
+uint64_t g_red_cap = 0;
 int g_rank = 0, g_world = 1;
 
 bool load_nccl() {
@@ -127,9 +129,16 @@ int rxc_comm_reduce_sum_f64(double *host_inout, uint64_t len, int root) {
     if (!host_inout) return RXC_ERR_INVALID;
     cudaError_t e = cudaSetDevice(rxc_get_device());
     if (e != cudaSuccess) return cuda_fail("cudaSetDevice", e);
-    double *d = nullptr;
-    e = cudaMalloc((void **)&d, len * sizeof(double));
-    if (e != cudaSuccess) return cuda_fail("cudaMalloc", e);
+    // staging buffer kept across calls: cudaMalloc / cudaFree synchronise the whole device
+    if (g_red_cap < len) {
+        if (g_red_buf) cudaFree(g_red_buf);
+        g_red_buf = nullptr;
+        g_red_cap = 0;
+        e = cudaMalloc((void **)&g_red_buf, len * sizeof(double));
+        if (e != cudaSuccess) return cuda_fail("cudaMalloc", e);
+        g_red_cap = len;
+    }
+    double *d = g_red_buf;
     int rc = RXC_OK;
     e = cudaMemcpyAsync(d, host_inout, len * sizeof(double), cudaMemcpyHostToDevice, g_comm_stream);
     if (e != cudaSuccess) rc = cuda_fail("cudaMemcpyAsync", e);
@@ -143,7 +152,6 @@ int rxc_comm_reduce_sum_f64(double *host_inout, uint64_t len, int root) {
     }
     e = cudaStreamSynchronize(g_comm_stream);
     if (e != cudaSuccess && rc == RXC_OK) rc = cuda_fail("cudaStreamSynchronize", e);
-    cudaFree(d);
     return rc;
 }
 
@@ -170,6 +178,9 @@ int rxc_comm_barrier(void) {
 void rxc_comm_destroy(void) {
     if (g_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g_comm);
     g_comm = nullptr;
+    if (g_red_buf) cudaFree(g_red_buf);
+    g_red_buf = nullptr;
+    g_red_cap = 0;
     if (g_comm_stream) cudaStreamDestroy(g_comm_stream);
     g_comm_stream = nullptr;
     g_rank = 0;
