@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -153,9 +155,10 @@ struct BcWorkspace {
 // caller's pageable buffer.  A plain cudaMemcpyAsync into pageable memory ran at ~4.5 GB/s here and
 // was 98 % of distance_matrix's end-to-end time on heavy_hex(51) (333 MB).
 struct PinnedStage {
-    static constexpr size_t SLOT = 32u << 20;
+    static constexpr size_t SLOT = 16u << 20;
     char *buf[2] = {nullptr, nullptr};
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    bool used[2] = {false, false};  // an event has been recorded for the slot
     ~PinnedStage() {
         for (int i = 0; i < 2; i++) {
             if (buf[i]) cudaFreeHost(buf[i]);
@@ -170,8 +173,19 @@ struct PinnedStage {
     }
 };
 
+// one staging pair per device, shared by every handle (pinning 64 MB costs more than a snapshot)
+struct PinnedSlot {
+    PinnedStage stage;
+    std::mutex mu;
+};
+static PinnedSlot &pinned_slot(int device) {
+    static PinnedSlot slots[64];
+    return slots[device & 63];
+}
+static PinnedStage &pinned_for(int device) { return pinned_slot(device).stage; }
+
 static void host_copy_parallel(char *dst, const char *src, size_t bytes) {
-    const size_t T = bytes >= (8u << 20) ? 4 : 1;
+    const size_t T = bytes >= (8u << 20) ? 8 : (bytes >= (2u << 20) ? 4 : 1);
     if (T == 1) {
         memcpy(dst, src, bytes);
         return;
@@ -188,6 +202,9 @@ static void host_copy_parallel(char *dst, const char *src, size_t bytes) {
 // dst: pageable host memory; src: device memory; everything queued on `st` before the call is
 // complete when it returns
 static void d2h_staged(PinnedStage &ps, void *dst, const void *src, size_t bytes, cudaStream_t st) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(pinned_slot(dev).mu);
     if (bytes < (4u << 20)) {
         RXC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
         RXC_CUDA(cudaStreamSynchronize(st));
@@ -199,6 +216,7 @@ static void d2h_staged(PinnedStage &ps, void *dst, const void *src, size_t bytes
         const size_t off = c * PinnedStage::SLOT, len = std::min(PinnedStage::SLOT, bytes - off);
         RXC_CUDA(cudaMemcpyAsync(ps.buf[c & 1], (const char *)src + off, len, cudaMemcpyDeviceToHost, st));
         RXC_CUDA(cudaEventRecord(ps.ev[c & 1], st));
+        ps.used[c & 1] = true;
     };
     issue(0);
     for (size_t c = 0; c < nchunks; c++) {
@@ -208,6 +226,30 @@ static void d2h_staged(PinnedStage &ps, void *dst, const void *src, size_t bytes
         host_copy_parallel((char *)dst + off, ps.buf[c & 1], len);
     }
     RXC_CUDA(cudaStreamSynchronize(st));
+}
+
+// src: pageable host memory; dst: device memory.  Returns with every copy queued on `st`; the
+// staging slots are reused only after their DMA has completed (events), so the caller's buffer may
+// be released as soon as this returns.
+static void h2d_staged(PinnedStage &ps, void *dst, const void *src, size_t bytes, cudaStream_t st) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(pinned_slot(dev).mu);
+    if (bytes < (4u << 20)) {
+        RXC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        RXC_CUDA(cudaStreamSynchronize(st));  // pageable source: keep the documented "copy on return"
+        return;
+    }
+    ps.ensure();
+    const size_t nchunks = (bytes + PinnedStage::SLOT - 1) / PinnedStage::SLOT;
+    for (size_t c = 0; c < nchunks; c++) {
+        const size_t off = c * PinnedStage::SLOT, len = std::min(PinnedStage::SLOT, bytes - off);
+        if (c >= 2 || ps.used[c & 1]) RXC_CUDA(cudaEventSynchronize(ps.ev[c & 1]));  // slot's last DMA done
+        host_copy_parallel(ps.buf[c & 1], (const char *)src + off, len);
+        RXC_CUDA(cudaMemcpyAsync((char *)dst + off, ps.buf[c & 1], len, cudaMemcpyHostToDevice, st));
+        RXC_CUDA(cudaEventRecord(ps.ev[c & 1], st));
+        ps.used[c & 1] = true;
+    }
 }
 
 struct BfsWorkspace {
@@ -245,7 +287,6 @@ struct rxc_graph {
     BcWorkspace bc_ws;
     BfsWorkspace bfs_ws;
     DevBuf<double> acc_buf;  // partial centrality vector of the current call
-    PinnedStage pinned;      // staging for large device-to-host results
     std::vector<std::unique_ptr<rxc_graph>> replicas;  // same snapshot on the other devices of rxc_set_devices
     std::mutex mu;
 
@@ -370,6 +411,14 @@ static void device_snapshot(rxc_graph *g, uint32_t n_bound, const uint32_t *live
                             const uint32_t *edst, const uint32_t *eid, uint64_t n_edges,
                             bool directed) {
     HostSnapshot &h = g->host;
+    const bool trace = getenv("RXC_TRACE") != nullptr;
+    const double tr0 = now_ms();
+    auto tp = [&](const char *what) {
+        if (trace) {
+            cudaStreamSynchronize(g->stream);
+            fprintf(stderr, "[rxc snapshot] %-12s %.2f ms\n", what, now_ms() - tr0);
+        }
+    };
     h.n_bound = n_bound;
     h.n_live = n_live;
     h.e_bound = e_bound;
@@ -386,6 +435,7 @@ static void device_snapshot(rxc_graph *g, uint32_t n_bound, const uint32_t *live
     }
     if ((directed ? n_edges : 2 * n_edges) >= 0xFFFFFFFFull)
         throw LimitError("more than 2^32-2 arcs are not supported");
+    tp("host maps");
     cudaStream_t st = g->stream;
     const uint32_t n = n_live;
     DevBuf<uint32_t> d_live, d_cmap, d_eid, d_deg_a, d_deg_b, cursor, tiles, d_small, long_rows;
@@ -401,12 +451,15 @@ static void device_snapshot(rxc_graph *g, uint32_t n_bound, const uint32_t *live
     long_rows.alloc(std::max<uint32_t>(n, 1));
     d_small.alloc(4);  // [0] error flags, [1] scan total, [2] long-row count
     RXC_CUDA(cudaMemsetAsync(d_small.p, 0, 16, st));
+    tp("allocs");
     if (n_live) RXC_CUDA(cudaMemcpyAsync(d_live.p, live_nodes, (size_t)n_live * 4, cudaMemcpyHostToDevice, st));
     if (n_edges) {
-        RXC_CUDA(cudaMemcpyAsync(d_src.p, esrc, n_edges * 4, cudaMemcpyHostToDevice, st));
-        RXC_CUDA(cudaMemcpyAsync(d_dst.p, edst, n_edges * 4, cudaMemcpyHostToDevice, st));
+        // the 12 bytes per edge go through the pinned staging slots (a pageable cudaMemcpy of the
+        // 100 MB of config 3 took 8 of the snapshot's 13 ms)
+        h2d_staged(pinned_for(g->device), d_src.p, esrc, n_edges * 4, st);
+        h2d_staged(pinned_for(g->device), d_dst.p, edst, n_edges * 4, st);
         if (eid) {
-            RXC_CUDA(cudaMemcpyAsync(d_eid.p, eid, n_edges * 4, cudaMemcpyHostToDevice, st));
+            h2d_staged(pinned_for(g->device), d_eid.p, eid, n_edges * 4, st);
         } else {  // edge ids default to the position in the list
             std::vector<uint32_t> iota(n_edges);
             for (uint64_t i = 0; i < n_edges; i++) iota[i] = (uint32_t)i;
@@ -414,6 +467,7 @@ static void device_snapshot(rxc_graph *g, uint32_t n_bound, const uint32_t *live
             RXC_CUDA(cudaStreamSynchronize(st));
         }
     }
+    tp("h2d");
     RXC_CUDA(cudaMemsetAsync(d_cmap.p, 0xFF, d_cmap.bytes(), st));
     RXC_CUDA(cudaMemsetAsync(d_deg_a.p, 0, d_deg_a.bytes(), st));
     if (directed) RXC_CUDA(cudaMemsetAsync(d_deg_b.p, 0, d_deg_b.bytes(), st));
@@ -435,6 +489,7 @@ static void device_snapshot(rxc_graph *g, uint32_t n_bound, const uint32_t *live
         device_build_csr(g->out, n, d_src.p, d_dst.p, d_eid_p, n_edges, 2, d_deg_a.p,
                          cursor, tiles, d_small.p + 1, st);
     }
+    tp("count+build");
     device_sort_rows(g->out, n, long_rows, d_small.p + 2, st);
     if (directed) device_sort_rows(g->in, n, long_rows, d_small.p + 2, st);
     uint32_t h_err = 0, h_arcs = 0;
@@ -442,6 +497,7 @@ static void device_snapshot(rxc_graph *g, uint32_t n_bound, const uint32_t *live
     RXC_CUDA(cudaMemcpyAsync(&h_arcs, g->out.row.p + n, 4, cudaMemcpyDeviceToHost, st));
     RXC_CUDA(cudaStreamSynchronize(st));
     RXC_CUDA(cudaGetLastError());
+    tp("sort");
     if (h_err & CSR_ERR_ENDPOINT_RANGE) throw std::invalid_argument("edge endpoint >= n_bound");
     if (h_err & CSR_ERR_ENDPOINT_DEAD) throw std::invalid_argument("edge endpoint is not a live node");
     if (h_err & CSR_ERR_EDGE_ID) throw std::invalid_argument("edge index >= e_bound");
@@ -792,7 +848,8 @@ static void bc_partial(rxc_graph *g, const std::vector<uint32_t> &sources, bool 
     const uint32_t n = g->host.n_live;
     const size_t out_len = edge_mode ? g->host.e_bound : g->host.n_bound;
     const size_t acc_len = edge_mode ? g->host.e_bound : n;
-    std::fill(out, out + out_len, 0.0);
+    const bool dense = edge_mode || g->host.n_bound == n;  // no holes: device order == original order
+    if (!dense || acc_len == 0) std::fill(out, out + out_len, 0.0);
     if (acc_len == 0) {
         end_call(g);
         return;
@@ -803,7 +860,7 @@ static void bc_partial(rxc_graph *g, const std::vector<uint32_t> &sources, bool 
     for (const auto &round : distinct_rounds(sources, n)) bc_run(g, round, endpoints, edge_mode, acc.p);
     end_call(g);
     const double t0 = now_ms();
-    if (edge_mode) {
+    if (dense) {
         RXC_CUDA(cudaMemcpyAsync(out, acc.p, acc_len * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
         RXC_CUDA(cudaStreamSynchronize(g->stream));
     } else {
@@ -997,7 +1054,7 @@ static void bfs_run(rxc_graph *g, const DeviceCSR &csr, const std::vector<uint32
         RXC_CUDA(cudaEventRecord(g->ev[1], st));
         const double t0 = now_ms();
         if (rows_mode) {
-            d2h_staged(g->pinned, out + (size_t)s0 * n, ws.rows.p, (size_t)cnt * n * 8, st);
+            d2h_staged(pinned_for(g->device), out + (size_t)s0 * n, ws.rows.p, (size_t)cnt * n * 8, st);
         } else {
             RXC_CUDA(cudaMemcpyAsync(h_vals.data(), ws.vals.p, (size_t)cnt * 8 * vstride,
                                      cudaMemcpyDeviceToHost, st));
@@ -1144,7 +1201,7 @@ static void bfs_smem_run(rxc_graph *g, const DeviceCSR &csr, const uint32_t *sou
         RXC_CUDA(cudaEventRecord(g->ev[1], st));
         const double t0 = now_ms();
         if (rows_mode)
-            d2h_staged(g->pinned, out + s0 * n, d_rows.p, cnt * (size_t)n * 8, st);
+            d2h_staged(pinned_for(g->device), out + s0 * n, d_rows.p, cnt * (size_t)n * 8, st);
         else
             RXC_CUDA(cudaMemcpyAsync(h_vals.data(), d_vals.p, cnt * 8 * vstride, cudaMemcpyDeviceToHost, st));
         RXC_CUDA(cudaStreamSynchronize(st));
@@ -1402,7 +1459,7 @@ static void wsp_run(rxc_graph *g, bool reversed, const double *d_cost, const std
             // te / v counters come from the tile pass; run it for the counters only when cheap
             RXC_CUDA(cudaEventRecord(g->ev[2], st));
             const double t0 = now_ms();
-            d2h_staged(g->pinned, out + s0 * n, d_rows.p, cnt * (size_t)n * 8, st);
+            d2h_staged(pinned_for(g->device), out + s0 * n, d_rows.p, cnt * (size_t)n * 8, st);
             RXC_CUDA(cudaGetLastError());
             g->stats.ms_d2h += now_ms() - t0;
         }
