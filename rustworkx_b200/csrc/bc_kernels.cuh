@@ -297,9 +297,11 @@ __device__ __forceinline__ void cp_async_wait_pending(int n) {
 
 // acc[k] += rows[v][lane][k] over the arcs in nz (lanes of v_lane / m_lane with a non-empty mask)
 // for the sources the arc's mask names, arc order preserved; up to STAGE rows in flight per warp.
+// Per-row bookkeeping is kept out of this loop (ncu: ~80 issued instructions per gathered row made
+// the big launches co-limited by issue slots): the union of the masks and the DAG-arc count are
+// formed once per look-up from the lanes' own masks by the callers.
 __device__ __forceinline__ void bc_gather(const double *rows, uint32_t v_lane, const Mask128 &m_lane,
-                                          uint32_t nz, int lane, double *stage, double (&acc)[BK],
-                                          Mask128 &seen, unsigned long long &dag) {
+                                          uint32_t nz, int lane, double *stage, double (&acc)[BK]) {
     // Batches of STAGE rows.  (A ring that tops itself up row by row, so that STAGE rows stay in
     // flight for the whole arc list, was measured: 80 -> 86 ms per 1024 sources -- its bookkeeping
     // costs more issue slots than the shorter waits give back.)
@@ -331,9 +333,6 @@ __device__ __forceinline__ void bc_gather(const double *rows, uint32_t v_lane, c
                 if ((mj.w[1] >> lane) & 1u) acc[1] += x0.y;
                 if ((mj.w[2] >> lane) & 1u) acc[2] += x1.x;
                 if ((mj.w[3] >> lane) & 1u) acc[3] += x1.y;
-#pragma unroll
-                for (int k = 0; k < BK; k++) seen.w[k] |= mj.w[k];
-                dag += mask_popc(mj);
             }
         }
         __syncwarp();  // the slots may be refilled by other lanes from here on
@@ -374,7 +373,7 @@ __device__ __forceinline__ void bc_fwd_scan(const BcParams &p, const double *row
                                             uint32_t tag_cur, uint32_t e0, uint32_t e1,
                                             uint32_t first, uint32_t step, const Mask128 &unv,
                                             int lane, double *stage, double (&acc)[BK],
-                                            Mask128 &newm, unsigned long long &dag) {
+                                            Mask128 &newm) {
     for (uint32_t e = e0 + first; e < e1; e += step) {
         const uint32_t idx = e + lane;
         uint32_t v = 0;
@@ -386,7 +385,11 @@ __device__ __forceinline__ void bc_fwd_scan(const BcParams &p, const double *row
             for (int k = 0; k < BK; k++) m.w[k] &= unv.w[k];
         }
         const uint32_t nz = __ballot_sync(FULL, mask_any(m));
-        bc_gather(rows, v, m, nz, lane, stage, acc, newm, dag);
+        if (nz) {
+#pragma unroll
+            for (int k = 0; k < BK; k++) newm.w[k] |= __reduce_or_sync(FULL, m.w[k]);
+            bc_gather(rows, v, m, nz, lane, stage, acc);
+        }
     }
 }
 
@@ -453,7 +456,6 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) bc_forward_kernel(BcPara
     const uint32_t ncand = s_ncand;
 
     // 2. warps take candidates dynamically (degree skew)
-    unsigned long long dag = 0;
     for (;;) {
         uint32_t i = 0;
         if (lane == 0) i = atomicAdd(&s_next, 1);
@@ -465,7 +467,7 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) bc_forward_kernel(BcPara
         if (e1 - e0 > p.hub_degree && bc_defer_hub(p, level, g, w, unv)) continue;
         double acc[BK] = {0.0, 0.0, 0.0, 0.0};
         Mask128 newm = mask_zero();
-        bc_fwd_scan(p, rows, Pcur, tag_cur, e0, e1, 0, 32, unv, lane, stage, acc, newm, dag);
+        bc_fwd_scan(p, rows, Pcur, tag_cur, e0, e1, 0, 32, unv, lane, stage, acc, newm);
         if (mask_any(newm)) {
 #pragma unroll
             for (int k = 0; k < BK; k++)
@@ -530,9 +532,7 @@ __global__ void __launch_bounds__(BLOCK) bc_forward_hub_kernel(BcParams p, uint3
         const uint32_t e0 = p.row[w], e1 = p.row[w + 1];
         double acc[BK] = {0.0, 0.0, 0.0, 0.0};
         Mask128 newm = mask_zero();
-        unsigned long long dag = 0;
-        bc_fwd_scan(p, rows, Pcur, tag_cur, e0, e1, wid * 32, WARPS * 32, unv, lane, stage, acc, newm,
-                    dag);
+        bc_fwd_scan(p, rows, Pcur, tag_cur, e0, e1, wid * 32, WARPS * 32, unv, lane, stage, acc, newm);
 #pragma unroll
         for (int k = 0; k < BK; k++) s_acc[wid][lane * BK + k] = acc[k];
         if (lane == 0) s_new[wid] = newm;
@@ -595,9 +595,9 @@ __device__ __forceinline__ void bc_bwd_scan(const BcParams &p, const double *row
             if (EDGE && mask_any(m)) ed = p.eid[idx];
         }
         uint32_t nz = __ballot_sync(FULL, mask_any(m));
+        dag += mask_popc(m);  // per lane: the sources of this lane's own arc (summed over the warp at the end)
         if (!EDGE) {
-            Mask128 seen = mask_zero();
-            bc_gather(rows, w, m, nz, lane, stage, acc, seen, dag);
+            bc_gather(rows, w, m, nz, lane, stage, acc);
         } else {
             while (nz) {
                 // stage up to STAGE successor rows, then form per-arc sums over all 128 sources
@@ -637,7 +637,6 @@ __device__ __forceinline__ void bc_bwd_scan(const BcParams &p, const double *row
                                 c[i] += ck;
                             }
                         }
-                        dag += mask_popc(mj);
                     }
                 }
                 // reduce the STAGE per-arc sums over the warp at once: log2(STAGE) halving exchanges
@@ -733,7 +732,8 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) bc_backward_kernel(BcPar
         for (int k = 0; k < BK; k++)
             if (reach[k]) atomicAdd(&p.reach[(size_t)g * BG + k * 32 + lane], reach[k]);
     }
-    if (lane == 0 && (te | vv | dag)) {  // dag is warp-uniform
+    dag = warp_sum_u64(dag);
+    if (lane == 0 && (te | vv | dag)) {
         atomicAdd(&p.stats[ST_TE], te);
         atomicAdd(&p.stats[ST_V], vv);
         atomicAdd(&p.stats[ST_DAG], dag);
@@ -769,6 +769,7 @@ __global__ void __launch_bounds__(BLOCK) bc_backward_hub_kernel(BcParams p, uint
         __syncthreads();  // every warp has read row v before warp 0 rewrites it
 #pragma unroll
         for (int k = 0; k < BK; k++) s_acc[wid][lane * BK + k] = acc[k];
+        dag = warp_sum_u64(dag);
         if (lane == 0) s_dag[wid] = dag;
         __syncthreads();
         if (wid == 0) {

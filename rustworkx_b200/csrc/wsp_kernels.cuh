@@ -183,6 +183,11 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) wsp_relax_kernel(WspPara
                 m = bc_level_mask(Ccur, v, tag_cur);
             }
             uint32_t nz = __ballot_sync(FULL, mask_any(m));
+            if (nz) {  // once per look-up instead of once per row
+#pragma unroll
+                for (int k = 0; k < BK; k++) touched.w[k] |= __reduce_or_sync(FULL, m.w[k]);
+                relaxed += mask_popc(m);  // per lane; summed over the warp at the end
+            }
             while (nz) {
                 uint32_t todo = nz;
                 int cnt = 0;
@@ -213,9 +218,6 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) wsp_relax_kernel(WspPara
                         if ((mj.w[1] >> lane) & 1u) best[1] = fmin(best[1], x0.y + cj);
                         if ((mj.w[2] >> lane) & 1u) best[2] = fmin(best[2], x1.x + cj);
                         if ((mj.w[3] >> lane) & 1u) best[3] = fmin(best[3], x1.y + cj);
-#pragma unroll
-                        for (int k = 0; k < BK; k++) touched.w[k] |= mj.w[k];
-                        relaxed += mask_popc(mj);
                     }
                 }
                 __syncwarp();
@@ -257,6 +259,7 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) wsp_relax_kernel(WspPara
     __syncthreads();
     if ((uint32_t)tid < nout)
         p.qv[(size_t)g * p.qstride + (size_t)((round + 1) & 1) * p.n + s_base + tid] = s_ov[tid];
+    relaxed = warp_sum_u64(relaxed);
     if (lane == 0 && relaxed) atomicAdd(&p.stats[ST_DAG], relaxed);
 }
 
