@@ -79,6 +79,9 @@ struct BcParams {
     const uint32_t *scol;
     uint32_t *maybe;      // [NG][mwords] bit v: v has a neighbour on the current frontier (sparse levels)
     double *sc;           // [NG][n][128] sigma on the way down, (1+delta)/sigma on the way up
+    uint32_t *sig32;      // [NG][n][128] narrow mode: sigma as exact 32-bit path counts (sc holds only
+                          // (1+delta)/sigma then); lane l owns the 16-byte chunk [4l..4l+3]
+    uint32_t *overflow;   // narrow mode: set when a path count does not fit 32 bits
     PEntry *P0;           // [NG][n] tagged level masks, even levels
     PEntry *P1;           // [NG][n] tagged level masks, odd levels
     Mask128 *visited;     // [NG][n]
@@ -172,6 +175,7 @@ __global__ void __launch_bounds__(BLOCK) bc_init_kernel(BcParams p) {
 }
 
 // Level 0: one warp per group seeds its (up to) 128 sources.
+template <bool NARROW>
 __global__ void __launch_bounds__(32) bc_seed_kernel(BcParams p) {
     const uint32_t g = blockIdx.x;
     const int lane = lane_id();
@@ -189,7 +193,8 @@ __global__ void __launch_bounds__(32) bc_seed_kernel(BcParams p) {
             for (int j = 0; j < BK; j++) vis.w[j] = ~valid.w[j] | bit.w[j];
             mask_store(&p.visited[gv], vis);  // sources of a group are distinct vertices
             bc_store_level(p.P0 + (size_t)g * p.n, s, p.tagbase + 1, bit);
-            p.sc[gv * BG + lane * BK + k] = 1.0;
+            if (NARROW) p.sig32[gv * BG + lane * BK + k] = 1u;
+            else p.sc[gv * BG + lane * BK + k] = 1.0;
             const uint32_t i = base + __popc(valid.w[k] & lanemask_lt());
             p.qv[(size_t)g * p.qcap + i] = s;
             mask_store(&p.qm[(size_t)g * p.qcap + i], bit);
@@ -339,6 +344,112 @@ __device__ __forceinline__ void bc_gather(const double *rows, uint32_t v_lane, c
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// narrow sigma rows
+//
+// sigma counts shortest paths: exact integers.  On small-world graphs they are tiny (BA(1M,8): below
+// 10^5), so the forward pass keeps them as uint32 -- a 512-byte row per vertex, 8 sources per DRAM
+// sector instead of 4 -- and accumulates in uint64.  That halves the bytes, the LDGSTS/LDS
+// wavefronts and the copy instructions of every gathered row, and leaves room for 8 rows in flight
+// per warp in the same shared memory.  The dependency sweep needs (1+delta)/sigma in f64 and writes
+// it to the f64 rows.  A path count that does not fit 32 bits (lattices: binomially many paths)
+// raises `overflow`; the host then redoes the batch with f64 sigma rows (the "wide" mode, which is
+// the layout described at the top of this file) and stays wide for the handle.
+// ---------------------------------------------------------------------------------------------
+template <bool NARROW>
+struct SigmaRows;
+template <>
+struct SigmaRows<false> {
+    using Elem = double;
+    using Acc = double;
+    static __device__ __forceinline__ Elem *rows(const BcParams &p, size_t gn) { return p.sc + gn * BG; }
+};
+template <>
+struct SigmaRows<true> {
+    using Elem = uint32_t;
+    using Acc = unsigned long long;
+    static __device__ __forceinline__ Elem *rows(const BcParams &p, size_t gn) { return p.sig32 + gn * BG; }
+};
+constexpr int STAGE32 = 2 * STAGE;  // 512-byte rows: twice as many slots in the same shared memory
+
+__device__ __forceinline__ void bc_gather(const uint32_t *rows, uint32_t v_lane, const Mask128 &m_lane,
+                                          uint32_t nz, int lane, double *stage_f64,
+                                          unsigned long long (&acc)[BK]) {
+    // lane l copies and reads back its own 16-byte chunk: contiguous on both sides, no swizzle, and
+    // cp.async.wait_all is the only synchronisation a lane needs for bytes it copied itself
+    uint4 *stage = reinterpret_cast<uint4 *>(stage_f64);
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage) + 16u * lane;
+    while (nz) {
+        uint32_t todo = nz;
+        int cnt = 0;
+#pragma unroll
+        for (int i = 0; i < STAGE32; i++) {
+            if (nz) {  // warp-uniform
+                const int a = __ffs(nz) - 1;
+                nz &= nz - 1;
+                const uint32_t vj = __shfl_sync(FULL, v_lane, a);
+                const uint32_t any = __shfl_sync(FULL, mask_or(m_lane), a);
+                const uint32_t on = (any >> lane) & 1u;
+                const uint32_t *src = rows + (size_t)vj * BG + lane * BK;
+                asm volatile(
+                    "{\n"
+                    ".reg .pred p1;\n"
+                    "setp.ne.u32 p1, %2, 0;\n"
+                    "@p1 cp.async.cg.shared.global [%0], [%1], 16;\n"
+                    "}\n" ::"r"(sbase + 512u * i),
+                    "l"(src), "r"(on)
+                    : "memory");
+                cnt = i + 1;
+            }
+        }
+        cp_async_wait_all();
+#pragma unroll
+        for (int i = 0; i < STAGE32; i++) {
+            if (i < cnt) {
+                const int a = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const Mask128 mj = mask_shfl(m_lane, a);
+                const uint4 x = stage[i * 32 + lane];
+                if ((mj.w[0] >> lane) & 1u) acc[0] += x.x;
+                if ((mj.w[1] >> lane) & 1u) acc[1] += x.y;
+                if ((mj.w[2] >> lane) & 1u) acc[2] += x.z;
+                if ((mj.w[3] >> lane) & 1u) acc[3] += x.w;
+            }
+        }
+    }
+}
+
+// sigma of a newly discovered (vertex, source); narrow mode flags counts beyond 32 bits
+template <bool NARROW>
+__device__ __forceinline__ void bc_store_sigma(const BcParams &p, typename SigmaRows<NARROW>::Elem *dst,
+                                               typename SigmaRows<NARROW>::Acc v) {
+    if (NARROW) {
+        if ((unsigned long long)v >> 32) *p.overflow = 1u;
+        *dst = (typename SigmaRows<NARROW>::Elem)v;
+    } else {
+        *dst = (typename SigmaRows<NARROW>::Elem)v;
+    }
+}
+
+// own sigma of the four sources of a lane, as f64
+template <bool NARROW>
+__device__ __forceinline__ Row4 bc_load_sigma(const BcParams &p, size_t gn, uint32_t v, int lane, bool on) {
+    if (NARROW) {
+        Row4 r;
+        r.x[0] = r.x[1] = r.x[2] = r.x[3] = 0.0;
+        if (on) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(p.sig32 + (gn + v) * BG + lane * BK);
+            r.x[0] = (double)q.x;
+            r.x[1] = (double)q.y;
+            r.x[2] = (double)q.z;
+            r.x[3] = (double)q.w;
+        }
+        return r;
+    }
+    return row_load(p.sc + gn * BG, v, lane, on);
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
@@ -369,10 +480,11 @@ __global__ void __launch_bounds__(BLOCK) bc_mark_kernel(BcParams p, uint32_t lev
 
 // One warp: scan the in-arcs of a vertex (chunks of 32 arcs starting at e0+first, stride `step`),
 // pick up the sources whose frontier holds the neighbour, and sum the neighbours' sigma rows.
-__device__ __forceinline__ void bc_fwd_scan(const BcParams &p, const double *rows, const PEntry *Pcur,
+template <class Elem, class Acc>
+__device__ __forceinline__ void bc_fwd_scan(const BcParams &p, const Elem *rows, const PEntry *Pcur,
                                             uint32_t tag_cur, uint32_t e0, uint32_t e1,
                                             uint32_t first, uint32_t step, const Mask128 &unv,
-                                            int lane, double *stage, double (&acc)[BK],
+                                            int lane, double *stage, Acc (&acc)[BK],
                                             Mask128 &newm) {
     for (uint32_t e = e0 + first; e < e1; e += step) {
         const uint32_t idx = e + lane;
@@ -396,7 +508,9 @@ __device__ __forceinline__ void bc_fwd_scan(const BcParams &p, const double *row
 // One BFS level for every group of the batch: vertices not yet reached by all 128 sources scan
 // their in-arcs -- the bottom-up form of centrality.rs:427-437.  No early exit: every frontier
 // parent contributes to sigma.
+template <bool NARROW>
 __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) bc_forward_kernel(BcParams p, uint32_t level) {
+    using Acc = typename SigmaRows<NARROW>::Acc;
     const uint32_t g = blockIdx.y;
     uint32_t *lc = p.lvlcnt + (size_t)g * p.lcap;
     uint32_t *lo = p.loff + (size_t)g * p.lcap;
@@ -421,7 +535,7 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) bc_forward_kernel(BcPara
     Mask128 *visited = p.visited + gn;
     const PEntry *Pcur = bc_P(p, level) + gn;
     PEntry *Pnext = bc_P(p, level + 1) + gn;
-    double *rows = p.sc + gn * BG;
+    auto *rows = SigmaRows<NARROW>::rows(p, gn);
     const uint32_t tag_cur = p.tagbase + level + 1, tag_next = tag_cur + 1;
 
     // 1. coalesced read of this CTA's 256 visited masks; compact the unfinished vertices
@@ -465,13 +579,13 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) bc_forward_kernel(BcPara
         const Mask128 unv = s_unv[i];
         const uint32_t e0 = p.row[w], e1 = p.row[w + 1];
         if (e1 - e0 > p.hub_degree && bc_defer_hub(p, level, g, w, unv)) continue;
-        double acc[BK] = {0.0, 0.0, 0.0, 0.0};
+        Acc acc[BK] = {0, 0, 0, 0};
         Mask128 newm = mask_zero();
         bc_fwd_scan(p, rows, Pcur, tag_cur, e0, e1, 0, 32, unv, lane, stage, acc, newm);
         if (mask_any(newm)) {
 #pragma unroll
             for (int k = 0; k < BK; k++)
-                if ((newm.w[k] >> lane) & 1u) rows[(size_t)w * BG + lane * BK + k] = acc[k];
+                if ((newm.w[k] >> lane) & 1u) bc_store_sigma<NARROW>(p, &rows[(size_t)w * BG + lane * BK + k], acc[k]);
             if (lane == 0) {
                 Mask128 vis;
 #pragma unroll
@@ -507,7 +621,9 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) bc_forward_kernel(BcPara
 }
 
 // Deferred high-degree vertices of the forward level: one CTA per vertex, warps split the arcs.
+template <bool NARROW>
 __global__ void __launch_bounds__(BLOCK) bc_forward_hub_kernel(BcParams p, uint32_t level) {
+    using Acc = typename SigmaRows<NARROW>::Acc;
     const uint32_t g = blockIdx.y;
     uint32_t *lc = p.lvlcnt + (size_t)g * p.lcap;
     uint32_t *lo = p.loff + (size_t)g * p.lcap;
@@ -519,9 +635,9 @@ __global__ void __launch_bounds__(BLOCK) bc_forward_hub_kernel(BcParams p, uint3
     Mask128 *visited = p.visited + gn;
     const PEntry *Pcur = bc_P(p, level) + gn;
     PEntry *Pnext = bc_P(p, level + 1) + gn;
-    double *rows = p.sc + gn * BG;
+    auto *rows = SigmaRows<NARROW>::rows(p, gn);
     const uint32_t tag_cur = p.tagbase + level + 1, tag_next = tag_cur + 1;
-    __shared__ double s_acc[WARPS][BG];
+    __shared__ Acc s_acc[WARPS][BG];
     __shared__ Mask128 s_new[WARPS];
     extern __shared__ __align__(16) double s_dyn_stage[];
     double *stage = s_dyn_stage + (size_t)(threadIdx.x >> 5) * STAGE * BG;
@@ -530,7 +646,7 @@ __global__ void __launch_bounds__(BLOCK) bc_forward_hub_kernel(BcParams p, uint3
         const uint32_t w = p.hubv[(size_t)g * p.hubcap + h];
         const Mask128 unv = mask_load(&p.hubm[(size_t)g * p.hubcap + h]);
         const uint32_t e0 = p.row[w], e1 = p.row[w + 1];
-        double acc[BK] = {0.0, 0.0, 0.0, 0.0};
+        Acc acc[BK] = {0, 0, 0, 0};
         Mask128 newm = mask_zero();
         bc_fwd_scan(p, rows, Pcur, tag_cur, e0, e1, wid * 32, WARPS * 32, unv, lane, stage, acc, newm);
 #pragma unroll
@@ -538,7 +654,7 @@ __global__ void __launch_bounds__(BLOCK) bc_forward_hub_kernel(BcParams p, uint3
         if (lane == 0) s_new[wid] = newm;
         __syncthreads();
         if (wid == 0) {
-            double tot[BK] = {0.0, 0.0, 0.0, 0.0};
+            Acc tot[BK] = {0, 0, 0, 0};
             Mask128 nm = mask_zero();
             for (int q = 0; q < WARPS; q++) {
 #pragma unroll
@@ -550,7 +666,7 @@ __global__ void __launch_bounds__(BLOCK) bc_forward_hub_kernel(BcParams p, uint3
             if (mask_any(nm)) {
 #pragma unroll
                 for (int k = 0; k < BK; k++)
-                    if ((nm.w[k] >> lane) & 1u) rows[(size_t)w * BG + lane * BK + k] = tot[k];
+                    if ((nm.w[k] >> lane) & 1u) bc_store_sigma<NARROW>(p, &rows[(size_t)w * BG + lane * BK + k], tot[k]);
                 if (lane == 0) {
                     Mask128 vis;
 #pragma unroll
@@ -689,7 +805,7 @@ __device__ __forceinline__ void bc_bwd_finish(const BcParams &p, uint32_t v, con
 //   delta[v][b] = sigma[v][b] * sum_{w in N+(v), depth_b(w) = level+1} (1+delta[w][b])/sigma[w][b]
 // which regroups centrality.rs:272-279 by predecessor (pull instead of push; no f64 atomics on the
 // rows).  The row of v is then overwritten with (1+delta)/sigma for the level above to pull.
-template <bool EDGE, bool ENDPOINTS>
+template <bool EDGE, bool ENDPOINTS, bool NARROW>
 __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) bc_backward_kernel(BcParams p, uint32_t level) {
     const uint32_t g = blockIdx.y;
     if (blockIdx.x == 0 && threadIdx.x == 0) *bc_hubcnt(p, level + 1, g) = 0;  // for the next launch
@@ -722,7 +838,7 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) bc_backward_kernel(BcPar
             for (int k = 0; k < BK; k++) reach[k] += (fm.w[k] >> lane) & 1u;
         }
         if (e1 - e0 > p.hub_degree && bc_defer_hub(p, level, g, v, fm)) continue;
-        const Row4 sg = row_load(rows, v, lane, (mask_or(fm) >> lane) & 1u);
+        const Row4 sg = bc_load_sigma<NARROW>(p, gn, v, lane, (mask_or(fm) >> lane) & 1u);
         double acc[BK] = {0.0, 0.0, 0.0, 0.0};
         bc_bwd_scan<EDGE>(p, rows, Pnext, tag_next, e0, e1, 0, 32, fm, sg.x, lane, stage, acc, dag);
         bc_bwd_finish<EDGE, ENDPOINTS>(p, v, fm, sg.x, acc, rows, Pcur, tag_cur, level, lane);
@@ -741,7 +857,7 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) bc_backward_kernel(BcPar
 }
 
 // Deferred high-degree entries of a backward level: one CTA per entry, warps split the arcs.
-template <bool EDGE, bool ENDPOINTS>
+template <bool EDGE, bool ENDPOINTS, bool NARROW>
 __global__ void __launch_bounds__(BLOCK) bc_backward_hub_kernel(BcParams p, uint32_t level) {
     const uint32_t g = blockIdx.y;
     const uint32_t nh = min(*bc_hubcnt(p, level, g), p.hubcap);
@@ -761,7 +877,7 @@ __global__ void __launch_bounds__(BLOCK) bc_backward_hub_kernel(BcParams p, uint
         const uint32_t v = p.hubv[(size_t)g * p.hubcap + h];
         const Mask128 fm = mask_load(&p.hubm[(size_t)g * p.hubcap + h]);
         const uint32_t e0 = p.row[v], e1 = p.row[v + 1];
-        const Row4 sg = row_load(rows, v, lane, (mask_or(fm) >> lane) & 1u);
+        const Row4 sg = bc_load_sigma<NARROW>(p, gn, v, lane, (mask_or(fm) >> lane) & 1u);
         double acc[BK] = {0.0, 0.0, 0.0, 0.0};
         unsigned long long dag = 0;
         bc_bwd_scan<EDGE>(p, rows, Pnext, tag_next, e0, e1, wid * 32, WARPS * 32, fm, sg.x, lane,
@@ -822,6 +938,7 @@ __global__ void __launch_bounds__(BLOCK)
 }
 
 // Level 0 in pair mode: source j seeds slots j and 64+j with one queue entry carrying both bits.
+template <bool NARROW>
 __global__ void __launch_bounds__(32) bc_seed_pair_kernel(BcParams p) {
     const uint32_t g = blockIdx.x;
     const int lane = lane_id();
@@ -839,8 +956,13 @@ __global__ void __launch_bounds__(32) bc_seed_pair_kernel(BcParams p) {
             for (int j = 0; j < BK; j++) vis.w[j] = ~valid.w[j] | bit.w[j];
             mask_store(&p.visited[gv], vis);  // sources are distinct vertices outside the group
             bc_store_level(p.P0 + (size_t)g * p.n, s, p.tagbase + 1, bit);
-            p.sc[gv * BG + lane * BK + k] = 1.0;
-            p.sc[gv * BG + lane * BK + k + 2] = 1.0;
+            if (NARROW) {
+                p.sig32[gv * BG + lane * BK + k] = 1u;
+                p.sig32[gv * BG + lane * BK + k + 2] = 1u;
+            } else {
+                p.sc[gv * BG + lane * BK + k] = 1.0;
+                p.sc[gv * BG + lane * BK + k + 2] = 1.0;
+            }
             const uint32_t i = base + __popc(valid.w[k] & lanemask_lt());
             p.qv[(size_t)g * p.qcap + i] = s;
             mask_store(&p.qm[(size_t)g * p.qcap + i], bit);
@@ -859,6 +981,7 @@ __global__ void __launch_bounds__(32) bc_seed_pair_kernel(BcParams p) {
 // After the forward pass: for every queue entry (t, mask) beyond level 0 with t outside the group,
 // add (sigma_full - paths_avoiding) / sigma_full for each source whose full BFS found t on this
 // level (centrality.rs:2054-2078).  One warp per entry; one atomicAdd per warp.
+template <bool NARROW>
 __global__ void __launch_bounds__(BLOCK) bc_group_finalize_kernel(BcParams p, uint32_t nlevels) {
     const uint32_t g = blockIdx.y;
     const uint32_t *lc = p.lvlcnt + (size_t)g * p.lcap;
@@ -872,7 +995,6 @@ __global__ void __launch_bounds__(BLOCK) bc_group_finalize_kernel(BcParams p, ui
     __syncthreads();
     const uint32_t end = s_end, first = lc[0];  // entries [0, first) are the sources themselves
     const int lane = lane_id();
-    const double *rows = p.sc + (size_t)g * p.n * BG;
     const uint32_t *qv = p.qv + (size_t)g * p.qcap;
     const Mask128 *qm = p.qm + (size_t)g * p.qcap;
     double sum = 0.0;
@@ -886,7 +1008,7 @@ __global__ void __launch_bounds__(BLOCK) bc_group_finalize_kernel(BcParams p, ui
         }
         if (i < first || ((p.blocked[t >> 5] >> (t & 31)) & 1u)) continue;
         const uint32_t full = fm.w[0] | fm.w[1];
-        const Row4 r = row_load(rows, t, lane, (full >> lane) & 1u);
+        const Row4 r = bc_load_sigma<NARROW>(p, (size_t)g * p.n, t, lane, (full >> lane) & 1u);
 #pragma unroll
         for (int k = 0; k < BK / 2; k++) {
             if ((fm.w[k] >> lane) & 1u) {

@@ -114,6 +114,7 @@ struct Options {
     int64_t bc_sparse_div = 16;  // forward levels with <= n/this queue entries use the frontier filter (0: off)
     int64_t device_csr = 1;      // build the CSR on the device (0: host counting sort)
     int64_t bfs_depth_switch = 48;  // auto: pilot BFS deeper than this many levels -> mode 2
+    int64_t bc_sigma = 0;           // betweenness sigma rows: 0 auto (uint32, f64 on overflow), 1 f64, 2 uint32
     int64_t bfs_threads = 0;        // CTA-per-source BFS: threads per CTA (0: 1024 for n >= 2^18, else 256)
     int64_t bfs_ell = 1;            // CTA-per-source BFS: ELL adjacency when every vertex has <= 4 arcs
 };
@@ -133,6 +134,7 @@ static double now_ms() {
 // otherwise cost more than a batch of kernels).
 struct BcWorkspace {
     DevBuf<double> sc;
+    DevBuf<uint32_t> sig32, overflow;  // narrow sigma rows (bc_kernels.cuh) and their overflow flag
     DevBuf<PEntry> P0, P1;
     DevBuf<Mask128> visited, qm, hubm;
     DevBuf<uint32_t> qv, loff, lvlcnt, lvl_total, src, hubv, hubcnt, maybe;
@@ -142,7 +144,7 @@ struct BcWorkspace {
     uint32_t tagbase = 0;   // tags already used in P0/P1
     uint32_t dirty_levels = 0;  // prefix of the level tables the last batch wrote
     void release() {
-        sc.release(); P0.release(); P1.release(); visited.release(); qv.release(); qm.release();
+        sc.release(); sig32.release(); overflow.release(); P0.release(); P1.release(); visited.release(); qv.release(); qm.release();
         loff.release(); lvlcnt.release(); lvl_total.release(); src.release(); reach.release();
         hubv.release(); hubm.release(); hubcnt.release(); maybe.release();
         ng = 0;
@@ -287,6 +289,7 @@ struct rxc_graph {
     BcWorkspace bc_ws;
     BfsWorkspace bfs_ws;
     DevBuf<double> acc_buf;  // partial centrality vector of the current call
+    bool sigma_wide = false;  // a path count overflowed 32 bits on this graph: keep f64 sigma rows
     std::vector<std::unique_ptr<rxc_graph>> replicas;  // same snapshot on the other devices of rxc_set_devices
     std::mutex mu;
 
@@ -593,14 +596,25 @@ static void bc_enable_smem() {
     bool &done = done_dev[dev & 63];
     if (done) return;
     const int b = BC_SMEM_BYTES;
-    RXC_CUDA(cudaFuncSetAttribute(bc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-    RXC_CUDA(cudaFuncSetAttribute(bc_forward_hub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-    RXC_CUDA(cudaFuncSetAttribute(bc_backward_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-    RXC_CUDA(cudaFuncSetAttribute(bc_backward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-    RXC_CUDA(cudaFuncSetAttribute(bc_backward_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-    RXC_CUDA(cudaFuncSetAttribute(bc_backward_hub_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-    RXC_CUDA(cudaFuncSetAttribute(bc_backward_hub_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-    RXC_CUDA(cudaFuncSetAttribute(bc_backward_hub_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    auto attr = [&](const void *fn) {
+        RXC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    };
+    attr((const void *)bc_forward_kernel<false>);
+    attr((const void *)bc_forward_kernel<true>);
+    attr((const void *)bc_forward_hub_kernel<false>);
+    attr((const void *)bc_forward_hub_kernel<true>);
+    attr((const void *)bc_backward_kernel<true, false, false>);
+    attr((const void *)bc_backward_kernel<false, true, false>);
+    attr((const void *)bc_backward_kernel<false, false, false>);
+    attr((const void *)bc_backward_kernel<true, false, true>);
+    attr((const void *)bc_backward_kernel<false, true, true>);
+    attr((const void *)bc_backward_kernel<false, false, true>);
+    attr((const void *)bc_backward_hub_kernel<true, false, false>);
+    attr((const void *)bc_backward_hub_kernel<false, true, false>);
+    attr((const void *)bc_backward_hub_kernel<false, false, false>);
+    attr((const void *)bc_backward_hub_kernel<true, false, true>);
+    attr((const void *)bc_backward_hub_kernel<false, true, true>);
+    attr((const void *)bc_backward_hub_kernel<false, false, true>);
     done = true;
 }
 
@@ -611,7 +625,7 @@ static uint64_t bc_ws_ensure(rxc_graph *g, uint64_t total_groups) {
     const uint32_t lcap = n + 2;
     const uint64_t qcap = (uint64_t)BG * n;
     // bytes per group: 1 KB row + worst-case queues + two tagged mask arrays + visited + level tables
-    const double per_group = (double)n * (1024.0 + 20.0 * BG + 64.0 + 16.0) + (double)lcap * 8.0 + 4096.0;
+    const double per_group = (double)n * (1024.0 + 512.0 + 20.0 * BG + 64.0 + 16.0) + (double)lcap * 8.0 + 4096.0;
     uint64_t ng = g_opt.bc_groups > 0 ? (uint64_t)g_opt.bc_groups
                                       : std::max<uint64_t>(1, (8ull << 20) / std::max<uint32_t>(n, 1));
     ng = std::min<uint64_t>(ng, 64);
@@ -625,6 +639,8 @@ static uint64_t bc_ws_ensure(rxc_graph *g, uint64_t total_groups) {
         ws.wanted = ng;
         ng = std::min<uint64_t>(ng, std::max<uint64_t>(1, (uint64_t)((double)device_budget() / per_group)));
         ws.sc.alloc((size_t)ng * n * BG);
+        ws.sig32.alloc((size_t)ng * n * BG);
+        ws.overflow.alloc(1);
         ws.P0.alloc((size_t)ng * n);
         ws.P1.alloc((size_t)ng * n);
         ws.visited.alloc((size_t)ng * n);
@@ -671,6 +687,8 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
 
     BcParams p{};
     p.sc = ws.sc.p;
+    p.sig32 = ws.sig32.p;
+    p.overflow = ws.overflow.p;
     p.P0 = ws.P0.p;
     p.P1 = ws.P1.p;
     p.visited = ws.visited.p;
@@ -703,7 +721,9 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
     const uint32_t vblocks = (n + BLOCK - 1) / BLOCK;
     uint32_t &clear_levels = ws.dirty_levels;  // prefix of the level tables the previous batch dirtied
 
-    for (uint64_t g0 = 0; g0 < total_groups; g0 += ng) {
+    // One batch; false when a path count overflowed the narrow sigma rows (nothing accumulated yet).
+    auto run_batch = [&](uint64_t g0, bool narrow) -> bool {
+        const rxc_stats stats_before = g->stats;
         const uint32_t bg = (uint32_t)std::min<uint64_t>(ng, total_groups - g0);
         std::fill(h_src.begin(), h_src.end(), NO_SOURCE);
         const size_t s0 = (size_t)g0 * per;
@@ -728,15 +748,19 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
                                  cudaMemcpyHostToDevice, st));
         RXC_CUDA(cudaMemset2DAsync(ws.lvlcnt.p, (size_t)lcap * 4, 0, (size_t)clear_levels * 4, ws.ng, st));
         RXC_CUDA(cudaMemsetAsync(ws.lvl_total.p, 0, (size_t)clear_levels * 4, st));
+        if (narrow) RXC_CUDA(cudaMemsetAsync(ws.overflow.p, 0, 4, st));
         bc_init_kernel<<<dim3(vblocks, bg), BLOCK, 0, st>>>(p);
         if (grp) {
             if (grp->n_members)
                 bc_group_block_kernel<<<dim3((grp->n_members + BLOCK - 1) / BLOCK, bg), BLOCK, 0, st>>>(
                     p, grp->d_members, grp->n_members);
-            bc_seed_pair_kernel<<<bg, 32, 0, st>>>(p);
+            if (narrow) bc_seed_pair_kernel<true><<<bg, 32, 0, st>>>(p);
+            else bc_seed_pair_kernel<false><<<bg, 32, 0, st>>>(p);
             g->stats.launches++;
+        } else if (narrow) {
+            bc_seed_kernel<true><<<bg, 32, 0, st>>>(p);
         } else {
-            bc_seed_kernel<<<bg, 32, 0, st>>>(p);
+            bc_seed_kernel<false><<<bg, 32, 0, st>>>(p);
         }
         g->stats.launches += 2;
 
@@ -749,8 +773,13 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
             g, ws.lvl_total.p, n,
             [&](uint32_t level) {
                 if (p.sparse_max) bc_mark_kernel<<<dim3(MARK_CTAS, bg), BLOCK, 0, st>>>(p, level);
-                bc_forward_kernel<<<dim3(vblocks, bg), BLOCK, BC_SMEM_BYTES, st>>>(p, level);
-                bc_forward_hub_kernel<<<dim3(HUB_CTAS, bg), BLOCK, BC_SMEM_BYTES, st>>>(p, level);
+                if (narrow) {
+                    bc_forward_kernel<true><<<dim3(vblocks, bg), BLOCK, BC_SMEM_BYTES, st>>>(p, level);
+                    bc_forward_hub_kernel<true><<<dim3(HUB_CTAS, bg), BLOCK, BC_SMEM_BYTES, st>>>(p, level);
+                } else {
+                    bc_forward_kernel<false><<<dim3(vblocks, bg), BLOCK, BC_SMEM_BYTES, st>>>(p, level);
+                    bc_forward_hub_kernel<false><<<dim3(HUB_CTAS, bg), BLOCK, BC_SMEM_BYTES, st>>>(p, level);
+                }
                 launched_levels++;
             },
             h_totals);
@@ -759,9 +788,23 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
         clear_levels = std::min<uint32_t>(lcap, launched_levels + 2);
         RXC_CUDA(cudaMemsetAsync(ws.hubcnt.p, 0, ws.hubcnt.bytes(), st));
         RXC_CUDA(cudaEventRecord(g->ev[1], st));
+        // the forward pass only wrote scratch: on overflow of the 32-bit path counts nothing has
+        // been accumulated yet and the caller redoes the batch with f64 sigma rows
+        uint32_t h_overflow = 0;
+        if (narrow) RXC_CUDA(cudaMemcpyAsync(&h_overflow, ws.overflow.p, 4, cudaMemcpyDeviceToHost, st));
 
         if (grp) {  // no dependency sweep: the sums come straight from the two sigma rows
-            bc_group_finalize_kernel<<<dim3(148 * 2, bg), BLOCK, 0, st>>>(p, std::min(L + 1, lcap));
+            if (narrow) {
+                RXC_CUDA(cudaStreamSynchronize(st));
+                if (h_overflow) {
+                    g->stats = stats_before;
+                    tagbase += launched_levels + 8;
+                    return false;
+                }
+                bc_group_finalize_kernel<true><<<dim3(148 * 2, bg), BLOCK, 0, st>>>(p, std::min(L + 1, lcap));
+            } else {
+                bc_group_finalize_kernel<false><<<dim3(148 * 2, bg), BLOCK, 0, st>>>(p, std::min(L + 1, lcap));
+            }
             g->stats.launches++;
             RXC_CUDA(cudaEventRecord(g->ev[2], st));
             RXC_CUDA(cudaStreamSynchronize(st));
@@ -774,7 +817,7 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
             g->stats.batches++;
             g->stats.sources += cnt;
             tagbase += launched_levels + 8;
-            continue;
+            return true;
         }
 
         // backward: out-arcs (pull from successors), deepest level first
@@ -782,6 +825,11 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
         RXC_CUDA(cudaMemcpy2DAsync(h_lvlcnt.data(), (size_t)L * 4, ws.lvlcnt.p, (size_t)lcap * 4,
                                    (size_t)L * 4, bg, cudaMemcpyDeviceToHost, st));
         RXC_CUDA(cudaStreamSynchronize(st));
+        if (h_overflow) {
+            g->stats = stats_before;
+            tagbase += launched_levels + 8;
+            return false;
+        }
         p.row = g->succ().row.p;
         p.col = g->succ().col.p;
         p.eid = g->succ().eid.p;
@@ -793,16 +841,22 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
             if (maxcnt == 0) continue;
             const uint32_t gx = std::min<uint32_t>((maxcnt + WARPS - 1) / WARPS, 16384);
             const dim3 grid(gx, bg), hgrid(HUB_CTAS, bg);
+#define RXC_BWD(E, P, N)                                                                \
+    do {                                                                                \
+        bc_backward_kernel<E, P, N><<<grid, BLOCK, BC_SMEM_BYTES, st>>>(p, l);          \
+        bc_backward_hub_kernel<E, P, N><<<hgrid, BLOCK, BC_SMEM_BYTES, st>>>(p, l);     \
+    } while (0)
             if (edge_mode) {
-                bc_backward_kernel<true, false><<<grid, BLOCK, BC_SMEM_BYTES, st>>>(p, l);
-                bc_backward_hub_kernel<true, false><<<hgrid, BLOCK, BC_SMEM_BYTES, st>>>(p, l);
+                if (narrow) RXC_BWD(true, false, true);
+                else RXC_BWD(true, false, false);
             } else if (endpoints) {
-                bc_backward_kernel<false, true><<<grid, BLOCK, BC_SMEM_BYTES, st>>>(p, l);
-                bc_backward_hub_kernel<false, true><<<hgrid, BLOCK, BC_SMEM_BYTES, st>>>(p, l);
+                if (narrow) RXC_BWD(false, true, true);
+                else RXC_BWD(false, true, false);
             } else {
-                bc_backward_kernel<false, false><<<grid, BLOCK, BC_SMEM_BYTES, st>>>(p, l);
-                bc_backward_hub_kernel<false, false><<<hgrid, BLOCK, BC_SMEM_BYTES, st>>>(p, l);
+                if (narrow) RXC_BWD(false, false, true);
+                else RXC_BWD(false, false, false);
             }
+#undef RXC_BWD
             g->stats.launches += 2;
         }
         if (endpoints && !edge_mode) {
@@ -820,6 +874,16 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
         g->stats.batches++;
         g->stats.sources += cnt;
         tagbase += launched_levels + 8;
+        return true;
+    };
+
+    for (uint64_t g0 = 0; g0 < total_groups; g0 += ng) {
+        const bool narrow = g_opt.bc_sigma == 2 || (g_opt.bc_sigma == 0 && !g->sigma_wide);
+        if (!run_batch(g0, narrow)) {
+            if (g_opt.bc_sigma == 2) throw std::runtime_error("path count exceeds 32 bits (bc_sigma=2 forces uint32 sigma rows)");
+            g->sigma_wide = true;
+            run_batch(g0, false);
+        }
     }
 }
 
@@ -2012,6 +2076,7 @@ int rxc_set_option(const char *name, int64_t value) {
     else if (k == "bfs_mode" && value >= 0 && value <= 2) g_opt.bfs_mode = value;
     else if (k == "bfs_depth_switch" && value >= 0) g_opt.bfs_depth_switch = value;
     else if (k == "bfs_threads" && (value == 0 || value == 128 || value == 256 || value == 512 || value == 1024)) g_opt.bfs_threads = value;
+    else if (k == "bc_sigma" && value >= 0 && value <= 2) g_opt.bc_sigma = value;
     else if (k == "bfs_ell" && (value == 0 || value == 1)) g_opt.bfs_ell = value;
     else if (k == "device_csr" && (value == 0 || value == 1)) g_opt.device_csr = value;
     else if (k == "bc_sparse_div" && value >= 0) g_opt.bc_sparse_div = value;

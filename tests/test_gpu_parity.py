@@ -759,3 +759,55 @@ def test_weighted_closeness_sampled_sources_ba(rx, oracle):
     want, _ = og.weighted_closeness_partial(w, sources, threads=oracle.max_threads())
     got = device_snapshot(g).weighted_closeness_partial(w, sources)
     assert np.allclose(got, want[sources], rtol=1e-12, atol=0.0)
+
+
+# ------------------------------------------------------------------------------------ sigma row formats
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("directed,n,m,seed,holes", CASES[2:6])
+def test_sigma_row_formats_vs_oracle(rx, oracle, directed, n, m, seed, holes, mode):
+    """bc_sigma = 1: f64 sigma rows; 2: uint32 path counts (the default tries uint32 first)."""
+    from rustworkx_b200 import _lib
+
+    g = random_graph(rx, directed, n, m, seed, holes)
+    og = oracle_graph(oracle, g)
+    nb, eb = g._bounds()
+    _lib.set_option("bc_sigma", mode)
+    try:
+        for endpoints in (False, True):
+            want, _ = og.betweenness_centrality(endpoints, True, 1 << 30, as_arrays=True)
+            gd, _ = dense_from_mapping(rx.betweenness_centrality(g, endpoints=endpoints), nb)
+            assert_close(gd, want)
+        want, _ = og.edge_betweenness_centrality(False, 1 << 30, as_arrays=True)
+        gd, _ = dense_from_mapping(rx.edge_betweenness_centrality(g, normalized=False), eb)
+        assert_close(gd, want)
+        group = list(g.node_indices())[:3]
+        want = og.group_betweenness_centrality(group, True, 1 << 30)
+        assert abs(rx.group_betweenness_centrality(g, group) - want) <= ATOL + RTOL * abs(want)
+    finally:
+        _lib.set_option("bc_sigma", 0)
+
+
+def test_sigma_overflow_falls_back_to_f64(rx, oracle):
+    """A 40x40 grid has C(78,39) ~ 2.7e22 shortest paths corner to corner: the uint32 path counts
+    overflow, the batch is redone with f64 sigma rows, and the handle stays wide."""
+    from rustworkx_b200 import _lib, device_snapshot
+
+    g = rx.generators.grid_graph(40, 40)
+    og = oracle_graph(oracle, g)
+    want, _ = og.betweenness_centrality(False, True, 1 << 30, as_arrays=True)
+    got = np.array(list(rx.betweenness_centrality(g).values()))
+    assert_close(got, want)
+    dg = device_snapshot(g)
+    st = dg.stats()
+    assert st["sources"] == 1600  # the redone batch is not counted twice
+    want_e, _ = og.edge_betweenness_centrality(True, 1 << 30, as_arrays=True)
+    assert_close(np.array(list(rx.edge_betweenness_centrality(g).values())), want_e)
+    group = [0, 820, 1599]
+    want_g = og.group_betweenness_centrality(group, True, 1 << 30)
+    assert abs(rx.group_betweenness_centrality(g, group) - want_g) <= RTOL * abs(want_g)
+    _lib.set_option("bc_sigma", 2)
+    try:
+        with pytest.raises(rx.RxCudaError):
+            device_snapshot(rx.generators.grid_graph(40, 41)).betweenness(False, True)
+    finally:
+        _lib.set_option("bc_sigma", 0)
