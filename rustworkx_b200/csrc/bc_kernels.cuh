@@ -247,7 +247,15 @@ __device__ __forceinline__ Row4 row_load(const double *rows, uint32_t v, int lan
 #define RXC_MINBLOCKS 4
 #endif
 constexpr int STAGE = RXC_STAGE;
-constexpr int BC_SMEM_BYTES = WARPS * STAGE * BG * 8;  // 32 KB per CTA
+constexpr int BC_SMEM_BYTES = WARPS * STAGE * BG * 8;  // 32 KB per CTA (forward, edge mode, weighted)
+// The dependency kernels have no static shared memory, so 6 row slots per warp still fit 4 CTAs per
+// SM (4 x 48 KB): measured 45.3 -> 43.3 ms per 1024 sources; the forward kernels (10 KB static)
+// would drop to 3 CTAs per SM with 6 slots and lose 3 ms.
+#ifndef RXC_BSTAGE
+#define RXC_BSTAGE 6
+#endif
+constexpr int BSTAGE = RXC_BSTAGE;
+constexpr int BC_BWD_SMEM_BYTES = WARPS * BSTAGE * BG * 8;
 
 // Staging a row (1 KB = 64 chunks of 16 bytes) without shared-memory bank conflicts on either side.
 // Copy: instruction 1 moves chunk `lane`, instruction 2 chunk `32 + lane`, so the global side of each
@@ -305,6 +313,7 @@ __device__ __forceinline__ void cp_async_wait_pending(int n) {
 // Per-row bookkeeping is kept out of this loop (ncu: ~80 issued instructions per gathered row made
 // the big launches co-limited by issue slots): the union of the masks and the DAG-arc count are
 // formed once per look-up from the lanes' own masks by the callers.
+template <int NS = STAGE>
 __device__ __forceinline__ void bc_gather(const double *rows, uint32_t v_lane, const Mask128 &m_lane,
                                           uint32_t nz, int lane, double *stage, double (&acc)[BK]) {
     // Batches of STAGE rows.  (A ring that tops itself up row by row, so that STAGE rows stay in
@@ -314,7 +323,7 @@ __device__ __forceinline__ void bc_gather(const double *rows, uint32_t v_lane, c
         uint32_t todo = nz;
         int cnt = 0;
 #pragma unroll
-        for (int i = 0; i < STAGE; i++) {
+        for (int i = 0; i < NS; i++) {
             if (nz) {  // warp-uniform
                 const int a = __ffs(nz) - 1;
                 nz &= nz - 1;
@@ -327,7 +336,7 @@ __device__ __forceinline__ void bc_gather(const double *rows, uint32_t v_lane, c
         cp_async_wait_all();
         __syncwarp();  // the chunks a lane reads were copied by other lanes
 #pragma unroll
-        for (int i = 0; i < STAGE; i++) {
+        for (int i = 0; i < NS; i++) {
             if (i < cnt) {
                 const int a = __ffs(todo) - 1;
                 todo &= todo - 1;
@@ -713,7 +722,7 @@ __device__ __forceinline__ void bc_bwd_scan(const BcParams &p, const double *row
         uint32_t nz = __ballot_sync(FULL, mask_any(m));
         dag += mask_popc(m);  // per lane: the sources of this lane's own arc (summed over the warp at the end)
         if (!EDGE) {
-            bc_gather(rows, w, m, nz, lane, stage, acc);
+            bc_gather<BSTAGE>(rows, w, m, nz, lane, stage, acc);
         } else {
             while (nz) {
                 // stage up to STAGE successor rows, then form per-arc sums over all 128 sources
@@ -821,7 +830,7 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) bc_backward_kernel(BcPar
     const Mask128 *qm = p.qm + (size_t)g * p.qcap + off;
 
     extern __shared__ __align__(16) double s_dyn_stage[];
-    double *stage = s_dyn_stage + (size_t)(threadIdx.x >> 5) * STAGE * BG;
+    double *stage = s_dyn_stage + (size_t)(threadIdx.x >> 5) * BSTAGE * BG;
     unsigned long long te = 0, vv = 0, dag = 0;
     unsigned long long reach[BK] = {0, 0, 0, 0};
     const uint32_t warp = blockIdx.x * WARPS + (threadIdx.x >> 5);
@@ -871,7 +880,7 @@ __global__ void __launch_bounds__(BLOCK) bc_backward_hub_kernel(BcParams p, uint
     __shared__ double s_acc[WARPS][BG];
     __shared__ unsigned long long s_dag[WARPS];
     extern __shared__ __align__(16) double s_dyn_stage[];
-    double *stage = s_dyn_stage + (size_t)(threadIdx.x >> 5) * STAGE * BG;
+    double *stage = s_dyn_stage + (size_t)(threadIdx.x >> 5) * BSTAGE * BG;
 
     for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
         const uint32_t v = p.hubv[(size_t)g * p.hubcap + h];

@@ -595,9 +595,9 @@ static void bc_enable_smem() {
     cudaGetDevice(&dev);
     bool &done = done_dev[dev & 63];
     if (done) return;
-    const int b = BC_SMEM_BYTES;
     auto attr = [&](const void *fn) {
-        RXC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+        RXC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      std::max(BC_SMEM_BYTES, BC_BWD_SMEM_BYTES)));
     };
     attr((const void *)bc_forward_kernel<false>);
     attr((const void *)bc_forward_kernel<true>);
@@ -843,8 +843,8 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
             const dim3 grid(gx, bg), hgrid(HUB_CTAS, bg);
 #define RXC_BWD(E, P, N)                                                                \
     do {                                                                                \
-        bc_backward_kernel<E, P, N><<<grid, BLOCK, BC_SMEM_BYTES, st>>>(p, l);          \
-        bc_backward_hub_kernel<E, P, N><<<hgrid, BLOCK, BC_SMEM_BYTES, st>>>(p, l);     \
+        bc_backward_kernel<E, P, N><<<grid, BLOCK, BC_BWD_SMEM_BYTES, st>>>(p, l);      \
+        bc_backward_hub_kernel<E, P, N><<<hgrid, BLOCK, BC_BWD_SMEM_BYTES, st>>>(p, l); \
     } while (0)
             if (edge_mode) {
                 if (narrow) RXC_BWD(true, false, true);
