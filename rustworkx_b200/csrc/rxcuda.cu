@@ -427,14 +427,18 @@ static void device_snapshot(rxc_graph *g, uint32_t n_bound, const uint32_t *live
     h.e_bound = e_bound;
     h.n_edges = n_edges;
     h.directed = directed;
-    h.orig_of_compact.assign(live_nodes, live_nodes + n_live);
-    h.compact_of_orig.assign(n_bound, 0xFFFFFFFFu);
     for (uint32_t i = 0; i < n_live; i++) {
         const uint32_t o = live_nodes[i];
         if (o >= n_bound) throw std::invalid_argument("live node index >= n_bound");
         if (i > 0 && live_nodes[i - 1] >= o)
             throw std::invalid_argument("live_nodes must be strictly ascending");
-        h.compact_of_orig[o] = i;
+    }
+    // strictly ascending, below n_bound, n_bound of them: the identity -- no host maps needed
+    h.identity = n_live == n_bound;
+    if (!h.identity) {
+        h.orig_of_compact.assign(live_nodes, live_nodes + n_live);
+        h.compact_of_orig.assign(n_bound, 0xFFFFFFFFu);
+        for (uint32_t i = 0; i < n_live; i++) h.compact_of_orig[live_nodes[i]] = i;
     }
     if ((directed ? n_edges : 2 * n_edges) >= 0xFFFFFFFFull)
         throw LimitError("more than 2^32-2 arcs are not supported");
@@ -897,9 +901,9 @@ static std::vector<uint32_t> to_compact(const rxc_graph *g, const uint32_t *sour
     std::vector<uint32_t> s(k);
     for (uint64_t i = 0; i < k; i++) {
         const uint32_t o = sources[i];
-        if (o >= g->host.n_bound || g->host.compact_of_orig[o] == 0xFFFFFFFFu)
-            throw std::invalid_argument("source " + std::to_string(o) + " is not a live node");
-        s[i] = g->host.compact_of_orig[o];
+        const uint32_t c = g->host.compact_of(o);
+        if (c == 0xFFFFFFFFu) throw std::invalid_argument("source " + std::to_string(o) + " is not a live node");
+        s[i] = c;
     }
     return s;
 }
@@ -930,7 +934,7 @@ static void bc_partial(rxc_graph *g, const std::vector<uint32_t> &sources, bool 
         std::vector<double> h(n);
         RXC_CUDA(cudaMemcpyAsync(h.data(), acc.p, acc_len * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
         RXC_CUDA(cudaStreamSynchronize(g->stream));
-        for (uint32_t i = 0; i < n; i++) out[g->host.orig_of_compact[i]] = h[i];
+        for (uint32_t i = 0; i < n; i++) out[g->host.orig_of(i)] = h[i];
     }
     fetch_stats(g);
     g->stats.ms_d2h += now_ms() - t0;
@@ -1924,7 +1928,7 @@ int rxc_newman_weighted_closeness(rxc_graph *g, const double *edge_weight, int w
             const std::vector<uint32_t> src = shard_sources(r->host.n_live, k, nk);
             std::vector<double> vals(src.size());
             wsp_closeness(r, edge_weight, true, true, src, wf_improved != 0, vals.data());
-            for (size_t i = 0; i < src.size(); i++) out[r->host.orig_of_compact[src[i]]] = vals[i];
+            for (size_t i = 0; i < src.size(); i++) out[r->host.orig_of(src[i])] = vals[i];
         });
     });
 }
@@ -1994,7 +1998,7 @@ int rxc_closeness(rxc_graph *g, int wf_improved, double *out) {
             // closeness follows incoming edges: BFS over Reversed(&graph), centrality.rs:1208
             bfs_dispatch(r, r->pred(), src, BfsMode::Closeness, wf_improved != 0, 0.0, vals.data());
             end_call(r);
-            for (size_t i = 0; i < src.size(); i++) out[r->host.orig_of_compact[src[i]]] = vals[i];
+            for (size_t i = 0; i < src.size(); i++) out[r->host.orig_of(src[i])] = vals[i];
             fetch_stats(r);
         });
     });

@@ -24,8 +24,15 @@ struct HostSnapshot {
     uint32_t n_bound = 0, n_live = 0, e_bound = 0;
     uint64_t n_edges = 0;  // live edges given (self-loops included)
     bool directed = false;
+    bool identity = false;                  // no holes: compact id == original index, maps left empty
     std::vector<uint32_t> orig_of_compact;  // n_live
     std::vector<uint32_t> compact_of_orig;  // n_bound, 0xFFFFFFFF for holes
+    uint32_t orig_of(uint32_t compact) const { return identity ? compact : orig_of_compact[compact]; }
+    // 0xFFFFFFFF when `orig` is not a live node
+    uint32_t compact_of(uint32_t orig) const {
+        if (orig >= n_bound) return 0xFFFFFFFFu;
+        return identity ? orig : compact_of_orig[orig];
+    }
     HostCSR out;  // successors (undirected: all incident arcs)
     HostCSR in;   // predecessors (empty when undirected: same as `out`)
 };

@@ -276,3 +276,56 @@ def test_group_argument_validation_happens_before_any_device_work():
         rx.group_betweenness_centrality(g, "01")
     with pytest.raises(TypeError):
         rx.digraph_group_closeness_centrality(g, [0])
+
+
+def test_all_pairs_path_length_mapping_behaviour():
+    """AllPairsPathLengthMapping / PathLengthMapping (src/iterators.rs, custom_hash_map_iter_impl!):
+    every live node is a key, the inner mapping holds the reached nodes except the node itself."""
+    import pickle as pk
+
+    from rustworkx_b200.iterators import AllPairsPathLengthMapping, PathLengthMapping
+
+    nan = float("nan")
+    rows = np.array([[0.0, 1.5, nan], [nan, 0.0, nan], [2.0, 3.5, 0.0]])
+    m = AllPairsPathLengthMapping([0, 2, 5], rows)
+    assert m == {0: {2: 1.5}, 2: {}, 5: {0: 2.0, 2: 3.5}}
+    assert list(m.keys()) == [0, 2, 5] and len(m) == 3 and 5 in m and 1 not in m
+    assert isinstance(m[5], PathLengthMapping) and m[5][2] == 3.5
+    with pytest.raises(IndexError):
+        m[1]
+    with pytest.raises(IndexError):
+        m[0][5]
+    assert m != {0: {2: 1.5}, 2: {}, 5: {0: 2.0}}
+    assert str(m).startswith("AllPairsPathLengthMapping{0: PathLengthMapping{2: 1.5}")
+    assert pk.loads(pk.dumps(m)) == m
+    assert [k for k, _ in m.items()] == [0, 2, 5]
+    empty = AllPairsPathLengthMapping([1, 3], None)  # a graph without edges
+    assert empty == {1: {}, 3: {}}
+    assert AllPairsPathLengthMapping() == {}
+
+
+def test_weight_validation_matches_is_valid_weight():
+    # src/lib.rs:303-313 (negative incl. -0.0 and NaN rejected, +inf and 0 accepted); extraction errors
+    import rustworkx_b200 as rx
+
+    g = rx.PyGraph()
+    g.add_nodes_from(range(3))
+    g.add_edges_from([(0, 1, 2.0), (1, 2, "x")])
+    for bad in (-1.0, -0.0, float("nan")):
+        with pytest.raises(ValueError):
+            rx.all_pairs_dijkstra_path_lengths(g, lambda _w, b=bad: b)
+    with pytest.raises(TypeError):
+        rx.all_pairs_dijkstra_path_lengths(g, lambda w: w)  # "x" is not a float
+    with pytest.raises(TypeError):
+        rx.all_pairs_dijkstra_path_lengths(g, 3)  # not callable
+    with pytest.raises(ValueError):
+        rx.newman_weighted_closeness_centrality(g, weight_fn=lambda _w: -2.0)
+    with pytest.raises(TypeError):
+        rx.newman_weighted_closeness_centrality(rx.PyGraph(), wf_improved=1)
+    with pytest.raises(TypeError):
+        rx.graph_newman_weighted_closeness_centrality(rx.PyDiGraph())
+    # graphs without nodes / edges never reach the device
+    assert rx.all_pairs_dijkstra_path_lengths(rx.PyDiGraph(), float) == {}
+    h = rx.PyGraph()
+    h.add_nodes_from(range(4))
+    assert rx.all_pairs_dijkstra_path_lengths(h, float) == {i: {} for i in range(4)}
