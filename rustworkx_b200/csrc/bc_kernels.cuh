@@ -81,7 +81,8 @@ struct BcParams {
     double *sc;           // [NG][n][128] sigma on the way down, (1+delta)/sigma on the way up
     uint32_t *sig32;      // [NG][n][128] narrow mode: sigma as exact 32-bit path counts (sc holds only
                           // (1+delta)/sigma then); lane l owns the 16-byte chunk [4l..4l+3]
-    uint32_t *overflow;   // narrow mode: set when a path count does not fit 32 bits
+    uint32_t *overflow;   // bit 0: a path count does not fit 32 bits (narrow mode); bit 1: a level
+                          // queue outgrew qcap (the host redoes the batch with worst-case queues)
     PEntry *P0;           // [NG][n] tagged level masks, even levels
     PEntry *P1;           // [NG][n] tagged level masks, odd levels
     Mask128 *visited;     // [NG][n]
@@ -437,7 +438,7 @@ template <bool NARROW>
 __device__ __forceinline__ void bc_store_sigma(const BcParams &p, typename SigmaRows<NARROW>::Elem *dst,
                                                typename SigmaRows<NARROW>::Acc v) {
     if (NARROW) {
-        if ((unsigned long long)v >> 32) *p.overflow = 1u;
+        if ((unsigned long long)v >> 32) atomicOr(p.overflow, 1u);
         *dst = (typename SigmaRows<NARROW>::Elem)v;
     } else {
         *dst = (typename SigmaRows<NARROW>::Elem)v;
@@ -475,6 +476,7 @@ __global__ void __launch_bounds__(BLOCK) bc_mark_kernel(BcParams p, uint32_t lev
     const uint32_t cnt = p.lvlcnt[(size_t)g * p.lcap + level];
     if (cnt == 0 || cnt > p.sparse_max) return;
     const uint32_t off = p.loff[(size_t)g * p.lcap + level];
+    if ((uint64_t)off + cnt > p.qcap) return;  // queue overflow (flagged by the forward kernel): batch is redone
     const uint32_t *qv = p.qv + (size_t)g * p.qcap + off;
     uint32_t *maybe = p.maybe + (size_t)g * p.mwords;
     const int lane = lane_id();
@@ -626,9 +628,14 @@ __global__ void __launch_bounds__(BLOCK, (NARROW ? RXC_FWD32_MINBLOCKS : RXC_MIN
     }
     __syncthreads();
     if ((uint32_t)tid < nout) {
-        const size_t q = (size_t)g * p.qcap + s_base + tid;
-        p.qv[q] = s_ov[tid];
-        mask_store(&p.qm[q], s_om[tid]);
+        const uint64_t pos = (uint64_t)s_base + tid;
+        if (pos < p.qcap) {
+            const size_t q = (size_t)g * p.qcap + pos;
+            p.qv[q] = s_ov[tid];
+            mask_store(&p.qm[q], s_om[tid]);
+        } else {
+            atomicOr(p.overflow, 2u);
+        }
     }
 }
 
@@ -687,9 +694,14 @@ __global__ void __launch_bounds__(BLOCK) bc_forward_hub_kernel(BcParams p, uint3
                     bc_store_level(Pnext, w, tag_next, nm);
                     const uint32_t pos = atomicAdd(&lc[level + 1], 1u);
                     atomicAdd(&p.lvl_total[level + 1], 1u);
-                    const size_t q = (size_t)g * p.qcap + lo[level] + fcnt + pos;
-                    p.qv[q] = w;
-                    mask_store(&p.qm[q], nm);
+                    const uint64_t qpos = (uint64_t)lo[level] + fcnt + pos;
+                    if (qpos < p.qcap) {
+                        const size_t q = (size_t)g * p.qcap + qpos;
+                        p.qv[q] = w;
+                        mask_store(&p.qm[q], nm);
+                    } else {
+                        atomicOr(p.overflow, 2u);
+                    }
                 }
             }
         }

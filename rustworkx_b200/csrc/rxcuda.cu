@@ -140,6 +140,7 @@ struct BcWorkspace {
     DevBuf<uint32_t> qv, loff, lvlcnt, lvl_total, src, hubv, hubcnt, maybe;
     DevBuf<unsigned long long> reach;
     uint64_t ng = 0;        // capacity in groups
+    uint64_t qper = 0;      // level-queue entries per vertex and group the queues were sized for
     uint64_t wanted = 0;    // groups asked for when `ng` was sized (may have been clamped by memory)
     uint32_t tagbase = 0;   // tags already used in P0/P1
     uint32_t dirty_levels = 0;  // prefix of the level tables the last batch wrote
@@ -148,6 +149,7 @@ struct BcWorkspace {
         loff.release(); lvlcnt.release(); lvl_total.release(); src.release(); reach.release();
         hubv.release(); hubm.release(); hubcnt.release(); maybe.release();
         ng = 0;
+        qper = 0;
         wanted = 0;
     }
 };
@@ -290,6 +292,7 @@ struct rxc_graph {
     BfsWorkspace bfs_ws;
     DevBuf<double> acc_buf;  // partial centrality vector of the current call
     bool sigma_wide = false;  // a path count overflowed 32 bits on this graph: keep f64 sigma rows
+    bool queue_wide = false;  // a level queue outgrew the typical-case size: keep worst-case queues
     std::vector<std::unique_ptr<rxc_graph>> replicas;  // same snapshot on the other devices of rxc_set_devices
     std::mutex mu;
 
@@ -627,17 +630,30 @@ static void bc_enable_smem() {
 static uint64_t bc_ws_ensure(rxc_graph *g, uint64_t total_groups) {
     const uint32_t n = g->host.n_live;
     const uint32_t lcap = n + 2;
-    const uint64_t qcap = (uint64_t)BG * n;
-    // bytes per group: 1 KB row + worst-case queues + two tagged mask arrays + visited + level tables
-    const double per_group = (double)n * (1024.0 + 512.0 + 20.0 * BG + 64.0 + 16.0) + (double)lcap * 8.0 + 4096.0;
+    // Level queues: a vertex enters a group's queue once per DISTINCT level it has among the 128
+    // sources -- 128 in the worst case (a path graph), 3-5 on small-world graphs.  The queues are
+    // sized for 16 and the kernels flag an overflow, after which the handle keeps worst-case queues
+    // (mapping 33 GB of mostly untouched queue memory cost 2.4 s on the first call at n = 10^6).
+    const uint64_t qper = g->queue_wide ? BG : std::min<uint64_t>(BG, 16);
+    const uint64_t qcap = qper * n;
+    // bytes per group: f64 + uint32 rows, queues, two tagged mask arrays, visited, level tables
+    const double per_group = (double)n * (1024.0 + 512.0 + 20.0 * (double)qper + 64.0 + 16.0) + (double)lcap * 8.0 + 4096.0;
     uint64_t ng = g_opt.bc_groups > 0 ? (uint64_t)g_opt.bc_groups
                                       : std::max<uint64_t>(1, (8ull << 20) / std::max<uint32_t>(n, 1));
     ng = std::min<uint64_t>(ng, 64);
     ng = std::min<uint64_t>(ng, total_groups);
     BcWorkspace &ws = g->bc_ws;
     cudaStream_t st = g->stream;
+    if (ws.qper < qper) ws.release();  // queues too small for this handle now
     if (ws.ng > 0 && ws.ng < ng && ws.wanted >= ng) ng = ws.ng;  // already clamped by memory for this request
     if (ws.ng < ng) {
+        const double t_alloc0 = now_ms();
+        struct TraceAlloc {
+            double t0;
+            ~TraceAlloc() {
+                if (getenv("RXC_TRACE")) fprintf(stderr, "[rxc workspace] alloc %.1f ms\n", now_ms() - t0);
+            }
+        } trace_alloc{t_alloc0};
         ws.release();
         g->bfs_ws.release();  // one scratch set at a time keeps the footprint predictable
         ws.wanted = ng;
@@ -661,6 +677,7 @@ static uint64_t bc_ws_ensure(rxc_graph *g, uint64_t total_groups) {
         ws.maybe.alloc((size_t)ng * ((n + 31) / 32));
         RXC_CUDA(cudaMemsetAsync(ws.maybe.p, 0, ws.maybe.bytes(), st));
         ws.ng = ng;
+        ws.qper = qper;
         ws.tagbase = 0;
         ws.dirty_levels = lcap;
         RXC_CUDA(cudaMemsetAsync(ws.P0.p, 0, ws.P0.bytes(), st));
@@ -684,9 +701,9 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
     const uint32_t per = grp ? BGP : BG;  // sources per group (pair mode: two slots per source)
     const uint64_t total_groups = (sources.size() + per - 1) / per;
     const uint32_t lcap = n + 2;
-    const uint64_t qcap = (uint64_t)BG * n;  // worst case: a vertex sits on a different level per source
     const uint64_t ng = bc_ws_ensure(g, total_groups);
     BcWorkspace &ws = g->bc_ws;
+    const uint64_t qcap = ws.qper * n;
     cudaStream_t st = g->stream;
 
     BcParams p{};
@@ -726,7 +743,7 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
     uint32_t &clear_levels = ws.dirty_levels;  // prefix of the level tables the previous batch dirtied
 
     // One batch; false when a path count overflowed the narrow sigma rows (nothing accumulated yet).
-    auto run_batch = [&](uint64_t g0, bool narrow) -> bool {
+    auto run_batch = [&](uint64_t g0, bool narrow) -> int {
         const rxc_stats stats_before = g->stats;
         const uint32_t bg = (uint32_t)std::min<uint64_t>(ng, total_groups - g0);
         std::fill(h_src.begin(), h_src.end(), NO_SOURCE);
@@ -752,7 +769,7 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
                                  cudaMemcpyHostToDevice, st));
         RXC_CUDA(cudaMemset2DAsync(ws.lvlcnt.p, (size_t)lcap * 4, 0, (size_t)clear_levels * 4, ws.ng, st));
         RXC_CUDA(cudaMemsetAsync(ws.lvl_total.p, 0, (size_t)clear_levels * 4, st));
-        if (narrow) RXC_CUDA(cudaMemsetAsync(ws.overflow.p, 0, 4, st));
+        RXC_CUDA(cudaMemsetAsync(ws.overflow.p, 0, 4, st));
         bc_init_kernel<<<dim3(vblocks, bg), BLOCK, 0, st>>>(p);
         if (grp) {
             if (grp->n_members)
@@ -795,20 +812,17 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
         // the forward pass only wrote scratch: on overflow of the 32-bit path counts nothing has
         // been accumulated yet and the caller redoes the batch with f64 sigma rows
         uint32_t h_overflow = 0;
-        if (narrow) RXC_CUDA(cudaMemcpyAsync(&h_overflow, ws.overflow.p, 4, cudaMemcpyDeviceToHost, st));
+        RXC_CUDA(cudaMemcpyAsync(&h_overflow, ws.overflow.p, 4, cudaMemcpyDeviceToHost, st));
 
         if (grp) {  // no dependency sweep: the sums come straight from the two sigma rows
-            if (narrow) {
-                RXC_CUDA(cudaStreamSynchronize(st));
-                if (h_overflow) {
-                    g->stats = stats_before;
-                    tagbase += launched_levels + 8;
-                    return false;
-                }
-                bc_group_finalize_kernel<true><<<dim3(148 * 2, bg), BLOCK, 0, st>>>(p, std::min(L + 1, lcap));
-            } else {
-                bc_group_finalize_kernel<false><<<dim3(148 * 2, bg), BLOCK, 0, st>>>(p, std::min(L + 1, lcap));
+            RXC_CUDA(cudaStreamSynchronize(st));
+            if (h_overflow) {
+                g->stats = stats_before;
+                tagbase += launched_levels + 8;
+                return (int)h_overflow;
             }
+            if (narrow) bc_group_finalize_kernel<true><<<dim3(148 * 2, bg), BLOCK, 0, st>>>(p, std::min(L + 1, lcap));
+            else bc_group_finalize_kernel<false><<<dim3(148 * 2, bg), BLOCK, 0, st>>>(p, std::min(L + 1, lcap));
             g->stats.launches++;
             RXC_CUDA(cudaEventRecord(g->ev[2], st));
             RXC_CUDA(cudaStreamSynchronize(st));
@@ -821,7 +835,7 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
             g->stats.batches++;
             g->stats.sources += cnt;
             tagbase += launched_levels + 8;
-            return true;
+            return 0;
         }
 
         // backward: out-arcs (pull from successors), deepest level first
@@ -832,7 +846,7 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
         if (h_overflow) {
             g->stats = stats_before;
             tagbase += launched_levels + 8;
-            return false;
+            return (int)h_overflow;
         }
         p.row = g->succ().row.p;
         p.col = g->succ().col.p;
@@ -878,15 +892,23 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
         g->stats.batches++;
         g->stats.sources += cnt;
         tagbase += launched_levels + 8;
-        return true;
+        return 0;
     };
 
     for (uint64_t g0 = 0; g0 < total_groups; g0 += ng) {
-        const bool narrow = g_opt.bc_sigma == 2 || (g_opt.bc_sigma == 0 && !g->sigma_wide);
-        if (!run_batch(g0, narrow)) {
+        for (;;) {
+            const bool narrow = g_opt.bc_sigma == 2 || (g_opt.bc_sigma == 0 && !g->sigma_wide);
+            const int over = run_batch(g0, narrow);
+            if (over == 0) break;
+            if (over & 2) {  // a level queue outgrew its typical-case size: worst-case queues from here on
+                if (g->queue_wide) throw std::runtime_error("level queue overflow with worst-case queues");
+                g->queue_wide = true;
+                const std::vector<uint32_t> rest(sources.begin() + (size_t)g0 * per, sources.end());
+                bc_run(g, rest, endpoints, edge_mode, d_acc, grp);  // re-sizes the scratch
+                return;
+            }
             if (g_opt.bc_sigma == 2) throw std::runtime_error("path count exceeds 32 bits (bc_sigma=2 forces uint32 sigma rows)");
             g->sigma_wide = true;
-            run_batch(g0, false);
         }
     }
 }
@@ -1453,7 +1475,7 @@ static void wsp_run(rxc_graph *g, bool reversed, const double *d_cost, const std
     p.lvl_total = ws.lvl_total.p;
     p.stats = g->d_stats.p;
     p.src = ws.src.p;
-    p.qstride = (uint64_t)BG * n;
+    p.qstride = ws.qper * n;  // >= 2 n: one queue of at most n vertices per round parity
     p.n = n;
     p.lcap = lcap;
     p.mwords = (n + 31) / 32;

@@ -811,3 +811,24 @@ def test_sigma_overflow_falls_back_to_f64(rx, oracle):
             device_snapshot(rx.generators.grid_graph(40, 41)).betweenness(False, True)
     finally:
         _lib.set_option("bc_sigma", 0)
+
+
+def test_level_queue_overflow_falls_back_to_worst_case_queues(rx, oracle):
+    """On a path graph every vertex sits on a different level for each of the 128 sources of a group:
+    the typical-case level queues (16 entries per vertex) overflow, the batch is redone with
+    worst-case queues, and the results still match the oracle."""
+    from rustworkx_b200 import device_snapshot
+
+    g = rx.generators.path_graph(600)
+    og = oracle_graph(oracle, g)
+    want, _ = og.betweenness_centrality(False, False, 1 << 30, as_arrays=True)
+    got = np.array(list(rx.betweenness_centrality(g, normalized=False).values()))
+    assert_close(got, want)
+    assert device_snapshot(g).stats()["sources"] == 600
+    want_e, _ = og.edge_betweenness_centrality(False, 1 << 30, as_arrays=True)
+    assert_close(np.array(list(rx.edge_betweenness_centrality(g, normalized=False).values())), want_e)
+    h = rx.generators.directed_path_graph(300)
+    oh = oracle_graph(oracle, h)
+    group = [10, 150]
+    want_g = oh.group_betweenness_centrality(group, False, 1 << 30)
+    assert abs(rx.group_betweenness_centrality(h, group, normalized=False) - want_g) <= RTOL * abs(want_g)
