@@ -639,7 +639,7 @@ static uint64_t bc_ws_ensure(rxc_graph *g, uint64_t total_groups) {
     // bytes per group: f64 + uint32 rows, queues, two tagged mask arrays, visited, level tables
     const double per_group = (double)n * (1024.0 + 512.0 + 20.0 * (double)qper + 64.0 + 16.0) + (double)lcap * 8.0 + 4096.0;
     uint64_t ng = g_opt.bc_groups > 0 ? (uint64_t)g_opt.bc_groups
-                                      : std::max<uint64_t>(1, (8ull << 20) / std::max<uint32_t>(n, 1));
+                                      : std::max<uint64_t>(1, (16ull << 20) / std::max<uint32_t>(n, 1));
     ng = std::min<uint64_t>(ng, 64);
     ng = std::min<uint64_t>(ng, total_groups);
     BcWorkspace &ws = g->bc_ws;
