@@ -99,6 +99,9 @@ struct BcParams {
     double *acc;          // node mode: [n] by compact vertex; edge mode: [e_bound] by edge index
     const uint32_t *src;  // [NG][128] compact source ids, NO_SOURCE padded; slot 32k+l = lane l, k
     const uint32_t *blocked;  // group betweenness: bitmap of the group's vertices, else nullptr
+    unsigned long long *dsum;   // distance-only mode: [NG][128] sum of distances per source
+    double *drows;              // distance-only mode: [NG*128][n_cols] distance rows, or nullptr
+    uint64_t n_cols;
     uint64_t qcap;
     uint32_t n;
     uint32_t lcap;
@@ -1050,6 +1053,169 @@ __global__ void __launch_bounds__(BLOCK) bc_group_finalize_kernel(BcParams p, ui
             atomicAdd(&p.stats[ST_V], vv);
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// distance-only BFS in the betweenness layout (closeness, distance_matrix, average path length on
+// shallow graphs; rustworkx-core/src/centrality.rs:1190-1220, shortest_path/distance_matrix.rs:127-157)
+//
+// Same bottom-up level kernel as bc_forward_kernel without the sigma rows: an unfinished vertex
+// scans its arcs of the pull adjacency, ORs the tagged 128-bit level masks of the neighbours that sit
+// on the frontier, and stops as soon as every missing source has been found.  One random access
+// moves a whole 32-byte sector and serves 128 sources; the 32-source top-down kernel it replaces on
+// small-world graphs (bfs_level_kernel: one 4-byte word and one atomicOr per arc and group) ran at
+// 131 GTEPS on BA(1M,8).  Per-source reach counts and distance sums are accumulated per lane
+// (lane l owns bit l of the four mask words), reduced in shared memory and added once per CTA.
+// ---------------------------------------------------------------------------------------------
+template <bool ROWS>
+__global__ void __launch_bounds__(BLOCK, 5) bfs128_level_kernel(BcParams p, uint32_t level) {
+    const uint32_t g = blockIdx.y;
+    uint32_t *lc = p.lvlcnt + (size_t)g * p.lcap;
+    uint32_t *lo = p.loff + (size_t)g * p.lcap;
+    const uint32_t fcnt = lc[level];
+    if (fcnt == 0) return;  // this group's BFS has finished
+
+    __shared__ Mask128 s_unv[BLOCK];
+    __shared__ uint32_t s_w[BLOCK], s_ov[BLOCK], s_cnt[BG];
+    __shared__ uint32_t s_ncand, s_next, s_nout, s_base;
+    __shared__ unsigned long long s_te;
+    const int tid = threadIdx.x, lane = lane_id();
+    if (tid == 0) {
+        s_ncand = 0;
+        s_next = 0;
+        s_nout = 0;
+        s_te = 0;
+    }
+    if (tid < BG) s_cnt[tid] = 0;
+    __syncthreads();
+
+    const size_t gn = (size_t)g * p.n;
+    Mask128 *visited = p.visited + gn;
+    const PEntry *Pcur = bc_P(p, level) + gn;
+    PEntry *Pnext = bc_P(p, level + 1) + gn;
+    const uint32_t tag_cur = p.tagbase + level + 1, tag_next = tag_cur + 1;
+
+    // 1. this CTA's 256 vertices: compact the unfinished ones (sparse levels: only marked ones)
+    {
+        const uint32_t w = blockIdx.x * BLOCK + tid;
+        Mask128 unv = mask_zero();
+        bool look = w < p.n;
+        if (fcnt <= p.sparse_max) {
+            uint32_t *word = p.maybe + (size_t)g * p.mwords + (w >> 5);
+            const uint32_t bits = (w < p.n) ? *word : 0u;
+            look = (bits >> lane) & 1u;
+            __syncwarp();
+            if (lane == 0 && bits) *word = 0;
+        }
+        if (look) {
+            const Mask128 vis = mask_load(&visited[w]);
+#pragma unroll
+            for (int k = 0; k < BK; k++) unv.w[k] = ~vis.w[k];
+        }
+        const bool any = mask_any(unv);
+        const uint32_t bal = __ballot_sync(FULL, any);
+        uint32_t wbase = 0;
+        if (lane == 0 && bal) wbase = atomicAdd(&s_ncand, __popc(bal));
+        wbase = __shfl_sync(FULL, wbase, 0);
+        if (any) {
+            const uint32_t i = wbase + __popc(bal & lanemask_lt());
+            s_w[i] = w;
+            s_unv[i] = unv;
+        }
+    }
+    __syncthreads();
+    const uint32_t ncand = s_ncand;
+
+    // 2. warps take candidates dynamically
+    uint32_t cnt[BK] = {0, 0, 0, 0};
+    unsigned long long te = 0;
+    for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(&s_next, 1);
+        i = __shfl_sync(FULL, i, 0);
+        if (i >= ncand) break;
+        const uint32_t w = s_w[i];
+        const Mask128 unv = s_unv[i];
+        const uint32_t e0 = p.row[w], e1 = p.row[w + 1];
+        Mask128 newm = mask_zero();
+        for (uint32_t e = e0; e < e1; e += 32) {
+            const uint32_t idx = e + lane;
+            Mask128 m = mask_zero();
+            if (idx < e1) {
+                m = bc_level_mask(Pcur, p.col[idx], tag_cur);
+#pragma unroll
+                for (int k = 0; k < BK; k++) m.w[k] &= unv.w[k];
+            }
+            if (__any_sync(FULL, mask_any(m))) {
+#pragma unroll
+                for (int k = 0; k < BK; k++) newm.w[k] |= __reduce_or_sync(FULL, m.w[k]);
+                // every missing source found: the remaining arcs cannot add anything
+                if (newm.w[0] == unv.w[0] && newm.w[1] == unv.w[1] && newm.w[2] == unv.w[2] &&
+                    newm.w[3] == unv.w[3])
+                    break;
+            }
+        }
+        if (!mask_any(newm)) continue;
+#pragma unroll
+        for (int k = 0; k < BK; k++) {
+            const uint32_t bit = (newm.w[k] >> lane) & 1u;
+            cnt[k] += bit;
+            if (ROWS && bit) p.drows[((size_t)g * BG + 32 * k + lane) * p.n_cols + w] = (double)(level + 1);
+        }
+        if (lane == 0) {
+            Mask128 vis;
+#pragma unroll
+            for (int k = 0; k < BK; k++) vis.w[k] = ~unv.w[k] | newm.w[k];
+            mask_store(&visited[w], vis);
+            bc_store_level(Pnext, w, tag_next, newm);
+            s_ov[atomicAdd(&s_nout, 1u)] = w;
+            te += (unsigned long long)mask_popc(newm) * (p.srow[w + 1] - p.srow[w]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < BK; k++)
+        if (cnt[k]) atomicAdd(&s_cnt[32 * k + lane], cnt[k]);
+    if (lane == 0 && te) atomicAdd(&s_te, te);
+    __syncthreads();
+
+    // 3. queue the discovered vertices (the frontier-marking kernel of the next level reads them),
+    //    add this CTA's per-source counts
+    const uint32_t nout = s_nout;
+    if (tid == 0) {
+        const uint32_t base = lo[level] + fcnt;
+        if (blockIdx.x == 0) lo[level + 1] = base;
+        uint32_t pos = 0;
+        if (nout) {
+            pos = atomicAdd(&lc[level + 1], nout);
+            atomicAdd(&p.lvl_total[level + 1], nout);
+        }
+        s_base = base + pos;
+        if (s_te) atomicAdd(&p.stats[ST_TE], s_te);
+    }
+    __syncthreads();
+    if ((uint32_t)tid < nout) {
+        const uint64_t pos = (uint64_t)s_base + tid;
+        if (pos < p.qcap) p.qv[(size_t)g * p.qcap + pos] = s_ov[tid];
+        else atomicOr(p.overflow, 2u);
+    }
+    if (tid < BG && s_cnt[tid]) {
+        atomicAdd(&p.reach[(size_t)g * BG + tid], (unsigned long long)s_cnt[tid]);
+        atomicAdd(&p.dsum[(size_t)g * BG + tid], (unsigned long long)s_cnt[tid] * (level + 1));
+        atomicAdd(&p.stats[ST_V], (unsigned long long)s_cnt[tid]);
+    }
+}
+
+// the sources themselves: reached at distance 0 (closeness counts them, centrality.rs:1209)
+__global__ void __launch_bounds__(BLOCK) bfs128_sources_kernel(BcParams p, uint32_t ngroups, int rows) {
+    const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= ngroups * BG) return;
+    const uint32_t s = p.src[i];
+    p.dsum[i] = 0ull;
+    p.reach[i] = s != NO_SOURCE ? 1ull : 0ull;
+    if (s == NO_SOURCE) return;
+    if (rows) p.drows[(size_t)i * p.n_cols + s] = 0.0;
+    atomicAdd(&p.stats[ST_TE], (unsigned long long)(p.srow[s + 1] - p.srow[s]));
+    atomicAdd(&p.stats[ST_V], 1ull);
 }
 
 }  // namespace rxc

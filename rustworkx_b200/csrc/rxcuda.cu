@@ -1161,6 +1161,150 @@ static void bfs_run(rxc_graph *g, const DeviceCSR &csr, const std::vector<uint32
 }
 
 // ------------------------------------------------------------------------------------------------
+// distance-only BFS in the betweenness layout (bfs128_level_kernel): the shallow-graph regime
+// ------------------------------------------------------------------------------------------------
+// push: the adjacency the search expands along; pull: its transpose.  sources: distinct compact ids.
+static void bfs128_run(rxc_graph *g, const DeviceCSR &push, const DeviceCSR &pull,
+                       const std::vector<uint32_t> &sources, BfsMode mode, bool wf_improved,
+                       double null_value, double *out) {
+    const uint32_t n = g->host.n_live;
+    if (sources.empty() || n == 0) return;
+    const bool rows_mode = mode == BfsMode::Rows;
+    const uint64_t total_groups = (sources.size() + BG - 1) / BG;
+    const uint32_t lcap = n + 2;
+    uint64_t ng = bc_ws_ensure(g, total_groups);
+    if (rows_mode)  // keep one batch of rows under 4 GiB
+        ng = std::min<uint64_t>(ng, std::max<uint64_t>(1, (4ull << 30) / ((uint64_t)n * BG * 8)));
+    BcWorkspace &ws = g->bc_ws;
+    cudaStream_t st = g->stream;
+    DevBuf<unsigned long long> d_dsum;
+    DevBuf<double> d_vals, d_rows;
+    d_dsum.alloc((size_t)ng * BG);
+    d_vals.alloc((size_t)ng * BG * 2);
+    if (rows_mode) d_rows.alloc((size_t)ng * BG * n);
+
+    BcParams p{};
+    p.row = pull.row.p;
+    p.col = pull.col.p;
+    p.srow = push.row.p;
+    p.scol = push.col.p;
+    p.sc = ws.sc.p;
+    p.sig32 = ws.sig32.p;
+    p.overflow = ws.overflow.p;
+    p.P0 = ws.P0.p;
+    p.P1 = ws.P1.p;
+    p.visited = ws.visited.p;
+    p.qv = ws.qv.p;
+    p.qm = ws.qm.p;
+    p.loff = ws.loff.p;
+    p.lvlcnt = ws.lvlcnt.p;
+    p.lvl_total = ws.lvl_total.p;
+    p.reach = ws.reach.p;
+    p.dsum = d_dsum.p;
+    p.drows = rows_mode ? d_rows.p : nullptr;
+    p.n_cols = n;
+    p.stats = g->d_stats.p;
+    p.src = ws.src.p;
+    p.hubv = ws.hubv.p;
+    p.hubm = ws.hubm.p;
+    p.hubcnt = ws.hubcnt.p;
+    p.hubcap = HUB_CAP;
+    p.maybe = ws.maybe.p;
+    p.mwords = (n + 31) / 32;
+    p.sparse_max = (uint32_t)std::min<int64_t>(g_opt.bc_sparse_div > 0 ? n / g_opt.bc_sparse_div : 0, 0x7FFFFFFF);
+    p.hub_degree = 0x7FFFFFFF;
+    p.qcap = ws.qper * n;
+    p.n = n;
+    p.lcap = lcap;
+    uint32_t &tagbase = ws.tagbase;
+    uint32_t &clear_levels = ws.dirty_levels;
+
+    std::vector<uint32_t> h_src((size_t)ng * BG), h_totals;
+    const size_t vstride = mode == BfsMode::Sums ? 2 : 1;
+    std::vector<double> h_vals((size_t)ng * BG * 2);
+    const uint32_t vblocks = (n + BLOCK - 1) / BLOCK;
+
+    for (uint64_t g0 = 0; g0 < total_groups; g0 += ng) {
+        const uint32_t bg = (uint32_t)std::min<uint64_t>(ng, total_groups - g0);
+        std::fill(h_src.begin(), h_src.end(), NO_SOURCE);
+        const size_t s0 = (size_t)g0 * BG;
+        const size_t cnt = std::min(sources.size() - s0, (size_t)bg * BG);
+        std::copy(sources.begin() + s0, sources.begin() + s0 + cnt, h_src.begin());
+        if ((uint64_t)tagbase + lcap + 16 > 0xFFFFFFF0ull) {
+            RXC_CUDA(cudaMemsetAsync(ws.P0.p, 0, ws.P0.bytes(), st));
+            RXC_CUDA(cudaMemsetAsync(ws.P1.p, 0, ws.P1.bytes(), st));
+            tagbase = 0;
+        }
+        p.tagbase = tagbase;
+        p.ngroups = bg;
+        RXC_CUDA(cudaEventRecord(g->ev[0], st));
+        RXC_CUDA(cudaMemcpyAsync(ws.src.p, h_src.data(), (size_t)bg * BG * 4, cudaMemcpyHostToDevice, st));
+        RXC_CUDA(cudaMemset2DAsync(ws.lvlcnt.p, (size_t)lcap * 4, 0, (size_t)clear_levels * 4, ws.ng, st));
+        RXC_CUDA(cudaMemsetAsync(ws.lvl_total.p, 0, (size_t)clear_levels * 4, st));
+        RXC_CUDA(cudaMemsetAsync(ws.overflow.p, 0, 4, st));
+        if (rows_mode) {
+            const uint64_t len = (uint64_t)bg * BG * n;
+            const uint32_t fb = (uint32_t)std::min<uint64_t>((len + BLOCK - 1) / BLOCK, 148 * 16);
+            bfs_fill_f64_kernel<<<fb, BLOCK, 0, st>>>(d_rows.p, len, null_value);
+            g->stats.launches++;
+        }
+        bc_init_kernel<<<dim3(vblocks, bg), BLOCK, 0, st>>>(p);
+        bc_seed_kernel<true><<<bg, 32, 0, st>>>(p);
+        bfs128_sources_kernel<<<(bg * BG + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(p, bg, rows_mode ? 1 : 0);
+        g->stats.launches += 3;
+        uint32_t launched = 0;
+        const uint32_t L = run_levels(
+            g, ws.lvl_total.p, n,
+            [&](uint32_t level) {
+                if (p.sparse_max) bc_mark_kernel<<<dim3(MARK_CTAS, bg), BLOCK, 0, st>>>(p, level);
+                if (rows_mode) bfs128_level_kernel<true><<<dim3(vblocks, bg), BLOCK, 0, st>>>(p, level);
+                else bfs128_level_kernel<false><<<dim3(vblocks, bg), BLOCK, 0, st>>>(p, level);
+                launched++;
+            },
+            h_totals);
+        g->stats.launches += (p.sparse_max ? 2 : 1) * launched;
+        g->stats.levels += L;
+        clear_levels = std::min<uint32_t>(lcap, launched + 2);
+        uint32_t h_overflow = 0;
+        RXC_CUDA(cudaMemcpyAsync(&h_overflow, ws.overflow.p, 4, cudaMemcpyDeviceToHost, st));
+        if (mode == BfsMode::Sums) {
+            distance_sums_kernel<<<(bg * BG + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(ws.reach.p, d_dsum.p, bg * BG, d_vals.p);
+            g->stats.launches++;
+        } else if (!rows_mode) {
+            closeness_finalize_kernel<<<(bg * BG + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(
+                ws.reach.p, d_dsum.p, ws.src.p, bg * BG, wf_improved ? 1 : 0, (unsigned long long)n, d_vals.p);
+            g->stats.launches++;
+        }
+        RXC_CUDA(cudaEventRecord(g->ev[1], st));
+        RXC_CUDA(cudaStreamSynchronize(st));
+        tagbase += launched + 8;
+        if (h_overflow & 2) {  // a level queue outgrew its typical size (deep graph forced into this regime)
+            if (g->queue_wide) throw std::runtime_error("level queue overflow with worst-case queues");
+            g->queue_wide = true;
+            const std::vector<uint32_t> rest(sources.begin() + s0, sources.end());
+            g->stats.levels -= L;
+            bfs128_run(g, push, pull, rest, mode, wf_improved, null_value, out + s0 * (rows_mode ? (size_t)n : vstride));
+            return;
+        }
+        const double t0 = now_ms();
+        if (rows_mode) {
+            d2h_staged(pinned_for(g->device), out + s0 * n, d_rows.p, cnt * (size_t)n * 8, st);
+        } else {
+            RXC_CUDA(cudaMemcpyAsync(h_vals.data(), d_vals.p, cnt * 8 * vstride, cudaMemcpyDeviceToHost, st));
+            RXC_CUDA(cudaStreamSynchronize(st));
+            std::copy(h_vals.begin(), h_vals.begin() + cnt * vstride, out + s0 * vstride);
+        }
+        RXC_CUDA(cudaGetLastError());
+        g->stats.ms_d2h += now_ms() - t0;
+        float f = 0.f;
+        RXC_CUDA(cudaEventElapsedTime(&f, g->ev[0], g->ev[1]));
+        g->stats.ms_forward += f;
+        g->stats.batches++;
+        g->stats.sources += cnt;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // CTA-per-source BFS with the visited bitmap in shared memory (high-diameter graphs)
 // ------------------------------------------------------------------------------------------------
 // Shared-memory plan of the CTA-per-source kernel: the visited bitmap goes to shared memory when it
@@ -1310,17 +1454,19 @@ static void bfs_smem_run(rxc_graph *g, const DeviceCSR &csr, const uint32_t *sou
     }
 }
 
-// Pick the regime.  Bit-parallel words pay off when the frontiers of different sources coincide
-// (small-world graphs: a handful of levels); on lattices and other long, thin graphs every word
-// carries one or two sources and a level launch per BFS level is pure overhead.  A pilot of up to
-// eight sources spread over the list runs CTA-per-source (cheap: one CTA each) and reports its BFS
-// depth; deep graphs stay in that regime, shallow ones go bit-parallel.
-static void bfs_dispatch(rxc_graph *g, const DeviceCSR &csr, const std::vector<uint32_t> &sources,
-                         BfsMode mode, bool wf_improved, double null_value, double *out) {
+// the transpose of one of the handle's adjacencies (what a bottom-up level pulls over)
+static const DeviceCSR &transpose_of(rxc_graph *g, const DeviceCSR &csr) {
+    if (!g->host.directed) return csr;  // `out` holds both directions
+    if (&csr == &g->out) return g->in;
+    if (&csr == &g->in) return g->out;
+    return csr;  // the symmetrised structure is its own transpose
+}
+
+static void bfs_dispatch_distinct(rxc_graph *g, const DeviceCSR &csr, const std::vector<uint32_t> &sources,
+                                  BfsMode mode, bool wf_improved, double null_value, double *out) {
     const uint32_t n = g->host.n_live;
-    if (sources.empty() || n == 0) return;
     const size_t stride = mode == BfsMode::Rows ? (size_t)n : (mode == BfsMode::Sums ? 2 : 1);
-    int64_t regime = g_opt.bfs_mode;  // 0 auto, 1 bit-parallel, 2 CTA-per-source
+    int64_t regime = g_opt.bfs_mode;  // 0 auto, 1 32-source words top-down, 2 CTA-per-source, 3 128-source bottom-up
     if (regime == 0) {
         const size_t k = sources.size(), np = std::min<size_t>(8, k);
         std::vector<uint32_t> pilot(np);
@@ -1331,12 +1477,41 @@ static void bfs_dispatch(rxc_graph *g, const DeviceCSR &csr, const std::vector<u
         // the pilot's work is redone below with everything else: keep the counters exact
         RXC_CUDA(cudaMemsetAsync(g->d_stats.p, 0, g->d_stats.bytes(), g->stream));
         g->stats.sources -= np;
-        regime = depth > (uint32_t)g_opt.bfs_depth_switch ? 2 : 1;
+        // shallow graphs: the 128-source bottom-up kernel once there are enough sources to fill groups
+        regime = depth > (uint32_t)g_opt.bfs_depth_switch ? 2 : (sources.size() >= 64 ? 3 : 1);
     }
     if (regime == 2)
         bfs_smem_run(g, csr, sources.data(), sources.size(), mode, wf_improved, null_value, out);
+    else if (regime == 3)
+        bfs128_run(g, csr, transpose_of(g, csr), sources, mode, wf_improved, null_value, out);
     else
         bfs_run(g, csr, sources, mode, wf_improved, null_value, out);
+}
+
+// Pick the regime.  Bit-parallel words pay off when the frontiers of different sources coincide
+// (small-world graphs: a handful of levels); on lattices and other long, thin graphs every word
+// carries one or two sources and a level launch per BFS level is pure overhead.  A pilot of up to
+// eight sources spread over the list runs CTA-per-source (cheap: one CTA each) and reports its BFS
+// depth; deep graphs stay in that regime, shallow ones go bit-parallel.  A source listed twice is
+// computed once (the kernels seed one bit per vertex and group).
+static void bfs_dispatch(rxc_graph *g, const DeviceCSR &csr, const std::vector<uint32_t> &sources,
+                         BfsMode mode, bool wf_improved, double null_value, double *out) {
+    const uint32_t n = g->host.n_live;
+    if (sources.empty() || n == 0) return;
+    std::vector<uint32_t> uniq = sources;
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    if (uniq.size() == sources.size()) {
+        bfs_dispatch_distinct(g, csr, sources, mode, wf_improved, null_value, out);
+        return;
+    }
+    const size_t stride = mode == BfsMode::Rows ? (size_t)n : (mode == BfsMode::Sums ? 2 : 1);
+    std::vector<double> tmp(uniq.size() * stride);
+    bfs_dispatch_distinct(g, csr, uniq, mode, wf_improved, null_value, tmp.data());
+    for (size_t i = 0; i < sources.size(); i++) {
+        const size_t j = std::lower_bound(uniq.begin(), uniq.end(), sources[i]) - uniq.begin();
+        std::copy(tmp.begin() + j * stride, tmp.begin() + (j + 1) * stride, out + i * stride);
+    }
 }
 
 // group closeness: one multi-source BFS over incoming arcs (Reversed(&graph), centrality.rs:1875-1899);
@@ -2098,7 +2273,7 @@ int rxc_set_option(const char *name, int64_t value) {
     if (k == "bc_groups") g_opt.bc_groups = value;
     else if (k == "bfs_groups") g_opt.bfs_groups = value;
     else if (k == "hub_degree" && value > 0) g_opt.hub_degree = value;
-    else if (k == "bfs_mode" && value >= 0 && value <= 2) g_opt.bfs_mode = value;
+    else if (k == "bfs_mode" && value >= 0 && value <= 3) g_opt.bfs_mode = value;
     else if (k == "bfs_depth_switch" && value >= 0) g_opt.bfs_depth_switch = value;
     else if (k == "bfs_threads" && (value == 0 || value == 128 || value == 256 || value == 512 || value == 1024)) g_opt.bfs_threads = value;
     else if (k == "bc_sigma" && value >= 0 && value <= 2) g_opt.bc_sigma = value;

@@ -400,10 +400,11 @@ def test_networkx_golden_fixture(rx):
         assert np.array_equal(dm, np.array(case["distance_matrix"]))
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 def test_distance_regimes_agree_with_oracle(rx, oracle, mode):
-    """Both distance-only regimes (bit-parallel level launches, CTA-per-source in shared memory) are
-    forced in turn and must be bit-exact; auto mode picks between them with a pilot group."""
+    """The distance-only regimes (1: 32-source words top-down, 2: CTA-per-source in shared memory,
+    3: 128-source masks bottom-up) are forced in turn and must be bit-exact; auto mode picks between
+    them with a pilot group.  (The grid forces regime 3 through its level-queue overflow path.)"""
     from rustworkx_b200 import _lib
 
     _lib.set_option("bfs_mode", mode)
@@ -421,9 +422,19 @@ def test_distance_regimes_agree_with_oracle(rx, oracle, mode):
                 for und in (False, True):
                     assert np.array_equal(rx.digraph_distance_matrix(g, as_undirected=und, null_value=-1.0),
                                           og.distance_matrix(300, und, -1.0))
+                    assert rx.digraph_unweighted_average_shortest_path_length(g, as_undirected=und, disconnected=True) \
+                        == og.average_shortest_path_length(300, und, True)
             else:
                 assert np.array_equal(rx.graph_distance_matrix(g, null_value=math.nan),
                                       og.distance_matrix(300, True, math.nan), equal_nan=True)
+        # duplicates in a partial call are computed once and copied
+        g = random_graph(rx, True, 300, 900, 21, holes=4)
+        og = oracle_graph(oracle, g)
+        live = np.asarray(g.node_indices(), dtype=np.uint32)
+        src = np.concatenate([live[:150], live[:20], live[100:140]])
+        want, _ = og.closeness_partial(np.unique(src), True)
+        from rustworkx_b200 import device_snapshot
+        assert np.array_equal(device_snapshot(g).closeness_partial(src, True), want[src])
     finally:
         _lib.set_option("bfs_mode", 0)
 
