@@ -299,8 +299,8 @@ def run_b200(args):
     # ---- e2e: C-ABI with host buffers, snapshot + step + readback per step -----------------------
     e2e = None
     if not args.no_e2e:
-        e2e_steps = max(1, min(args.steps, 3))
-        for step in range(1):  # one warm-up
+        e2e_steps = max(1, args.steps)
+        for step in range(2):  # warm-up: the pinned staging slots and the pool's second workspace
             g2 = make_device_graph()
             g2.betweenness_partial(sources_for(step), False)
             g2.close()
