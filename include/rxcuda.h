@@ -163,7 +163,20 @@ void rxc_comm_destroy(void);
 
 /* ---- instrumentation --------------------------------------------------------------------------- */
 int rxc_get_stats(const rxc_graph *g, rxc_stats *out);
-/* Tunables (0 = library default): sources per batch for the centrality kernels. */
+/* Tunables (tests and A/B measurements; the defaults are the measured optimum):
+ *   bc_groups N        groups of 128 sources per betweenness batch (0: 16M / n_live, at most 64)
+ *   bc_sigma 0|1|2     sigma rows: 0 uint32 path counts with f64 fall-back on overflow, 1 f64, 2 uint32
+ *   bc_sparse_div N    forward levels with <= n/N queue entries use the frontier filter (0: off)
+ *   hub_degree N       vertices above N arcs are handled by a whole CTA (512)
+ *   bfs_mode 0|1|2|3   distance-only regime: 0 auto (pilot), 1 32-source words top-down,
+ *                      2 CTA-per-source in shared memory, 3 128-source masks bottom-up
+ *   bfs_depth_switch N auto: pilot BFS deeper than N levels -> regime 2 (48)
+ *   bfs_ell 0|1        regime 2: one uint4 per vertex when no vertex has more than 4 arcs (1)
+ *   bfs_threads N      regime 2: threads per CTA (0: 1024 for n >= 2^18, else 256)
+ *   bfs_groups N       regime 1: groups of 32 sources per batch (0: up to 4096)
+ *   device_csr 0|1     build the CSR on the device (1) or with the host counting sort (0)
+ *   mem_fraction_pct N share of free HBM the scratch may take (70)
+ * RXC_TRACE=1 in the environment prints the phases of a snapshot and scratch allocations to stderr. */
 int rxc_set_option(const char *name, int64_t value);
 
 /* ---- benchmark inputs (host-side restatement of the reference's seeded generators;

@@ -16,6 +16,12 @@
 // Every level appends its (vertex, mask) pairs to a per-group queue; the backward sweep replays the
 // queue levels in reverse and pulls from successors (no atomics on the f64 rows).
 //
+// Three users share this layout: betweenness proper (forward + backward), group betweenness (two
+// slots per source in one forward pass, end of this file) and the distance-only BFS of shallow
+// graphs (bfs128_level_kernel: the forward kernel without rows).  By default the forward pass keeps
+// sigma as exact uint32 path counts in 512-byte rows ("narrow sigma rows" below) and falls back to
+// the f64 rows described here when a count overflows.
+//
 // Why 128: ncu on the 32-source version showed ~40 issued instructions per gathered row and half
 // of all issue slots busy; with four sources per lane the per-arc look-up, shuffles and address
 // arithmetic are amortised over 4x the sources and every load carries 32 bytes per lane.
@@ -237,13 +243,12 @@ __device__ __forceinline__ Row4 row_load(const double *rows, uint32_t v, int lan
     return r;
 }
 
-// Staging area: every warp owns STAGE row slots of 1 KB in (dynamic) shared memory.  cp.async
-// (LDGSTS, 16-byte, L1-bypassing) fetches a lane's 32-byte sector into its own slice of the slot;
-// lanes none of whose four sources needs the arc zero-fill without touching memory.  A lane later
-// reads only bytes it copied itself, so cp.async.wait_all is the only synchronisation needed and
-// up to STAGE KB per warp are in flight without holding registers (32 warps/SM x 4 KB = 128 KB).
-// Measured on BA(1M,8), 1024 sources (GTEPS): STAGE 8 x 3 CTAs/SM 169, 4 x 4 176, 4 x 5 172, 4 x 6 162,
-// 2 x 6 165, 2 x 8 148 -- flat: the big launches sit at the random-sector DRAM ceiling (~5.4 TB/s).
+// Staging area: every warp owns STAGE row slots of 1 KB in (dynamic) shared memory and fills them
+// with cp.async (LDGSTS, 16-byte, L1-bypassing), so up to STAGE KB per warp are in flight without
+// holding registers (32 warps/SM x 4 KB = 128 KB); sectors none of whose four sources needs the arc
+// are not fetched.  Measured on BA(1M,8), 1024 sources, f64 rows (GTEPS): STAGE 8 x 3 CTAs/SM 169,
+// 4 x 4 176, 4 x 5 172, 4 x 6 162, 2 x 6 165, 2 x 8 148 with the first slot layout; the same ranking
+// with the conflict-free layout below (4 x 4: 204).
 #ifndef RXC_STAGE
 #define RXC_STAGE 4
 #endif
