@@ -15,8 +15,8 @@ accumulates a partial vector, and ONE NCCL reduce at the end of the timed region
                library's own stream, max over ranks).  TE = (source, arc) pairs traversed, counted
                once per source although Brandes sweeps each twice.
 * ``e2e``    : the same metric through the C-ABI with HOST buffers: every step re-snapshots the graph
-               from host edge arrays (H2D + device CSR build), runs the step and reads the partial
-               vector back (D2H); wall clock around the calls.
+               from edge arrays in pinned host memory (H2D + device CSR build), runs the step and
+               reads the partial vector back into pinned host memory (D2H); wall clock around the calls.
 * ``roofline``: algorithmic bytes of the dominant kernel / its CUDA-event time, against the measured
                HBM copy peak in MEASURED_PEAKS.json.
 * ``cpu_baseline``: the oracle port of the reference algorithm on the box's host cores (rank 0, N=1).
@@ -236,9 +236,18 @@ def run_b200(args):
         idx = np.arange(i, i + S) % n
         return np.ascontiguousarray(plan[idx])
 
+    # Host inputs live in page-locked memory (rxc_host_alloc), as a binding that assembles the edge
+    # arrays itself would hold them: the snapshot's H2D is then one DMA per array.  A graph from which
+    # no edge was removed passes edge_id = NULL ("the position in the list").
+    ids_are_positions = bool(snap.get("edge_id_is_position"))
+    host_in = {k: _lib.pinned_copy(snap[k]) for k in ("live_nodes", "edge_src", "edge_dst")}
+    host_in["edge_id"] = None if ids_are_positions else _lib.pinned_copy(snap["edge_id"])
+    host_out = _lib.pinned_empty(max(int(snap["n_bound"]), 1), np.float64)
+
     def make_device_graph():
-        return _lib.DeviceGraph(snap["n_bound"], snap["live_nodes"], snap["e_bound"], snap["edge_src"],
-                                snap["edge_dst"], snap["edge_id"], snap["directed"])
+        return _lib.DeviceGraph(snap["n_bound"], host_in["live_nodes"], snap["e_bound"],
+                                host_in["edge_src"], host_in["edge_dst"], host_in["edge_id"],
+                                snap["directed"])
 
     # multi-GPU: our own NCCL communicator for the single end-of-run reduce
     if world > 1:
@@ -302,16 +311,25 @@ def run_b200(args):
         e2e_steps = max(1, args.steps)
         for step in range(2):  # warm-up: the pinned staging slots and the pool's second workspace
             g2 = make_device_graph()
-            g2.betweenness_partial(sources_for(step), False)
+            g2.betweenness_partial(sources_for(step), False, out=host_out)
             g2.close()
         barrier()
         t0 = time.perf_counter()
         te_e2e = 0
+        phase = [0.0, 0.0, 0.0]  # wall clock of snapshot / call / free, summed over the steps
         for step in range(e2e_steps):
+            src_step = sources_for(args.warmup + step)
+            ta = time.perf_counter()
             g2 = make_device_graph()
-            g2.betweenness_partial(sources_for(args.warmup + step), False)
+            tb = time.perf_counter()
+            g2.betweenness_partial(src_step, False, out=host_out)
+            tc_ = time.perf_counter()
             te_e2e += g2.stats()["te"]
             g2.close()
+            td = time.perf_counter()
+            phase[0] += tb - ta
+            phase[1] += tc_ - tb
+            phase[2] += td - tc_
         barrier()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -321,10 +339,14 @@ def run_b200(args):
             tc = torch.tensor([float(te_e2e)], dtype=torch.float64, device="cuda")
             dist.all_reduce(tc, op=dist.ReduceOp.SUM)
             te_e2e = tc.item()
-        h2d = 4 * n + 12 * graph.num_edges() + 4 * S  # live nodes + (src, dst, id) per edge + sources
+        # live nodes + (src, dst[, id]) per edge + sources
+        h2d = 4 * n + (8 if ids_are_positions else 12) * graph.num_edges() + 4 * S
         e2e = {"value": te_e2e / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(8 * n), "steps": e2e_steps,
-               "includes": "H2D of the edge list + device CSR build + kernels + D2H partial vector"}
+               "ms_per_step": {"snapshot": 1e3 * phase[0] / e2e_steps, "call": 1e3 * phase[1] / e2e_steps,
+                               "free": 1e3 * phase[2] / e2e_steps, "total": 1e3 * dt / e2e_steps},
+               "includes": "H2D of the edge list from pinned host memory + device CSR build + kernels "
+                           "+ D2H of the partial vector into pinned host memory"}
 
     if rank != 0:
         if dist is not None:

@@ -72,10 +72,19 @@ int rxc_get_device(void);
  * shard the live sources over them, one host thread per device.  n = 0 returns to single-device. */
 int rxc_set_devices(const int *devices, int n);
 
+/* Page-locked host buffers.  Every host pointer of this API may be pageable (it is then staged
+ * through the library's own pinned slots, ~16 GB/s) or page-locked -- from rxc_host_alloc,
+ * cudaHostAlloc or cudaHostRegister -- in which case the DMA engine reads / writes it directly at
+ * PCIe speed.  A binding that owns its edge arrays (the snapshot of a StableGraph is assembled by
+ * the binding anyway) should assemble them in rxc_host_alloc memory. */
+int rxc_host_alloc(size_t bytes, void **out);
+void rxc_host_free(void *p);
+
 /* ---- snapshot: StableGraph -> compact int32 CSR/CSC in HBM ---------------------------------------
  * live_nodes[n_live]: ascending original indices of live nodes (PyGraph.node_indices()).
  * edge_src/edge_dst/edge_id[n_edges]: endpoints (original node indices) and original edge index of
- * every live edge (PyGraph.edge_list() / edge_indices()).  Parallel edges are kept (path
+ * every live edge (PyGraph.edge_list() / edge_indices()); edge_id == NULL means "the position in the
+ * list" (a graph from which no edge was ever removed) and saves a third of the copy.  Parallel edges are kept (path
  * multiplicity, centrality.rs:433-436); self-loops are dropped (no effect on BFS).  The snapshot is
  * a copy: the caller's graph may change afterwards. */
 int rxc_graph_snapshot(uint32_t n_bound, const uint32_t *live_nodes, uint32_t n_live,

@@ -63,6 +63,8 @@ SYMBOLS = {
     "rxc_graph_snapshot": (C.c_int, [C.c_uint32, _u32p, C.c_uint32, C.c_uint32, _u32p, _u32p, _u32p,
                                      C.c_uint64, C.c_int, C.POINTER(_vp)]),
     "rxc_graph_free": (None, [_vp]),
+    "rxc_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
+    "rxc_host_free": (None, [_vp]),
     "rxc_graph_info": (C.c_int, [_vp, _u32p, _u32p, _u32p, C.POINTER(C.c_uint64),
                                  C.POINTER(C.c_int)]),
     "rxc_betweenness": (C.c_int, [_vp, C.c_int, C.c_int, _f64p]),
@@ -147,6 +149,43 @@ def device_count():
     return int(lib().rxc_device_count())
 
 
+class _PinnedBlock:
+    """Owner of one ``rxc_host_alloc`` block; arrays made by :func:`pinned_empty` keep it alive."""
+
+    def __init__(self, nbytes):
+        self.ptr = _vp()
+        check(lib().rxc_host_alloc(int(nbytes), C.byref(self.ptr)))
+        self.nbytes = int(nbytes)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().rxc_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """numpy array in page-locked host memory (``rxc_host_alloc``): the library copies such buffers
+    by direct DMA instead of staging them through its own pinned slots."""
+    dtype = np.dtype(dtype)
+    shape = (int(shape),) if np.isscalar(shape) else tuple(int(x) for x in shape)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    block = _PinnedBlock(max(nbytes, 1))
+    buf = (C.c_char * max(nbytes, 1)).from_address(block.ptr.value)
+    buf._rxc_owner = block  # the ctypes buffer is the array's base: ties the block's lifetime to it
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+
+
+def pinned_copy(a):
+    """Copy of ``a`` in page-locked host memory."""
+    a = np.ascontiguousarray(a)
+    out = pinned_empty(a.shape, a.dtype)
+    out[...] = a
+    return out
+
+
 def set_device(device):
     check(lib().rxc_set_device(int(device)))
 
@@ -169,20 +208,31 @@ class DeviceGraph:
     """An ``rxc_graph*``: the StableGraph snapshot as compact CSR/CSC resident in HBM."""
 
     def __init__(self, n_bound, live_nodes, e_bound, edge_src, edge_dst, edge_id, directed):
+        """``edge_id=None``: the edge index is the position in the list (no edge was ever removed);
+        the C-ABI then gets NULL and nothing is copied for it."""
         L = lib()
         self.live_nodes = np.ascontiguousarray(live_nodes, dtype=np.uint32)
-        self.edge_id = np.ascontiguousarray(edge_id, dtype=np.uint32)
         src = np.ascontiguousarray(edge_src, dtype=np.uint32)
         dst = np.ascontiguousarray(edge_dst, dtype=np.uint32)
+        self._edge_id = None if edge_id is None else np.ascontiguousarray(edge_id, dtype=np.uint32)
+        self._n_edges = int(src.shape[0])
         self.n_bound = int(n_bound)
         self.e_bound = int(e_bound)
         self.n_live = int(self.live_nodes.shape[0])
         self.directed = bool(directed)
         h = _vp()
         check(L.rxc_graph_snapshot(self.n_bound, p_u32(self.live_nodes), self.n_live, self.e_bound,
-                                   p_u32(src), p_u32(dst), p_u32(self.edge_id), src.shape[0],
-                                   1 if directed else 0, C.byref(h)))
+                                   p_u32(src), p_u32(dst),
+                                   None if self._edge_id is None else p_u32(self._edge_id),
+                                   src.shape[0], 1 if directed else 0, C.byref(h)))
         self._h = h
+
+    @property
+    def edge_id(self):
+        """original edge index of every listed edge"""
+        if self._edge_id is None:
+            self._edge_id = np.arange(self._n_edges, dtype=np.uint32)
+        return self._edge_id
 
     @classmethod
     def from_graph(cls, graph):
@@ -191,7 +241,7 @@ class DeviceGraph:
         if hasattr(graph, "_snapshot_arrays"):
             s = graph._snapshot_arrays()
             return cls(s["n_bound"], s["live_nodes"], s["e_bound"], s["edge_src"], s["edge_dst"],
-                       s["edge_id"], s["directed"])
+                       None if s.get("edge_id_is_position") else s["edge_id"], s["directed"])
         nodes = np.asarray(graph.node_indices(), dtype=np.uint32)
         eids = np.asarray(graph.edge_indices(), dtype=np.uint32)
         el = np.asarray(graph.edge_list(), dtype=np.uint32).reshape(-1, 2)
@@ -294,9 +344,13 @@ class DeviceGraph:
         return out
 
     # ---- partial calls (source shards; un-rescaled) ---------------------------------------------
-    def betweenness_partial(self, sources, include_endpoints=False):
+    def betweenness_partial(self, sources, include_endpoints=False, out=None):
+        """``out``: optional caller buffer of at least n_bound doubles (e.g. ``pinned_empty``)."""
         src = np.ascontiguousarray(sources, dtype=np.uint32)
-        out = np.zeros(max(self.n_bound, 1), dtype=np.float64)
+        if out is None:
+            out = np.zeros(max(self.n_bound, 1), dtype=np.float64)
+        elif out.dtype != np.float64 or not out.flags.c_contiguous or out.size < self.n_bound:
+            raise ValueError("out must be a C-contiguous float64 array of at least n_bound elements")
         check(lib().rxc_betweenness_partial(self._h, p_u32(src), src.shape[0],
                                             int(include_endpoints), p_f64(out)))
         return out[: self.n_bound]

@@ -175,18 +175,50 @@ __global__ void __launch_bounds__(BLOCK)
 }
 
 // Restore a deterministic arc order inside every row: ascending (original edge id, target).
-// One warp per row; rows of up to 32 arcs are ranked in registers, longer rows are queued for the
-// CTA-per-row bitonic sort below.
+// One warp per row: rows of up to 32 arcs are ranked in registers, rows of up to CSR_SORT_MID arcs
+// are sorted by the warp in shared memory (BA(10^6,8) has 60 000 rows of 33..256 arcs: sending them
+// all to the CTA-per-row kernel below made it 2.4 ms of a 5 ms snapshot), longer rows are queued for
+// the CTA-per-row bitonic sort.
+constexpr uint32_t CSR_SORT_MID = 256;
 __global__ void __launch_bounds__(BLOCK)
     csr_sort_rows_kernel(const uint32_t *row, uint32_t n, uint32_t *col, uint32_t *arc_eid,
                          uint32_t *long_rows, uint32_t *n_long) {
+    __shared__ unsigned long long s_mid[WARPS][CSR_SORT_MID];
     const uint32_t r = blockIdx.x * WARPS + (threadIdx.x >> 5);
     if (r >= n) return;
     const int lane = lane_id();
     const uint32_t e0 = row[r], e1 = row[r + 1], deg = e1 - e0;
     if (deg <= 1) return;
-    if (deg > 32) {
+    if (deg > CSR_SORT_MID) {
         if (lane == 0) long_rows[atomicAdd(n_long, 1u)] = r;
+        return;
+    }
+    if (deg > 32) {
+        unsigned long long *s = s_mid[threadIdx.x >> 5];
+        uint32_t N = 64;
+        while (N < deg) N <<= 1;
+        for (uint32_t i = lane; i < N; i += 32)
+            s[i] = i < deg ? (((unsigned long long)arc_eid[e0 + i] << 32) | col[e0 + i]) : ~0ull;
+        __syncwarp();
+        for (uint32_t k = 2; k <= N; k <<= 1) {
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                for (uint32_t i = lane; i < N; i += 32) {
+                    const uint32_t ixj = i ^ j;
+                    if (ixj > i) {
+                        const unsigned long long a = s[i], b = s[ixj];
+                        if ((a > b) == ((i & k) == 0)) {
+                            s[i] = b;
+                            s[ixj] = a;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        for (uint32_t i = lane; i < deg; i += 32) {
+            col[e0 + i] = (uint32_t)s[i];
+            arc_eid[e0 + i] = (uint32_t)(s[i] >> 32);
+        }
         return;
     }
     const bool ok = (uint32_t)lane < deg;
@@ -204,11 +236,18 @@ __global__ void __launch_bounds__(BLOCK)
     }
 }
 
+// edge_id == NULL in rxc_graph_snapshot: the edge index is the position in the list
+__global__ void __launch_bounds__(BLOCK) csr_iota_kernel(uint32_t *out, uint64_t len) {
+    for (uint64_t i = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; i < len; i += (uint64_t)gridDim.x * BLOCK)
+        out[i] = (uint32_t)i;
+}
+
 constexpr uint32_t CSR_SORT_MAX = 16384;  // keys a CTA sorts in shared memory (128 KB)
 
 // Bitonic sort of one long row per CTA in shared memory.  Rows beyond CSR_SORT_MAX arcs keep the
 // scatter order (their f64 sums are then order-nondeterministic, within the 1e-9 bar).
-__global__ void __launch_bounds__(BLOCK)
+constexpr uint32_t CSR_SORT_THREADS = 1024;  // 128 KB of keys: one CTA per SM, so make it a full one
+__global__ void __launch_bounds__(CSR_SORT_THREADS)
     csr_sort_long_kernel(const uint32_t *row, const uint32_t *long_rows, const uint32_t *n_long,
                          uint32_t *col, uint32_t *arc_eid) {
     extern __shared__ unsigned long long s_keys[];
@@ -219,12 +258,12 @@ __global__ void __launch_bounds__(BLOCK)
         if (deg > CSR_SORT_MAX) continue;
         uint32_t N = 64;
         while (N < deg) N <<= 1;
-        for (uint32_t i = threadIdx.x; i < N; i += BLOCK)
+        for (uint32_t i = threadIdx.x; i < N; i += CSR_SORT_THREADS)
             s_keys[i] = i < deg ? (((unsigned long long)arc_eid[e0 + i] << 32) | col[e0 + i]) : ~0ull;
         __syncthreads();
         for (uint32_t k = 2; k <= N; k <<= 1) {
             for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-                for (uint32_t i = threadIdx.x; i < N; i += BLOCK) {
+                for (uint32_t i = threadIdx.x; i < N; i += CSR_SORT_THREADS) {
                     const uint32_t ixj = i ^ j;
                     if (ixj > i) {
                         const unsigned long long a = s_keys[i], b = s_keys[ixj];
@@ -238,7 +277,7 @@ __global__ void __launch_bounds__(BLOCK)
                 __syncthreads();
             }
         }
-        for (uint32_t i = threadIdx.x; i < deg; i += BLOCK) {
+        for (uint32_t i = threadIdx.x; i < deg; i += CSR_SORT_THREADS) {
             col[e0 + i] = (uint32_t)s_keys[i];
             arc_eid[e0 + i] = (uint32_t)(s_keys[i] >> 32);
         }

@@ -203,13 +203,24 @@ static void host_copy_parallel(char *dst, const char *src, size_t bytes) {
     for (auto &x : th) x.join();
 }
 
-// dst: pageable host memory; src: device memory; everything queued on `st` before the call is
-// complete when it returns
+// Page-locked caller buffers (rxc_host_alloc, cudaHostAlloc, cudaHostRegister) are DMA targets
+// themselves: no staging, the copy runs at PCIe speed.
+static bool host_is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// dst: host memory; src: device memory; everything queued on `st` before the call is complete when
+// it returns
 static void d2h_staged(PinnedStage &ps, void *dst, const void *src, size_t bytes, cudaStream_t st) {
     int dev = 0;
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lock(pinned_slot(dev).mu);
-    if (bytes < (4u << 20)) {
+    if (bytes < (4u << 20) || host_is_pinned(dst)) {
         RXC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
         RXC_CUDA(cudaStreamSynchronize(st));
         return;
@@ -232,12 +243,18 @@ static void d2h_staged(PinnedStage &ps, void *dst, const void *src, size_t bytes
     RXC_CUDA(cudaStreamSynchronize(st));
 }
 
-// src: pageable host memory; dst: device memory.  Returns with every copy queued on `st`; the
-// staging slots are reused only after their DMA has completed (events), so the caller's buffer may
-// be released as soon as this returns.
+// src: host memory; dst: device memory.  Pageable sources: returns with every copy queued on `st`;
+// the staging slots are reused only after their DMA has completed (events), so the caller's buffer
+// may be released as soon as this returns.  Page-locked sources are copied straight from the
+// caller's buffer and only QUEUED: the caller must synchronise `st` before handing the buffer back
+// (rxc_graph_snapshot does, at the end of the build).
 static void h2d_staged(PinnedStage &ps, void *dst, const void *src, size_t bytes, cudaStream_t st) {
     int dev = 0;
     cudaGetDevice(&dev);
+    if (host_is_pinned(src)) {
+        RXC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        return;
+    }
     std::lock_guard<std::mutex> lock(pinned_slot(dev).mu);
     if (bytes < (4u << 20)) {
         RXC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
@@ -390,7 +407,7 @@ static void device_sort_rows(DeviceCSR &csr, uint32_t n, DevBuf<uint32_t> &long_
     RXC_CUDA(cudaMemsetAsync(d_nlong, 0, 4, st));
     csr_sort_rows_kernel<<<(n + WARPS - 1) / WARPS, BLOCK, 0, st>>>(csr.row.p, n, csr.col.p, csr.eid.p,
                                                                    long_rows.p, d_nlong);
-    csr_sort_long_kernel<<<296, BLOCK, CSR_SORT_MAX * 8, st>>>(csr.row.p, long_rows.p, d_nlong,
+    csr_sort_long_kernel<<<148, CSR_SORT_THREADS, CSR_SORT_MAX * 8, st>>>(csr.row.p, long_rows.p, d_nlong,
                                                               csr.col.p, csr.eid.p);
 }
 
@@ -430,22 +447,8 @@ static void device_snapshot(rxc_graph *g, uint32_t n_bound, const uint32_t *live
     h.e_bound = e_bound;
     h.n_edges = n_edges;
     h.directed = directed;
-    for (uint32_t i = 0; i < n_live; i++) {
-        const uint32_t o = live_nodes[i];
-        if (o >= n_bound) throw std::invalid_argument("live node index >= n_bound");
-        if (i > 0 && live_nodes[i - 1] >= o)
-            throw std::invalid_argument("live_nodes must be strictly ascending");
-    }
-    // strictly ascending, below n_bound, n_bound of them: the identity -- no host maps needed
-    h.identity = n_live == n_bound;
-    if (!h.identity) {
-        h.orig_of_compact.assign(live_nodes, live_nodes + n_live);
-        h.compact_of_orig.assign(n_bound, 0xFFFFFFFFu);
-        for (uint32_t i = 0; i < n_live; i++) h.compact_of_orig[live_nodes[i]] = i;
-    }
     if ((directed ? n_edges : 2 * n_edges) >= 0xFFFFFFFFull)
         throw LimitError("more than 2^32-2 arcs are not supported");
-    tp("host maps");
     cudaStream_t st = g->stream;
     const uint32_t n = n_live;
     DevBuf<uint32_t> d_live, d_cmap, d_eid, d_deg_a, d_deg_b, cursor, tiles, d_small, long_rows;
@@ -470,14 +473,28 @@ static void device_snapshot(rxc_graph *g, uint32_t n_bound, const uint32_t *live
         h2d_staged(pinned_for(g->device), d_dst.p, edst, n_edges * 4, st);
         if (eid) {
             h2d_staged(pinned_for(g->device), d_eid.p, eid, n_edges * 4, st);
-        } else {  // edge ids default to the position in the list
-            std::vector<uint32_t> iota(n_edges);
-            for (uint64_t i = 0; i < n_edges; i++) iota[i] = (uint32_t)i;
-            RXC_CUDA(cudaMemcpyAsync(d_eid.p, iota.data(), n_edges * 4, cudaMemcpyHostToDevice, st));
-            RXC_CUDA(cudaStreamSynchronize(st));
+        } else {  // edge ids default to the position in the list: nothing to copy
+            const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_edges + BLOCK - 1) / BLOCK, 148 * 32);
+            csr_iota_kernel<<<blocks, BLOCK, 0, st>>>(d_eid.p, n_edges);
         }
     }
     tp("h2d");
+    // host-side checks and index maps, while the DMA engine works on the copies queued above
+    bool ascending = true, in_range = true;
+    for (uint32_t i = 0; i < n_live; i++) {
+        in_range &= live_nodes[i] < n_bound;
+        ascending &= i == 0 || live_nodes[i - 1] < live_nodes[i];
+    }
+    if (!in_range) throw std::invalid_argument("live node index >= n_bound");
+    if (!ascending) throw std::invalid_argument("live_nodes must be strictly ascending");
+    // strictly ascending, below n_bound, n_bound of them: the identity -- no host maps needed
+    h.identity = n_live == n_bound;
+    if (!h.identity) {
+        h.orig_of_compact.assign(live_nodes, live_nodes + n_live);
+        h.compact_of_orig.assign(n_bound, 0xFFFFFFFFu);
+        for (uint32_t i = 0; i < n_live; i++) h.compact_of_orig[live_nodes[i]] = i;
+    }
+    tp("host maps");
     RXC_CUDA(cudaMemsetAsync(d_cmap.p, 0xFF, d_cmap.bytes(), st));
     RXC_CUDA(cudaMemsetAsync(d_deg_a.p, 0, d_deg_a.bytes(), st));
     if (directed) RXC_CUDA(cudaMemsetAsync(d_deg_b.p, 0, d_deg_b.bytes(), st));
@@ -556,6 +573,15 @@ static void fetch_stats(rxc_graph *g) {
 static std::vector<std::vector<uint32_t>> distinct_rounds(const std::vector<uint32_t> &src,
                                                           uint32_t n) {
     std::vector<std::vector<uint32_t>> rounds;
+    if (src.empty()) return rounds;
+    if (src.size() <= n / 16) {  // short list: a sort is cheaper than touching an n-sized table
+        std::vector<uint32_t> sorted(src);
+        std::sort(sorted.begin(), sorted.end());
+        if (std::adjacent_find(sorted.begin(), sorted.end()) == sorted.end()) {
+            rounds.push_back(src);
+            return rounds;
+        }
+    }
     std::vector<uint32_t> seen(n, 0);
     for (uint32_t s : src) {
         const uint32_t r = seen[s]++;
@@ -1982,6 +2008,26 @@ int rxc_graph_snapshot(uint32_t n_bound, const uint32_t *live_nodes, uint32_t n_
 }
 
 void rxc_graph_free(rxc_graph *g) { delete g; }
+
+int rxc_host_alloc(size_t bytes, void **out) {
+    if (!out) return RXC_ERR_INVALID;
+    *out = nullptr;
+    return guarded([&] {
+        require_device();
+        void *p = nullptr;
+        const cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
+        if (e == cudaErrorMemoryAllocation) {
+            cudaGetLastError();
+            throw std::bad_alloc();
+        }
+        RXC_CUDA(e);
+        *out = p;
+    });
+}
+
+void rxc_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
 
 int rxc_graph_info(const rxc_graph *g, uint32_t *n_bound, uint32_t *n_live, uint32_t *e_bound,
                    uint64_t *n_arcs, int *directed) {

@@ -417,6 +417,8 @@ class _StableGraph:
             "edge_src": np.ascontiguousarray(self._esrc[live_edges]),
             "edge_dst": np.ascontiguousarray(self._edst[live_edges]),
             "edge_id": live_edges,
+            # no edge slot was ever vacated: the edge index is the position in the list
+            "edge_id_is_position": bool(live_edges.size == self._elen),
             "edge_seq": np.ascontiguousarray(self._eseq[live_edges]),
             "directed": self._directed,
         }

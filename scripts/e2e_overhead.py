@@ -8,12 +8,18 @@ n = 1_000_000; S = 1024
 g = rx.barabasi_albert_graph(n, 8, seed=1)
 snap = g._snapshot_arrays()
 plan = np.random.default_rng(1).permutation(n).astype(np.uint32)
+PINNED = os.environ.get("PINNED", "0") == "1"   # inputs / output in rxc_host_alloc memory
+NOIDS = os.environ.get("NOIDS", "0") == "1"     # edge_id = NULL (the position in the list)
+arr = {k: (_lib.pinned_copy(snap[k]) if PINNED else snap[k]) for k in ("live_nodes", "edge_src", "edge_dst", "edge_id")}
+if NOIDS:
+    arr["edge_id"] = None
+buf = _lib.pinned_empty(n, np.float64) if PINNED else None
 for i in range(6):
     t0 = time.perf_counter()
-    dg = _lib.DeviceGraph(snap["n_bound"], snap["live_nodes"], snap["e_bound"], snap["edge_src"],
-                          snap["edge_dst"], snap["edge_id"], snap["directed"])
+    dg = _lib.DeviceGraph(snap["n_bound"], arr["live_nodes"], snap["e_bound"], arr["edge_src"],
+                          arr["edge_dst"], arr["edge_id"], snap["directed"])
     t1 = time.perf_counter()
-    out = dg.betweenness_partial(plan[i * S:(i + 1) * S], False)
+    out = dg.betweenness_partial(plan[i * S:(i + 1) * S], False, out=buf)
     t2 = time.perf_counter()
     st = dg.stats()
     dg.close()
