@@ -469,6 +469,41 @@ def test_device_and_host_csr_builders_agree(rx, oracle):
                          np.array([3], np.uint32), np.array([0], np.uint32), False)
 
 
+def test_pinned_host_buffers_and_positional_edge_ids(rx, oracle):
+    """rxc_host_alloc memory is copied by direct DMA (no staging) and edge_id = NULL means "the
+    position in the list": both must give what pageable buffers with explicit ids give, and the
+    oracle's numbers."""
+    from rustworkx_b200 import _lib
+
+    g = rx.barabasi_albert_graph(20000, 5, seed=11)
+    s = g._snapshot_arrays()
+    assert s["edge_id_is_position"]
+    src = np.arange(0, 20000, 157, dtype=np.uint32)
+    plain = _lib.DeviceGraph(s["n_bound"], s["live_nodes"], s["e_bound"], s["edge_src"], s["edge_dst"],
+                             s["edge_id"], s["directed"])
+    pinned = _lib.DeviceGraph(s["n_bound"], _lib.pinned_copy(s["live_nodes"]), s["e_bound"],
+                              _lib.pinned_copy(s["edge_src"]), _lib.pinned_copy(s["edge_dst"]), None,
+                              s["directed"])
+    assert np.array_equal(pinned.edge_id, s["edge_id"])
+    out = _lib.pinned_empty(s["n_bound"], np.float64)
+    out[:] = -1.0
+    got = pinned.betweenness_partial(src, False, out=out)
+    assert got.base is not None and np.shares_memory(got, out)
+    assert_close(got, plain.betweenness_partial(src, False))
+    assert_close(pinned.edge_betweenness_partial(src), plain.edge_betweenness_partial(src))
+    assert np.array_equal(pinned.closeness(True), plain.closeness(True))
+    og = oracle.OracleGraph.from_graph(g)
+    want, _ = og.closeness_centrality(True, 50, as_arrays=True)
+    assert np.array_equal(pinned.closeness(True), want)
+    # a graph that lost an edge keeps explicit ids
+    g.remove_edge_from_index(3)
+    assert not g._snapshot_arrays()["edge_id_is_position"]
+    with pytest.raises(ValueError):
+        pinned.betweenness_partial(src, False, out=np.zeros(5))
+    plain.close()
+    pinned.close()
+
+
 def test_full_size_invariant_ba_1m(rx):
     """BASELINE.json configs[2] at full size (BA(10^6, 8)): size-independent property instead of the
     oracle.  Every shortest s-t path of length d has d-1 interior vertices whose pair-dependencies
