@@ -198,7 +198,7 @@ def run_reference(args):
         "note": "reference Rust crate cannot be built here (no cargo/rustc); this is oracle/ (C "
                 "restatement, OpenMP over sources, one global lock as in centrality.rs:107,280)",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -413,13 +413,32 @@ def run_b200(args):
         "work": {"te": te_all, "te_dag": dag_all, "v": v_all, "levels": agg["levels"],
                  "batches": agg["batches"], "wall_ms": wall_ms_max, "reduce_ms": reduce_ms},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
     args = parse_args()
+    # Libraries print to stdout behind our back (NCCL's "NCCL version ..." banner on rank 0): keep the
+    # real stdout for the JSON line and send everything else written to fd 1 to stderr.
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
