@@ -935,6 +935,24 @@ __global__ void __launch_bounds__(BLOCK) bc_backward_hub_kernel(BcParams p, uint
     }
 }
 
+// Ordering key of a source: the size of its two-hop neighbourhood along the expansion direction,
+// sum of deg(w) over its arcs (s,w).  On BA(200k,8) it correlates -0.985 with the mean BFS distance
+// of the source, i.e. with WHEN its search reaches the bulk of the graph (rxcuda.cu, bc_order_sources).
+__global__ void __launch_bounds__(BLOCK)
+    bc_source_keys_kernel(const uint32_t *row, const uint32_t *col, const uint32_t *src, uint32_t k,
+                          unsigned long long *keys) {
+    const uint32_t i = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (i >= k) return;
+    const uint32_t s = src[i];
+    unsigned long long sum = 0;
+    for (uint32_t e = row[s] + lane_id(); e < row[s + 1]; e += 32) {
+        const uint32_t w = col[e];
+        sum += row[w + 1] - row[w];
+    }
+    sum = warp_sum_u64(sum);
+    if (lane_id() == 0) keys[i] = sum;
+}
+
 // endpoints: the source itself receives |S| - 1 (centrality.rs:282-284)
 __global__ void __launch_bounds__(BLOCK) bc_endpoint_sources_kernel(BcParams p, uint32_t ngroups) {
     const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;

@@ -117,6 +117,7 @@ struct Options {
     int64_t bc_sigma = 0;           // betweenness sigma rows: 0 auto (uint32, f64 on overflow), 1 f64, 2 uint32
     int64_t bfs_threads = 0;        // CTA-per-source BFS: threads per CTA (0: 1024 for n >= 2^18, else 256)
     int64_t bfs_ell = 1;            // CTA-per-source BFS: ELL adjacency when every vertex has <= 4 arcs
+    int64_t bc_order = 1;           // betweenness: group sources of similar two-hop neighbourhood size
 };
 static Options g_opt;
 constexpr uint32_t HUB_CAP = 4096;  // deferred high-degree work items per group and level
@@ -712,6 +713,40 @@ static uint64_t bc_ws_ensure(rxc_graph *g, uint64_t total_groups) {
     return std::min<uint64_t>(ng, ws.ng);
 }
 
+// Which sources share a group -- and, inside a group, a DRAM sector -- is free: contributions are
+// additive over sources.  A row gather moves the sectors in which ANY of a lane's four sources needs
+// the arc, and a vertex enters a group's level queue once per DISTINCT level it has among the 128
+// sources, so sources whose searches reach the bulk of the graph at the same level cost fewer
+// gathered rows, fewer queue entries and fewer bytes per useful value.  The sources are therefore
+// sorted by the size of their two-hop neighbourhood (bc_source_keys_kernel; a proxy for the mean BFS
+// distance, correlation -0.985 on BA graphs); consecutive sources of the sorted list become the four
+// sources of one lane (run_batch).  Simulated on BA(200k,8), 512 random sources: 14 % fewer gathered
+// rows, 9 % fewer bytes per useful value in the dependency sweep, 12 % in the forward pass.
+static std::vector<uint32_t> bc_order_sources(rxc_graph *g, const std::vector<uint32_t> &sources) {
+    const size_t k = sources.size();
+    if (!g_opt.bc_order || k <= (size_t)BK) return sources;
+    cudaStream_t st = g->stream;
+    DevBuf<uint32_t> d_src;
+    DevBuf<unsigned long long> d_keys;
+    d_src.alloc(k);
+    d_keys.alloc(k);
+    RXC_CUDA(cudaMemcpyAsync(d_src.p, sources.data(), k * 4, cudaMemcpyHostToDevice, st));
+    bc_source_keys_kernel<<<(uint32_t)((k + WARPS - 1) / WARPS), BLOCK, 0, st>>>(
+        g->succ().row.p, g->succ().col.p, d_src.p, (uint32_t)k, d_keys.p);
+    g->stats.launches++;
+    std::vector<unsigned long long> keys(k);
+    RXC_CUDA(cudaMemcpyAsync(keys.data(), d_keys.p, k * 8, cudaMemcpyDeviceToHost, st));
+    RXC_CUDA(cudaStreamSynchronize(st));
+    std::vector<uint32_t> idx(k);
+    for (size_t i = 0; i < k; i++) idx[i] = (uint32_t)i;
+    std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {
+        return keys[a] != keys[b] ? keys[a] > keys[b] : sources[a] < sources[b];
+    });
+    std::vector<uint32_t> out(k);
+    for (size_t i = 0; i < k; i++) out[i] = sources[idx[i]];
+    return out;
+}
+
 // Group betweenness (bc_kernels.cuh, "pair mode"): the group's vertices on the device.
 struct GroupSpec {
     const uint32_t *d_members;  // compact ids, distinct
@@ -719,11 +754,13 @@ struct GroupSpec {
     const uint32_t *d_blocked;  // bitmap over compact ids
 };
 
-static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endpoints,
+static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources_in, bool endpoints,
                    bool edge_mode, double *d_acc, const GroupSpec *grp = nullptr) {
     bc_enable_smem();
     const uint32_t n = g->host.n_live;
-    if (sources.empty() || n == 0) return;
+    if (sources_in.empty() || n == 0) return;
+    // pair mode keeps the caller's order (its slot layout is fixed by the pairing)
+    const std::vector<uint32_t> sources = grp ? sources_in : bc_order_sources(g, sources_in);
     const uint32_t per = grp ? BGP : BG;  // sources per group (pair mode: two slots per source)
     const uint64_t total_groups = (sources.size() + per - 1) / per;
     const uint32_t lcap = n + 2;
@@ -776,7 +813,9 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources, bool endp
         const size_t s0 = (size_t)g0 * per;
         const size_t cnt = std::min(sources.size() - s0, (size_t)bg * per);
         if (!grp) {
-            std::copy(sources.begin() + s0, sources.begin() + s0 + cnt, h_src.begin());
+            // slot 32k + l is source k of lane l: consecutive (similar) sources share a lane's sector
+            for (size_t i = 0; i < cnt; i++)
+                h_src[(i / BG) * BG + (i % BK) * 32 + (i % BG) / BK] = sources[s0 + i];
         } else {  // slot j and slot 64+j of a group carry the same source
             for (size_t i = 0; i < cnt; i++) {
                 const size_t slot = (i / BGP) * BG + i % BGP;
@@ -2320,6 +2359,7 @@ int rxc_set_option(const char *name, int64_t value) {
     else if (k == "bfs_groups") g_opt.bfs_groups = value;
     else if (k == "hub_degree" && value > 0) g_opt.hub_degree = value;
     else if (k == "bfs_mode" && value >= 0 && value <= 3) g_opt.bfs_mode = value;
+    else if (k == "bc_order" && value >= 0 && value <= 1) g_opt.bc_order = value;
     else if (k == "bfs_depth_switch" && value >= 0) g_opt.bfs_depth_switch = value;
     else if (k == "bfs_threads" && (value == 0 || value == 128 || value == 256 || value == 512 || value == 1024)) g_opt.bfs_threads = value;
     else if (k == "bc_sigma" && value >= 0 && value <= 2) g_opt.bc_sigma = value;
