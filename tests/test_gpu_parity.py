@@ -833,6 +833,43 @@ def test_sigma_row_formats_vs_oracle(rx, oracle, directed, n, m, seed, holes, mo
         _lib.set_option("bc_sigma", 0)
 
 
+@pytest.mark.parametrize("directed", [False, True])
+def test_source_order_does_not_change_results(rx, oracle, directed):
+    """bc_order = 1 (default) sorts the sources of a call by two-hop neighbourhood size and spreads
+    consecutive ones over a lane's sector; bc_order = 0 keeps the caller's order.  Contributions are
+    additive over sources, so both must agree with the oracle -- including a last group that is not
+    full, a source list in descending order and the endpoints / edge variants."""
+    from rustworkx_b200 import _lib, device_snapshot
+
+    g = random_graph(rx, directed, 2500, 15000, 77, holes=25)
+    og = oracle_graph(oracle, g)
+    nb, eb = g._bounds()
+    nodes = np.asarray(g.node_indices(), dtype=np.uint32)
+    src = nodes[::-1][: 3 * 128 + 37].copy()
+    res = {}
+    for flag in (1, 0):
+        _lib.set_option("bc_order", flag)
+        try:
+            dg = device_snapshot(g)
+            res[flag] = (dg.betweenness_partial(src, False), dg.betweenness_partial(src, True),
+                         dg.edge_betweenness_partial(src), dg.stats()["te"], dg.stats()["v"])
+        finally:
+            _lib.set_option("bc_order", 1)
+    for a, b in zip(res[1][:3], res[0][:3]):
+        assert_close(a, b)
+    assert res[1][3:] == res[0][3:]
+    want, ost = og.betweenness_partial(src, False)
+    assert_close(res[1][0], want)
+    assert_close(res[1][1], og.betweenness_partial(src, True)[0])
+    assert_close(res[1][2], og.edge_betweenness_partial(src)[0])
+    assert ost["te"] == res[1][3] and ost["v"] == res[1][4]
+    # all sources, through the public API, against the oracle
+    for endpoints in (False, True):
+        want, _ = og.betweenness_centrality(endpoints, True, 1 << 30, as_arrays=True)
+        gd, _ = dense_from_mapping(rx.betweenness_centrality(g, endpoints=endpoints), nb)
+        assert_close(gd, want)
+
+
 def test_sigma_overflow_falls_back_to_f64(rx, oracle):
     """A 40x40 grid has C(78,39) ~ 2.7e22 shortest paths corner to corner: the uint32 path counts
     overflow, the batch is redone with f64 sigma rows, and the handle stays wide."""

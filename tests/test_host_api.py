@@ -53,6 +53,21 @@ def test_no_cpu_fallback(rx):
             call()
 
 
+def test_pinned_allocation_needs_a_device(rx):
+    """rxc_host_alloc page-locks memory through the CUDA runtime: without a device it fails loudly
+    instead of quietly handing out pageable memory."""
+    from rustworkx_b200 import _lib
+
+    if _lib.device_count() > 0:
+        a = _lib.pinned_copy(np.arange(10, dtype=np.uint32))
+        assert a.dtype == np.uint32 and a.tolist() == list(range(10))
+        b = _lib.pinned_empty((3, 4), np.float64)
+        assert b.shape == (3, 4) and b.flags.c_contiguous
+        return
+    with pytest.raises(rx.RxCudaError):
+        _lib.pinned_empty(16, np.float64)
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "rustworkx_b200")
     for dirpath, _, files in os.walk(pkg):
