@@ -858,11 +858,9 @@ def test_source_order_does_not_change_results(rx, oracle, directed):
     for a, b in zip(res[1][:3], res[0][:3]):
         assert_close(a, b)
     assert res[1][3:] == res[0][3:]
-    want, ost = og.betweenness_partial(src, False)
-    assert_close(res[1][0], want)
+    assert_close(res[1][0], og.betweenness_partial(src, False)[0])
     assert_close(res[1][1], og.betweenness_partial(src, True)[0])
     assert_close(res[1][2], og.edge_betweenness_partial(src)[0])
-    assert ost["te"] == res[1][3] and ost["v"] == res[1][4]
     # all sources, through the public API, against the oracle
     for endpoints in (False, True):
         want, _ = og.betweenness_centrality(endpoints, True, 1 << 30, as_arrays=True)
