@@ -131,6 +131,31 @@ def test_snapshot_arrays(rx):
     s = g._snapshot_arrays()
     assert s["n_bound"] == 5 and s["directed"] and list(s["live_nodes"]) == [0, 1, 3, 4]
     assert list(zip(s["edge_src"], s["edge_dst"])) == [(0, 1), (3, 4)] and list(s["edge_id"]) == [0, 3]
+    assert not s["edge_id_is_position"]
+
+
+def test_snapshot_arrays_without_holes_are_views(rx):
+    """No slot ever vacated: no scans, no copies -- read-only views of the container's storage and
+    "the edge index is the position in the list" (the C-ABI then gets edge_id = NULL)."""
+    g = rx.generators.path_graph(6)
+    s = g._snapshot_arrays()
+    assert s["edge_id_is_position"] and s["n_bound"] == 6 and s["e_bound"] == 5
+    assert list(s["live_nodes"]) == list(range(6)) and list(s["edge_id"]) == list(range(5))
+    assert np.shares_memory(s["edge_src"], g._esrc) and not s["edge_src"].flags.writeable
+    assert g._esrc.flags.writeable  # the container itself stays mutable
+    assert list(zip(s["edge_src"].tolist(), s["edge_dst"].tolist())) == [(i, i + 1) for i in range(5)]
+    assert g._bounds() == (6, 5)
+    # vacate a slot: explicit ids; re-use it: positional again, with the new endpoints in place
+    g.remove_edge_from_index(1)
+    s = g._snapshot_arrays()
+    assert not s["edge_id_is_position"] and list(s["edge_id"]) == [0, 2, 3, 4] and s["e_bound"] == 5
+    assert not np.shares_memory(s["edge_src"], g._esrc)
+    assert g.add_edge(0, 5, None) == 1
+    s = g._snapshot_arrays()
+    assert s["edge_id_is_position"] and (int(s["edge_src"][1]), int(s["edge_dst"][1])) == (0, 5)
+    # the last node removed: the bound shrinks to the highest live index + 1
+    g.remove_node(5)
+    assert g._bounds()[0] == 5 and list(g._snapshot_arrays()["live_nodes"]) == [0, 1, 2, 3, 4]
 
 
 def test_centrality_mapping_behaviour(rx):
@@ -146,6 +171,15 @@ def test_centrality_mapping_behaviour(rx):
         m < {}
     assert str(m) == "CentralityMapping{0: 0.5, 2: 1.0, 5: 0.25}"
     assert pickle.loads(pickle.dumps(m)) == m and hash(m) == hash(pickle.loads(pickle.dumps(m)))
+    # look-ups before the dict exists are binary searches over the ascending keys
+    big = rx.CentralityMapping._from_arrays(np.arange(0, 200000, 2), np.arange(100000, dtype=np.float64))
+    assert big[19998] == 9999.0 and 19999 not in big and big._dict is None
+    with pytest.raises(IndexError, match="No node found for index"):
+        big[200001]
+    with pytest.raises(OverflowError):
+        big[-1]
+    with pytest.raises(TypeError):
+        big[1.0]
     e = rx.EdgeCentralityMapping._from_arrays([1], [2.0])
     assert str(e) == "EdgeCentralityMapping{1: 2.0}" and rx.CentralityMapping() == {}
 
