@@ -116,7 +116,9 @@ def _node_mapping(dg, dense):
 
 
 def _edge_mapping(dg, dense):
-    keys = np.sort(dg.edge_id.astype(np.int64))
+    keys = dg.edge_id.astype(np.int64)
+    if keys.size > 1 and not bool(np.all(keys[1:] > keys[:-1])):  # edge_indices() is ascending already
+        keys = np.sort(keys)
     return EdgeCentralityMapping._from_arrays(keys, dense[keys] if keys.size else np.zeros(0))
 
 
