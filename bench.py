@@ -150,6 +150,12 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # CPU legs: the oracle port of the reference algorithm (the only place bench.py executes oracle/)
 # --------------------------------------------------------------------------------------------------
+def workload_name(args):
+    """config.workload, identical on both arms"""
+    return (f"betweenness_centrality on barabasi_albert_graph({args.nodes}, {args.m}, "
+            f"seed={args.seed}) [BASELINE.json configs[2]]")
+
+
 def cpu_oracle_graph(graph):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle
@@ -189,8 +195,9 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"betweenness_centrality on barabasi_albert_graph({args.nodes}, "
-                               f"{args.m}, seed={args.seed})", "sources_per_step": per_step},
+        "config": {"workload": workload_name(args), "nodes": graph.num_nodes(),
+                   "edges": graph.num_edges(), "sources_per_step": per_step,
+                   "timing": "wall clock around the oracle call, all host threads"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -401,8 +408,7 @@ def run_b200(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {
-            "workload": f"betweenness_centrality on barabasi_albert_graph({args.nodes}, {args.m}, "
-                        f"seed={args.seed}) [BASELINE.json configs[2]]",
+            "workload": workload_name(args),
             "nodes": n, "edges": graph.num_edges(), "sources_per_step_per_gpu": S,
             "sharding": f"sources sharded over {world} rank(s), CSR replicated, one NCCL reduce at end",
             "l2": "inputs larger than L2 (per-batch state >= 2 GB vs 126 MB L2)",
