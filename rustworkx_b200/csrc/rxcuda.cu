@@ -663,6 +663,8 @@ static uint64_t bc_ws_ensure(rxc_graph *g, uint64_t total_groups) {
     // (mapping 33 GB of mostly untouched queue memory cost 2.4 s on the first call at n = 10^6).
     const uint64_t qper = g->queue_wide ? BG : std::min<uint64_t>(BG, 16);
     const uint64_t qcap = qper * n;
+    if (qcap >= 0xFFFFFFFFull)  // queue offsets are 32-bit (unreachable below ~140 GB per group)
+        throw LimitError("level queues beyond 2^32 entries per group are not supported");
     // bytes per group: f64 + uint32 rows, queues, two tagged mask arrays, visited, level tables
     const double per_group = (double)n * (1024.0 + 512.0 + 20.0 * (double)qper + 64.0 + 16.0) + (double)lcap * 8.0 + 4096.0;
     uint64_t ng = g_opt.bc_groups > 0 ? (uint64_t)g_opt.bc_groups
