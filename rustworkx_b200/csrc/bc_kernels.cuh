@@ -953,6 +953,30 @@ __global__ void __launch_bounds__(BLOCK)
     if (lane_id() == 0) keys[i] = sum;
 }
 
+// bc_order = 2 (experimental): the highest-degree neighbour of each source.
+// Sources that hang off the same hub are siblings in the BFS tree of that hub and agree on the level
+// of almost every vertex; sorting by (hub, key) puts them into the same lane.
+__global__ void __launch_bounds__(BLOCK)
+    bc_source_hubs_kernel(const uint32_t *row, const uint32_t *col, const uint32_t *src, uint32_t k,
+                          uint32_t *hubs) {
+    const uint32_t i = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (i >= k) return;
+    const uint32_t s = src[i];
+    // packed (degree, ~id): the maximum is the highest degree, ties to the lowest id
+    unsigned long long best = 0;
+    for (uint32_t e = row[s] + lane_id(); e < row[s + 1]; e += 32) {
+        const uint32_t w = col[e];
+        const unsigned long long cand = ((unsigned long long)(row[w + 1] - row[w]) << 32) | (0xFFFFFFFFu - w);
+        best = cand > best ? cand : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(FULL, best, o);
+        best = other > best ? other : best;
+    }
+    if (lane_id() == 0) hubs[i] = best ? 0xFFFFFFFFu - (uint32_t)best : s;  // isolated source: itself
+}
+
 // endpoints: the source itself receives |S| - 1 (centrality.rs:282-284)
 __global__ void __launch_bounds__(BLOCK) bc_endpoint_sources_kernel(BcParams p, uint32_t ngroups) {
     const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;

@@ -738,10 +738,24 @@ static std::vector<uint32_t> bc_order_sources(rxc_graph *g, const std::vector<ui
     g->stats.launches++;
     std::vector<unsigned long long> keys(k);
     RXC_CUDA(cudaMemcpyAsync(keys.data(), d_keys.p, k * 8, cudaMemcpyDeviceToHost, st));
+    // bc_order = 2 (experimental, not the default: simulated, not yet measured -- DESIGN.md section 7):
+    // large source sets are sorted by (highest-degree neighbour, key) so that siblings share a lane
+    std::vector<uint32_t> hubs;
+    if (g_opt.bc_order == 2 && k >= 4096) {
+        DevBuf<uint32_t> d_hubs;
+        d_hubs.alloc(k);
+        bc_source_hubs_kernel<<<(uint32_t)((k + WARPS - 1) / WARPS), BLOCK, 0, st>>>(
+            g->succ().row.p, g->succ().col.p, d_src.p, (uint32_t)k, d_hubs.p);
+        g->stats.launches++;
+        hubs.resize(k);
+        RXC_CUDA(cudaMemcpyAsync(hubs.data(), d_hubs.p, k * 4, cudaMemcpyDeviceToHost, st));
+        RXC_CUDA(cudaStreamSynchronize(st));  // before d_hubs goes back to the pool
+    }
     RXC_CUDA(cudaStreamSynchronize(st));
     std::vector<uint32_t> idx(k);
     for (size_t i = 0; i < k; i++) idx[i] = (uint32_t)i;
     std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {
+        if (!hubs.empty() && hubs[a] != hubs[b]) return hubs[a] < hubs[b];
         return keys[a] != keys[b] ? keys[a] > keys[b] : sources[a] < sources[b];
     });
     std::vector<uint32_t> out(k);
@@ -2361,7 +2375,7 @@ int rxc_set_option(const char *name, int64_t value) {
     else if (k == "bfs_groups") g_opt.bfs_groups = value;
     else if (k == "hub_degree" && value > 0) g_opt.hub_degree = value;
     else if (k == "bfs_mode" && value >= 0 && value <= 3) g_opt.bfs_mode = value;
-    else if (k == "bc_order" && value >= 0 && value <= 1) g_opt.bc_order = value;
+    else if (k == "bc_order" && value >= 0 && value <= 2) g_opt.bc_order = value;
     else if (k == "bfs_depth_switch" && value >= 0) g_opt.bfs_depth_switch = value;
     else if (k == "bfs_threads" && (value == 0 || value == 128 || value == 256 || value == 512 || value == 1024)) g_opt.bfs_threads = value;
     else if (k == "bc_sigma" && value >= 0 && value <= 2) g_opt.bc_sigma = value;
