@@ -244,6 +244,40 @@ def test_oracle_vs_networkx_fixture(oracle):
         assert np.array_equal(dm, np.array(case["distance_matrix"]))
 
 
+def test_oracle_next_rows_vs_networkx_fixture(oracle):
+    """The SURVEY 8f restatements against independent networkx vectors
+    (tests/golden/make_golden_next_rows.py): group centralities, Newman weighted closeness,
+    all-pairs Dijkstra lengths and the sums behind unweighted_average_shortest_path_length."""
+    import json
+
+    base = json.load(open(os.path.join(ROOT, "tests", "golden", "nx_golden.json")))["cases"]
+    fx = json.load(open(os.path.join(ROOT, "tests", "golden", "nx_golden_next_rows.json")))
+    assert len(fx["cases"]) == len(base)
+    checked_gbc = 0
+    for c, b in zip(fx["cases"], base):
+        n = b["n"]
+        g = oracle.OracleGraph.from_edges(b["directed"], [tuple(e) for e in b["edges"]], num_nodes=n)
+        for normalized in (True, False):
+            want = c["group_betweenness"][str(normalized)]  # enumerated shortest paths
+            got = g.group_betweenness_centrality(c["group"], normalized, 1 << 30)
+            assert abs(got - want) <= 1e-12 * max(1.0, abs(want))
+            checked_gbc += 1
+        assert abs(g.group_closeness_centrality(c["group"]) - c["group_closeness"]) <= 1e-15
+        w = np.array(c["weights"])
+        got, _ = g.newman_weighted_closeness_centrality(w, True, 1 << 30, as_arrays=True)
+        assert np.allclose(got, c["newman_closeness_wf"], rtol=1e-13, atol=0)
+        rows = g.dijkstra_lengths_rows(w, np.arange(n, dtype=np.uint32))
+        for s in range(n):
+            for t in range(n):
+                want = c["dijkstra_lengths"][s][t]
+                if want is None:
+                    assert s == t or np.isnan(rows[s, t])
+                else:
+                    assert rows[s, t] == want  # same left-to-right sums: bit-identical
+        assert g.distance_sum(300, False) == (c["distance_total"], c["connected_pairs"])
+    assert checked_gbc == 2 * len(base)
+
+
 # --------------------------------------------------------------------------------- multi-process
 GLOO_WORKER = r"""
 import os, sys
