@@ -388,3 +388,76 @@ def test_all_pairs_dijkstra_goldens(oracle):
         got = {s: {t: rows[i, t] for t in range(rows.shape[1]) if t != s and not math.isnan(rows[i, t])}
                for i, s in enumerate(live)}
         assert got == expected, name
+
+
+# ---------------------------------------------------------------------------------------------
+# multigraph semantics from first principles
+# ---------------------------------------------------------------------------------------------
+def _definition_by_matrix_powers(directed, n, edges, endpoints):
+    """Betweenness from its definition, with exact integer path counts: sigma(s,t) is the (s,t) entry
+    of A^d(s,t), A holding edge MULTIPLICITIES (a neighbour listed k times adds k paths,
+    centrality.rs:433-436; a self-loop is on no shortest path).  Independent of Brandes' recursion."""
+    A = np.zeros((n, n), dtype=object)
+    for a, b in edges:
+        if a == b:
+            continue
+        A[a, b] += 1
+        if not directed:
+            A[b, a] += 1
+    INF = 10**9
+    dist = np.full((n, n), INF, dtype=np.int64)
+    sig = np.zeros((n, n), dtype=object)
+    P = np.eye(n, dtype=object)
+    for i in range(n):
+        dist[i, i] = 0
+        sig[i, i] = 1
+    for d in range(1, n):
+        P = P.dot(A)
+        new = (dist == INF) & (P != 0)
+        if not new.any():
+            break
+        dist[new] = d
+        sig[new] = P[new]
+    bc = np.zeros(n)
+    ebc = np.zeros(len(edges))
+    for s in range(n):
+        for t in range(n):
+            if s == t or dist[s, t] >= INF:
+                continue
+            for v in range(n):
+                if v not in (s, t) and dist[s, v] + dist[v, t] == dist[s, t]:
+                    bc[v] += float(sig[s, v] * sig[v, t]) / float(sig[s, t])
+            if endpoints:  # centrality.rs:281-290: the source gets |S|-1, every reached vertex +1
+                bc[s] += 1.0
+                bc[t] += 1.0
+            for e, (a, b) in enumerate(edges):
+                if a == b:
+                    continue
+                for x, y in (((a, b),) if directed else ((a, b), (b, a))):
+                    if (dist[s, x] < INF and dist[y, t] < INF
+                            and dist[s, x] + 1 + dist[y, t] == dist[s, t]):
+                        ebc[e] += float(sig[s, x] * sig[y, t]) / float(sig[s, t])
+    if not directed:  # _rescale with normalized = false: 0.5 for undirected graphs, centrality.rs:236-241
+        bc /= 2.0
+        ebc /= 2.0
+    return bc, ebc
+
+
+@pytest.mark.parametrize("directed", [False, True])
+def test_multigraph_semantics_from_first_principles(oracle, directed):
+    """Parallel edges count as distinct shortest paths, self-loops never matter, per-edge scores of
+    parallel edges are separate: the oracle against the matrix-power definition on random
+    multigraphs (the reference pins these semantics only on a handful of tiny cases)."""
+    rng = np.random.default_rng(7 + int(directed))
+    for _ in range(10):
+        n = int(rng.integers(5, 14))
+        m = int(rng.integers(n, 3 * n))
+        edges = [(int(a), int(b)) for a, b in rng.integers(0, n, size=(m, 2))]
+        edges += [edges[int(i)] for i in rng.integers(0, m, size=max(1, m // 4))]  # parallel copies
+        g = oracle.OracleGraph.from_edges(directed, edges, num_nodes=n)
+        for endpoints in (False, True):
+            want_bc, want_ebc = _definition_by_matrix_powers(directed, n, edges, endpoints)
+            got = np.array(g.betweenness_centrality(endpoints, False, 1 << 30), dtype=float)
+            assert np.allclose(got, want_bc, rtol=1e-12, atol=1e-12)
+        got_e = np.array(g.edge_betweenness_centrality(False, 1 << 30), dtype=float)
+        assert np.allclose(got_e, want_ebc, rtol=1e-12, atol=1e-12)
