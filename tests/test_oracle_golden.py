@@ -461,3 +461,74 @@ def test_multigraph_semantics_from_first_principles(oracle, directed):
             assert np.allclose(got, want_bc, rtol=1e-12, atol=1e-12)
         got_e = np.array(g.edge_betweenness_centrality(False, 1 << 30), dtype=float)
         assert np.allclose(got_e, want_ebc, rtol=1e-12, atol=1e-12)
+
+
+def _hop_distances(directed, n, edges, as_undirected=False):
+    """All-pairs hop distances by repeated boolean matrix products (no BFS): -1 where unreachable."""
+    A = np.zeros((n, n), dtype=bool)
+    for a, b in edges:
+        A[a, b] = True
+        if not directed or as_undirected:
+            A[b, a] = True
+    dist = np.full((n, n), -1, dtype=np.int64)
+    np.fill_diagonal(dist, 0)
+    reach = np.eye(n, dtype=bool)
+    for d in range(1, n + 1):
+        reach = (reach.astype(np.int64) @ A.astype(np.int64)) > 0
+        new = reach & (dist < 0)
+        if not new.any():
+            break
+        dist[new] = d
+    return dist
+
+
+@pytest.mark.parametrize("directed", [False, True])
+def test_distance_functions_from_first_principles_with_holes(oracle, directed):
+    """closeness (incoming distances, Wasserman-Faust scaling), distance_matrix (compacted order,
+    null value, as_undirected), group closeness and the average-path-length sums on random
+    multigraphs from which nodes were removed -- against distances obtained by boolean matrix
+    powers, with the reference's own floating-point expression order (centrality.rs:1209-1220)."""
+    rng = np.random.default_rng(31 + int(directed))
+    for _ in range(8):
+        n0 = int(rng.integers(6, 16))
+        m = int(rng.integers(n0, 3 * n0))
+        edges0 = [(int(a), int(b)) for a, b in rng.integers(0, n0, size=(m, 2))]
+        g = oracle.OracleGraph.from_edges(directed, edges0, num_nodes=n0)
+        removed = sorted(int(x) for x in rng.choice(n0, size=2, replace=False))
+        for r in removed:
+            g.remove_node(r)
+        live = [v for v in range(n0) if v not in removed]
+        pos = {v: i for i, v in enumerate(live)}
+        n = len(live)
+        edges = [(pos[a], pos[b]) for a, b in edges0 if a in pos and b in pos]
+        dist = _hop_distances(directed, n, edges)
+        # closeness of v: distances TO v (Reversed graph, centrality.rs:1208)
+        for wf in (True, False):
+            got = g.closeness_centrality(wf, 1 << 30)
+            assert [x is None for x in got] == [v not in pos for v in range(len(got))]
+            for v in live:
+                col = dist[:, pos[v]]
+                reach = int((col >= 0).sum())
+                total = int(col[col >= 0].sum())
+                if reach == 1:
+                    want = 0.0
+                else:
+                    want = float(reach - 1) / float(total)
+                    if wf:
+                        want = want * float(reach - 1) / float(n - 1)
+                assert got[v] == want, (v, got[v], want)
+        for as_undirected in (False, True):
+            d2 = _hop_distances(directed, n, edges, as_undirected)
+            want = np.where(d2 >= 0, d2, -7).astype(np.float64)
+            np.fill_diagonal(want, 0.0)
+            assert np.array_equal(g.distance_matrix(300, as_undirected, -7.0), want)
+            off = ~np.eye(n, dtype=bool)
+            assert g.distance_sum(300, as_undirected) == (int(d2[off & (d2 > 0)].sum()),
+                                                          int((off & (d2 > 0)).sum()))
+        group = [live[0], live[n // 2]]
+        to_group = np.stack([dist[:, pos[x]] for x in group])          # incoming distances again
+        to_group = np.where(to_group < 0, 10**9, to_group).min(axis=0)
+        others = [i for i in range(n) if live[i] not in group]
+        total = sum(int(to_group[i]) for i in others if to_group[i] < 10**9)
+        want = 0.0 if total == 0 else float(len(others)) / float(total)
+        assert g.group_closeness_centrality(group) == want
