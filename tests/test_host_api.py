@@ -3,6 +3,7 @@ stand-in, mappings, generators, sharding + reduce over gloo) behaves like the re
 product path fails loudly without a GPU.  No compute calls on a device here.
 """
 
+import ctypes
 import os
 import pickle
 import re
@@ -412,3 +413,43 @@ def test_weight_validation_matches_is_valid_weight():
     h = rx.PyGraph()
     h.add_nodes_from(range(4))
     assert rx.all_pairs_dijkstra_path_lengths(h, float) == {i: {} for i in range(4)}
+
+
+def test_stand_in_container_and_oracle_container_agree_under_mutation(rx, oracle):
+    """Two independent restatements of petgraph's StableGraph index discipline -- the numpy-backed
+    stand-in (rustworkx_b200/graph.py) that feeds the device and the intrusive-list one inside the C
+    oracle -- driven by the same random add / remove sequence: every returned index, the counts and
+    the bounds must agree (vacated slots are re-used LIFO; removing a node removes its edges)."""
+    for directed in (False, True):
+        rng = np.random.default_rng(99 + int(directed))
+        g = rx.PyDiGraph() if directed else rx.PyGraph()
+        og = oracle.OracleGraph(directed)
+        live_nodes, live_edges = [], []
+        for step in range(600):
+            op = rng.random()
+            if op < 0.30 or len(live_nodes) < 2:
+                a, b = g.add_node(None), og.add_node()
+                assert a == b
+                live_nodes.append(a)
+            elif op < 0.75:
+                u, v = (int(x) for x in rng.choice(live_nodes, size=2))
+                a, b = g.add_edge(u, v, None), og.add_edge(u, v)
+                assert a == b
+                live_edges.append(a)
+            elif op < 0.88 and live_edges:
+                e = live_edges.pop(int(rng.integers(0, len(live_edges))))
+                g.remove_edge_from_index(e)
+                og.remove_edge(e)
+            elif live_nodes:
+                x = live_nodes.pop(int(rng.integers(0, len(live_nodes))))
+                g.remove_node(x)
+                og.remove_node(x)
+                live_edges = [int(e) for e in g.edge_indices()]
+            assert (g.num_nodes(), g.num_edges()) == (og.node_count(), og.edge_count())
+            assert g._bounds() == (og.node_bound(), og.edge_bound())
+        s = g._snapshot_arrays()
+        assert [int(x) for x in s["live_nodes"]] == sorted(live_nodes)
+        for e, a, b in zip(s["edge_id"].tolist(), s["edge_src"].tolist(), s["edge_dst"].tolist()):
+            pa, pb = ctypes.c_uint32(), ctypes.c_uint32()
+            assert og._L.rxo_edge_endpoints(og._h, e, ctypes.byref(pa), ctypes.byref(pb)) == 0
+            assert (pa.value, pb.value) == (a, b)
