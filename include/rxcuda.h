@@ -59,6 +59,8 @@ typedef struct {
     double ms_backward;   /* device time in dependency kernels                                   */
     double ms_snapshot;   /* host CSR build + H2D of the snapshot (wall clock)                   */
     double ms_d2h;        /* device-to-host result copies                                        */
+    double ms_reduce;     /* rxc_*_partial_reduce: the in-place ncclReduce on the handle's stream
+                             (CUDA events; includes waiting for the slowest rank)                */
 } rxc_stats;
 
 /* ---- library / device ------------------------------------------------------------------------- */
@@ -92,6 +94,21 @@ int rxc_graph_snapshot(uint32_t n_bound, const uint32_t *live_nodes, uint32_t n_
                        const uint32_t *edge_id, uint64_t n_edges, int directed,
                        rxc_graph **out_graph);
 void rxc_graph_free(rxc_graph *g);
+
+/* Content-keyed snapshot cache.  The reference re-reads the StableGraph on every
+ * call (the bindings borrow `&graph.graph`, src/centrality.rs:89; a caller outside the crate feeds
+ * `edge_list()` / `extend_from_edge_list`, src/graph.rs:815-826,983-998) and has no mutation counter
+ * a binding could key on, so the key is a 128-bit hash of exactly what rxc_graph_snapshot receives
+ * (bounds, live nodes, edge arrays, direction, device set).  A hit returns the SAME handle again
+ * (*hit = 1; reference counted): its CSR in HBM, its scratch and its tuned state (sigma row format,
+ * queue sizing) are re-used, and nothing is copied.  Every returned handle is released with
+ * rxc_graph_free; the cache keeps `snapshot_cache_entries` (option, default 2) handles alive,
+ * most recently used first.  rxc_snapshot_cache_clear drops them and returns how many it held. */
+int rxc_graph_snapshot_cached(uint32_t n_bound, const uint32_t *live_nodes, uint32_t n_live,
+                              uint32_t e_bound, const uint32_t *edge_src, const uint32_t *edge_dst,
+                              const uint32_t *edge_id, uint64_t n_edges, int directed,
+                              rxc_graph **out_graph, int *hit);
+int rxc_snapshot_cache_clear(void);
 int rxc_graph_info(const rxc_graph *g, uint32_t *n_bound, uint32_t *n_live, uint32_t *e_bound,
                    uint64_t *n_arcs, int *directed);
 
@@ -167,6 +184,17 @@ void rxc_rescale(double *x, uint64_t len, uint64_t node_count, int normalized, i
 int rxc_comm_unique_id(uint8_t id_out[128]);
 int rxc_comm_init(int rank, int world, const uint8_t id[128]);
 int rxc_comm_reduce_sum_f64(double *host_inout, uint64_t len, int root);
+/* The sharded call of a multi-process run (one process per GPU): this rank's share of
+ * the sources goes through the betweenness kernels, the partial vector STAYS in HBM, one in-place
+ * ncclReduce(sum, f64) on the handle's stream combines the ranks over NVLink, and only `root` copies
+ * the result to `out` (n_bound / e_bound doubles, original indexing, un-rescaled; ignored on the
+ * other ranks, may be NULL there).  Replaces the reference's shared Vec behind an RwLock
+ * (rustworkx-core/src/centrality.rs:107,280,317).  Every rank of rxc_comm_init must make the call;
+ * without a communicator it is rxc_*_partial.  rxc_stats.ms_reduce times the collective. */
+int rxc_betweenness_partial_reduce(rxc_graph *g, const uint32_t *sources, uint64_t n_sources,
+                                   int include_endpoints, int root, double *out);
+int rxc_edge_betweenness_partial_reduce(rxc_graph *g, const uint32_t *sources, uint64_t n_sources,
+                                        int root, double *out);
 int rxc_comm_barrier(void);
 void rxc_comm_destroy(void);
 
@@ -191,16 +219,6 @@ int rxc_get_stats(const rxc_graph *g, rxc_stats *out);
  *   mem_fraction_pct N share of free HBM the scratch may take (70)
  * RXC_TRACE=1 in the environment prints the phases of a snapshot and scratch allocations to stderr. */
 int rxc_set_option(const char *name, int64_t value);
-
-/* ---- benchmark inputs (host-side restatement of the reference's seeded generators;
- *      rustworkx-core/src/generators/random_graph.rs:249-345,402-466,756-824).  Each writes at most
- *      `cap` edges and returns the number of edges generated (or a negative rxc_status). -------------- */
-int64_t rxc_gen_gnp(uint32_t n, double p, uint64_t seed, int directed, uint32_t *src,
-                    uint32_t *dst, uint64_t cap);
-int64_t rxc_gen_gnm(uint32_t n, uint64_t m, uint64_t seed, int directed, uint32_t *src,
-                    uint32_t *dst, uint64_t cap);
-int64_t rxc_gen_barabasi_albert(uint32_t n, uint32_t m, uint64_t seed, uint32_t *src,
-                                uint32_t *dst, uint64_t cap);
 
 #ifdef __cplusplus
 }

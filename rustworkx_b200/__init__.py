@@ -15,6 +15,7 @@ All computation happens in ``librxcuda.so`` (hand-written sm_100a kernels behind
 from __future__ import annotations
 
 import functools
+import weakref
 
 import numpy as np
 
@@ -85,27 +86,40 @@ def _graph_arg(graph, cls, name):
 
 
 # ---------------------------------------------------------------------------------------------
-# snapshot cache: one device CSR per graph version (mutating the graph invalidates it)
+# snapshot cache: one device CSR per graph state
+#
+# * stand-in containers carry a mutation stamp (``graph._version``, never handed out twice): the
+#   snapshot is kept in a weak dictionary OUTSIDE the graph object, so pickling, ``copy.deepcopy``
+#   and ``graph.copy()`` never see a device handle, and ``clear()`` can never resurrect a stale one;
+# * any other container with the reference's accessors (a real ``rustworkx.PyGraph``, which has no
+#   mutation counter to key on) goes through ``rxc_graph_snapshot_cached``: the library keys its
+#   handles on a content hash of the node and edge arrays, so an unchanged graph re-uses the CSR in
+#   HBM, the scratch and the tuned state of the previous call.
 # ---------------------------------------------------------------------------------------------
 _SNAPSHOT_CACHE = True
+_SNAPSHOTS = weakref.WeakKeyDictionary()  # graph -> (version, DeviceGraph)
 
 
 def set_snapshot_cache(enabled):
     """Enable/disable re-use of the device snapshot across calls on an unchanged graph."""
     global _SNAPSHOT_CACHE
     _SNAPSHOT_CACHE = bool(enabled)
+    if not _SNAPSHOT_CACHE:
+        _SNAPSHOTS.clear()
 
 
 def device_snapshot(graph):
     """StableGraph -> compact CSR/CSC in HBM (``rxc_graph_snapshot``)."""
     version = getattr(graph, "_version", None)
-    if _SNAPSHOT_CACHE and version is not None:
-        cached = graph.__dict__.get("_rxc_snapshot")
+    if version is None:  # not a stand-in container: content-keyed cache behind the C-ABI
+        return DeviceGraph.from_graph(graph, cached=_SNAPSHOT_CACHE)
+    if _SNAPSHOT_CACHE:
+        cached = _SNAPSHOTS.get(graph)
         if cached is not None and cached[0] == version:
             return cached[1]
     dg = DeviceGraph.from_graph(graph)
-    if _SNAPSHOT_CACHE and version is not None:
-        graph.__dict__["_rxc_snapshot"] = (version, dg)
+    if _SNAPSHOT_CACHE:
+        _SNAPSHOTS[graph] = (version, dg)
     return dg
 
 

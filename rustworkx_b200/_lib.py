@@ -42,6 +42,7 @@ class Stats(C.Structure):
         ("ms_backward", C.c_double),
         ("ms_snapshot", C.c_double),
         ("ms_d2h", C.c_double),
+        ("ms_reduce", C.c_double),
     ]
 
     def as_dict(self):
@@ -63,6 +64,9 @@ SYMBOLS = {
     "rxc_graph_snapshot": (C.c_int, [C.c_uint32, _u32p, C.c_uint32, C.c_uint32, _u32p, _u32p, _u32p,
                                      C.c_uint64, C.c_int, C.POINTER(_vp)]),
     "rxc_graph_free": (None, [_vp]),
+    "rxc_graph_snapshot_cached": (C.c_int, [C.c_uint32, _u32p, C.c_uint32, C.c_uint32, _u32p, _u32p, _u32p,
+                                            C.c_uint64, C.c_int, C.POINTER(_vp), C.POINTER(C.c_int)]),
+    "rxc_snapshot_cache_clear": (C.c_int, []),
     "rxc_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     "rxc_host_free": (None, [_vp]),
     "rxc_graph_info": (C.c_int, [_vp, _u32p, _u32p, _u32p, C.POINTER(C.c_uint64),
@@ -87,10 +91,19 @@ SYMBOLS = {
     "rxc_comm_unique_id": (C.c_int, [_u8p]),
     "rxc_comm_init": (C.c_int, [C.c_int, C.c_int, _u8p]),
     "rxc_comm_reduce_sum_f64": (C.c_int, [_f64p, C.c_uint64, C.c_int]),
+    "rxc_betweenness_partial_reduce": (C.c_int, [_vp, _u32p, C.c_uint64, C.c_int, C.c_int, _f64p]),
+    "rxc_edge_betweenness_partial_reduce": (C.c_int, [_vp, _u32p, C.c_uint64, C.c_int, _f64p]),
     "rxc_comm_barrier": (C.c_int, []),
     "rxc_comm_destroy": (None, []),
     "rxc_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "rxc_set_option": (C.c_int, [C.c_char_p, C.c_int64]),
+}
+
+_lib = None
+
+# include/rxgen.h: the benchmark input generators live in their own host-only library
+GEN_LIB_PATH = os.environ.get("RXGEN_LIB") or os.path.join(_HERE, "librxgen.so")
+GEN_SYMBOLS = {
     "rxc_gen_gnp": (C.c_int64, [C.c_uint32, C.c_double, C.c_uint64, C.c_int, _u32p, _u32p,
                                 C.c_uint64]),
     "rxc_gen_gnm": (C.c_int64, [C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, _u32p, _u32p,
@@ -98,8 +111,22 @@ SYMBOLS = {
     "rxc_gen_barabasi_albert": (C.c_int64, [C.c_uint32, C.c_uint32, C.c_uint64, _u32p, _u32p,
                                             C.c_uint64]),
 }
+_gen = None
 
-_lib = None
+
+def gen_lib():
+    """Load librxgen.so (once): seeded random-graph generators for benchmark inputs, no CUDA."""
+    global _gen
+    if _gen is None:
+        if not os.path.exists(GEN_LIB_PATH):
+            raise RxCudaError(f"{GEN_LIB_PATH} is missing: build it with `make -C rustworkx_b200/csrc`")
+        G = C.CDLL(GEN_LIB_PATH)
+        for name, (restype, argtypes) in GEN_SYMBOLS.items():
+            fn = getattr(G, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _gen = G
+    return _gen
 
 
 def lib():
@@ -207,9 +234,10 @@ def set_option(name, value):
 class DeviceGraph:
     """An ``rxc_graph*``: the StableGraph snapshot as compact CSR/CSC resident in HBM."""
 
-    def __init__(self, n_bound, live_nodes, e_bound, edge_src, edge_dst, edge_id, directed):
+    def __init__(self, n_bound, live_nodes, e_bound, edge_src, edge_dst, edge_id, directed, cached=False):
         """``edge_id=None``: the edge index is the position in the list (no edge was ever removed);
-        the C-ABI then gets NULL and nothing is copied for it."""
+        the C-ABI then gets NULL and nothing is copied for it.  ``cached=True`` goes through
+        ``rxc_graph_snapshot_cached`` (content-keyed; ``self.cache_hit`` tells what happened)."""
         L = lib()
         self.live_nodes = np.ascontiguousarray(live_nodes, dtype=np.uint32)
         src = np.ascontiguousarray(edge_src, dtype=np.uint32)
@@ -221,10 +249,15 @@ class DeviceGraph:
         self.n_live = int(self.live_nodes.shape[0])
         self.directed = bool(directed)
         h = _vp()
-        check(L.rxc_graph_snapshot(self.n_bound, p_u32(self.live_nodes), self.n_live, self.e_bound,
-                                   p_u32(src), p_u32(dst),
-                                   None if self._edge_id is None else p_u32(self._edge_id),
-                                   src.shape[0], 1 if directed else 0, C.byref(h)))
+        self.cache_hit = False
+        args = (self.n_bound, p_u32(self.live_nodes), self.n_live, self.e_bound, p_u32(src), p_u32(dst),
+                None if self._edge_id is None else p_u32(self._edge_id), src.shape[0], 1 if directed else 0)
+        if cached:
+            hit = C.c_int(0)
+            check(L.rxc_graph_snapshot_cached(*args, C.byref(h), C.byref(hit)))
+            self.cache_hit = bool(hit.value)
+        else:
+            check(L.rxc_graph_snapshot(*args, C.byref(h)))
         self._h = h
 
     @property
@@ -235,20 +268,20 @@ class DeviceGraph:
         return self._edge_id
 
     @classmethod
-    def from_graph(cls, graph):
+    def from_graph(cls, graph, cached=False):
         """Snapshot a PyGraph / PyDiGraph (stand-in or, when importable, a real rustworkx graph --
         both expose node_indices() / edge_indices() / edge_list(), src/graph.rs:418,462,815)."""
         if hasattr(graph, "_snapshot_arrays"):
             s = graph._snapshot_arrays()
             return cls(s["n_bound"], s["live_nodes"], s["e_bound"], s["edge_src"], s["edge_dst"],
-                       None if s.get("edge_id_is_position") else s["edge_id"], s["directed"])
+                       None if s.get("edge_id_is_position") else s["edge_id"], s["directed"], cached=cached)
         nodes = np.asarray(graph.node_indices(), dtype=np.uint32)
         eids = np.asarray(graph.edge_indices(), dtype=np.uint32)
         el = np.asarray(graph.edge_list(), dtype=np.uint32).reshape(-1, 2)
         directed = type(graph).__name__ in ("PyDiGraph", "PyDAG")
         nb = int(nodes[-1]) + 1 if nodes.size else 0
         eb = int(eids[-1]) + 1 if eids.size else 0
-        return cls(nb, nodes, eb, el[:, 0], el[:, 1], eids, directed)
+        return cls(nb, nodes, eb, el[:, 0], el[:, 1], eids, directed, cached=cached)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -354,6 +387,23 @@ class DeviceGraph:
         check(lib().rxc_betweenness_partial(self._h, p_u32(src), src.shape[0],
                                             int(include_endpoints), p_f64(out)))
         return out[: self.n_bound]
+
+    def betweenness_partial_reduce(self, sources, include_endpoints=False, root=0, out=None):
+        """This rank's shard; the partial vector is reduced in HBM over the ranks of ``rxc_comm_init``
+        and returned on ``root`` only (``None`` elsewhere)."""
+        src = np.ascontiguousarray(sources, dtype=np.uint32)
+        if out is None:
+            out = np.zeros(max(self.n_bound, 1), dtype=np.float64)
+        check(lib().rxc_betweenness_partial_reduce(self._h, p_u32(src), src.shape[0],
+                                                   int(include_endpoints), int(root), p_f64(out)))
+        return out[: self.n_bound]
+
+    def edge_betweenness_partial_reduce(self, sources, root=0):
+        src = np.ascontiguousarray(sources, dtype=np.uint32)
+        out = np.zeros(max(self.e_bound, 1), dtype=np.float64)
+        check(lib().rxc_edge_betweenness_partial_reduce(self._h, p_u32(src), src.shape[0], int(root),
+                                                        p_f64(out)))
+        return out[: self.e_bound]
 
     def edge_betweenness_partial(self, sources):
         src = np.ascontiguousarray(sources, dtype=np.uint32)

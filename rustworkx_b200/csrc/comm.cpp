@@ -16,6 +16,9 @@
 
 namespace rxc {
 void set_error(const std::string &msg);
+int comm_reduce_device(double *d_inout, uint64_t len, int root, cudaStream_t st);
+int comm_rank();
+int comm_world();
 }
 
 namespace {
@@ -88,6 +91,20 @@ int cuda_fail(const char *what, cudaError_t e) {
 
 }  // namespace
 
+namespace rxc {
+// In-place sum-reduce of a DEVICE vector to `root`, queued on the caller's stream: the partial
+// centrality vector never leaves HBM before it is combined (rxc_*_partial_reduce).  Without a
+// communicator (single process) this is the identity.
+int comm_reduce_device(double *d_inout, uint64_t len, int root, cudaStream_t st) {
+    if (!g_comm || g_world == 1 || len == 0) return RXC_OK;
+    nccl_result_t r = g_nccl.Reduce(d_inout, d_inout, len, NCCL_FLOAT64, NCCL_SUM, root, g_comm, st);
+    if (r != 0) return nccl_fail("ncclReduce", r);
+    return RXC_OK;
+}
+int comm_rank() { return g_rank; }
+int comm_world() { return g_comm ? g_world : 1; }
+}  // namespace rxc
+
 extern "C" {
 
 int rxc_comm_unique_id(uint8_t id_out[128]) {
@@ -113,6 +130,8 @@ int rxc_comm_init(int rank, int world, const uint8_t id[128]) {
     nccl_result_t r = g_nccl.CommInitRank(&g_comm, world, uid, rank);
     if (r != 0) {
         g_comm = nullptr;
+        cudaStreamDestroy(g_comm_stream);
+        g_comm_stream = nullptr;
         return nccl_fail("ncclCommInitRank", r);
     }
     g_rank = rank;

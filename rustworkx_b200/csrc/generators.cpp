@@ -1,4 +1,4 @@
-// generators.cpp -- benchmark-input restatements of the reference's seeded random generators.
+// generators.cpp (librxgen.so, host only) -- benchmark-input restatements of the reference's seeded random generators.
 //
 // Generators are not part of the accelerated path (OUT OF SCOPE as a product);
 // BASELINE.json's configs name three of them, so their ALGORITHMS are restated here:
@@ -13,7 +13,7 @@
 
 #include <vector>
 
-#include "../../include/rxcuda.h"
+#include "../../include/rxgen.h"
 
 namespace {
 
@@ -106,7 +106,7 @@ struct U64Set {
 
 extern "C" int64_t rxc_gen_gnp(uint32_t n, double p, uint64_t seed, int directed, uint32_t *src,
                                uint32_t *dst, uint64_t cap) {
-    if (n == 0 || !(p >= 0.0 && p <= 1.0)) return RXC_ERR_INVALID;
+    if (n == 0 || !(p >= 0.0 && p <= 1.0)) return RXG_ERR_INVALID;
     EdgeSink out{src, dst, cap};
     Pcg64 rng(seed);
     if (p > 0.0) {
@@ -145,12 +145,12 @@ extern "C" int64_t rxc_gen_gnp(uint32_t n, double p, uint64_t seed, int directed
             }
         }
     }
-    return out.overflow ? (int64_t)RXC_ERR_INVALID : (int64_t)out.n;
+    return out.overflow ? (int64_t)RXG_ERR_INVALID : (int64_t)out.n;
 }
 
 extern "C" int64_t rxc_gen_gnm(uint32_t n, uint64_t m, uint64_t seed, int directed, uint32_t *src,
                                uint32_t *dst, uint64_t cap) {
-    if (n == 0) return RXC_ERR_INVALID;
+    if (n == 0) return RXG_ERR_INVALID;
     EdgeSink out{src, dst, cap};
     Pcg64 rng(seed);
     const uint64_t div_by = directed ? 1 : 2;
@@ -176,12 +176,12 @@ extern "C" int64_t rxc_gen_gnm(uint32_t n, uint64_t m, uint64_t seed, int direct
             }
         }
     }
-    return out.overflow ? (int64_t)RXC_ERR_INVALID : (int64_t)out.n;
+    return out.overflow ? (int64_t)RXG_ERR_INVALID : (int64_t)out.n;
 }
 
 extern "C" int64_t rxc_gen_barabasi_albert(uint32_t n, uint32_t m, uint64_t seed, uint32_t *src,
                                            uint32_t *dst, uint64_t cap) {
-    if (m < 1 || m >= n) return RXC_ERR_INVALID;
+    if (m < 1 || m >= n) return RXG_ERR_INVALID;
     EdgeSink out{src, dst, cap};
     Pcg64 rng(seed);
     // star_graph(m): hub 0, leaves 1..m-1 (star_graph.rs:98-108)
@@ -210,5 +210,5 @@ extern "C" int64_t rxc_gen_barabasi_albert(uint32_t n, uint32_t m, uint64_t seed
         repeated.insert(repeated.end(), targets.begin(), targets.end());
         repeated.insert(repeated.end(), m, source);
     }
-    return out.overflow ? (int64_t)RXC_ERR_INVALID : (int64_t)out.n;
+    return out.overflow ? (int64_t)RXG_ERR_INVALID : (int64_t)out.n;
 }

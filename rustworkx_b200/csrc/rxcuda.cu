@@ -35,8 +35,14 @@ namespace rxc {
 
 static thread_local std::string g_err;
 void set_error(const std::string &msg) { g_err = msg; }
+int comm_reduce_device(double *d_inout, uint64_t len, int root, cudaStream_t st);  // comm.cpp
+int comm_rank();
+int comm_world();
 
 struct OomError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+struct NcclError : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
 
@@ -59,12 +65,14 @@ template <class T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    int dev = -1;  // device the block came from: frees go back to that device's pool
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     void alloc(size_t count) {
         release();
         if (count) {
+            cudaGetDevice(&dev);
             cudaError_t e = cudaMallocAsync((void **)&p, count * sizeof(T), 0);
             if (e == cudaSuccess) e = cudaStreamSynchronize(0);
             if (e == cudaErrorMemoryAllocation) {
@@ -76,9 +84,16 @@ struct DevBuf {
         }
         n = count;
     }
-    // callers only release buffers whose consumer stream has been synchronised
+    // Callers release buffers whose consumer stream has been synchronised; on an exception the
+    // C-ABI wrapper (`guarded`) synchronises the device before anything can be allocated again.
     void release() {
-        if (p) cudaFreeAsync(p, 0);
+        if (p) {
+            int cur = dev;
+            cudaGetDevice(&cur);
+            if (cur != dev) cudaSetDevice(dev);
+            cudaFreeAsync(p, 0);
+            if (cur != dev) cudaSetDevice(cur);
+        }
         p = nullptr;
         n = 0;
     }
@@ -119,7 +134,12 @@ struct Options {
     int64_t bfs_ell = 1;            // CTA-per-source BFS: ELL adjacency when every vertex has <= 4 arcs
     int64_t bc_order = 1;           // betweenness: group sources of similar two-hop neighbourhood size
 };
-static Options g_opt;
+static Options g_opt;      // process-wide defaults (rxc_set_option), guarded by g_opt_mu
+static std::mutex g_opt_mu;  // every call works on the copy begin_call() takes into its handle
+static Options options_now() {
+    std::lock_guard<std::mutex> lock(g_opt_mu);
+    return g_opt;
+}
 constexpr uint32_t HUB_CAP = 4096;  // deferred high-degree work items per group and level
 constexpr uint32_t HUB_CTAS = 32;   // CTAs per group in the hub kernels
 constexpr uint32_t MARK_CTAS = 64;  // CTAs per group in the frontier-marking kernel
@@ -296,7 +316,7 @@ using namespace rxc;
 struct rxc_graph {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [4],[5]: whole call
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [4],[5]: whole call; [6],[7]: the reduce
     HostSnapshot host;
     DeviceCSR out, in, sym;
     bool has_sym = false;
@@ -313,12 +333,20 @@ struct rxc_graph {
     bool queue_wide = false;  // a level queue outgrew the typical-case size: keep worst-case queues
     std::vector<std::unique_ptr<rxc_graph>> replicas;  // same snapshot on the other devices of rxc_set_devices
     std::mutex mu;
+    Options opt;    // the tunables this call runs with: copied from the process defaults by begin_call()
+    int sms = 148;  // cudaDevAttrMultiProcessorCount of `device`
+    uint64_t cache_key[2] = {0, 0};  // rxc_graph_snapshot_cached: content hash (0,0: not cached)
+    int refs = 1;                    // rxc_graph_snapshot_cached / rxc_graph_free
 
     const DeviceCSR &succ() const { return out; }
     const DeviceCSR &pred() const { return host.directed ? in : out; }
     ~rxc_graph() {
+        replicas.clear();  // each replica switches to its own device while it goes away
         cudaSetDevice(device);
-        if (stream) cudaStreamSynchronize(stream);  // members return their buffers to the pool after this
+        if (stream) cudaStreamSynchronize(stream);  // nothing in flight touches the buffers below
+        bc_ws.release();
+        bfs_ws.release();
+        acc_buf.release();
         for (auto &e : ev)
             if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
@@ -329,8 +357,20 @@ namespace rxc {
 
 template <class F>
 static int guarded(F &&f) {
+    // On every error path the device is drained before the status goes back: buffers released while
+    // the stack unwound went to the pool with work possibly still in flight on the handle's stream.
+    struct Drain {
+        bool armed = true;
+        ~Drain() {
+            if (armed) {
+                cudaDeviceSynchronize();
+                cudaGetLastError();
+            }
+        }
+    } drain;
     try {
         f();
+        drain.armed = false;
         return RXC_OK;
     } catch (const CudaError &e) {
         set_error(std::string("CUDA error: ") + cudaGetErrorString(e.code) + " at " + e.file + ":" +
@@ -340,6 +380,9 @@ static int guarded(F &&f) {
     } catch (const OomError &e) {
         set_error(std::string("out of device memory: ") + e.what());
         return RXC_ERR_OOM;
+    } catch (const NcclError &e) {
+        set_error(e.what());
+        return RXC_ERR_NCCL;
     } catch (const std::bad_alloc &) {
         set_error("out of host memory");
         return RXC_ERR_OOM;
@@ -364,7 +407,7 @@ static void require_device() {
     }
 }
 
-static size_t device_budget() {
+static size_t device_budget(int64_t mem_fraction_pct) {
     size_t free_b = 0, total_b = 0;
     RXC_CUDA(cudaMemGetInfo(&free_b, &total_b));
     // memory parked in the pool (reserved, not in use) is available to us as well
@@ -379,7 +422,7 @@ static size_t device_budget() {
             free_b += (size_t)(reserved - used);
     }
     cudaGetLastError();
-    return (size_t)((double)free_b * (double)g_opt.mem_fraction_pct / 100.0);
+    return (size_t)((double)free_b * (double)mem_fraction_pct / 100.0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -395,7 +438,7 @@ static void device_scan(const uint32_t *in, uint32_t *out_row, uint32_t n, DevBu
 }
 
 static void device_sort_rows(DeviceCSR &csr, uint32_t n, DevBuf<uint32_t> &long_rows,
-                             uint32_t *d_nlong, cudaStream_t st) {
+                             uint32_t *d_nlong, cudaStream_t st, int sms) {
     if (n == 0 || !csr.eid.p) return;
     static bool attr_done[64] = {false};  // function attributes are per device
     int dev = 0;
@@ -408,7 +451,7 @@ static void device_sort_rows(DeviceCSR &csr, uint32_t n, DevBuf<uint32_t> &long_
     RXC_CUDA(cudaMemsetAsync(d_nlong, 0, 4, st));
     csr_sort_rows_kernel<<<(n + WARPS - 1) / WARPS, BLOCK, 0, st>>>(csr.row.p, n, csr.col.p, csr.eid.p,
                                                                    long_rows.p, d_nlong);
-    csr_sort_long_kernel<<<148, CSR_SORT_THREADS, CSR_SORT_MAX * 8, st>>>(csr.row.p, long_rows.p, d_nlong,
+    csr_sort_long_kernel<<<sms, CSR_SORT_THREADS, CSR_SORT_MAX * 8, st>>>(csr.row.p, long_rows.p, d_nlong,
                                                               csr.col.p, csr.eid.p);
 }
 
@@ -416,7 +459,7 @@ static void device_sort_rows(DeviceCSR &csr, uint32_t n, DevBuf<uint32_t> &long_
 static void device_build_csr(DeviceCSR &csr, uint32_t n, const uint32_t *d_src, const uint32_t *d_dst,
                              const uint32_t *d_eid, uint64_t n_edges, int mode,
                              const uint32_t *d_deg, DevBuf<uint32_t> &cursor, DevBuf<uint32_t> &tiles,
-                             uint32_t *d_total, cudaStream_t st) {
+                             uint32_t *d_total, cudaStream_t st, int sms) {
     const uint64_t cap = mode == 2 ? 2 * n_edges : n_edges;
     csr.row.alloc((size_t)n + 1);
     csr.col.alloc(cap ? cap : 1);
@@ -424,7 +467,7 @@ static void device_build_csr(DeviceCSR &csr, uint32_t n, const uint32_t *d_src, 
     device_scan(d_deg, csr.row.p, n, tiles, d_total, st);
     RXC_CUDA(cudaMemsetAsync(cursor.p, 0, ((size_t)n + 1) * 4, st));
     if (n_edges) {
-        const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_edges + BLOCK - 1) / BLOCK, 148 * 32);
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_edges + BLOCK - 1) / BLOCK, (uint64_t)sms * 32);
         csr_scatter_kernel<<<blocks, BLOCK, 0, st>>>(d_src, d_dst, d_eid, n_edges, mode, csr.row.p,
                                                      cursor.p, csr.col.p, d_eid ? csr.eid.p : nullptr);
     }
@@ -475,7 +518,7 @@ static void device_snapshot(rxc_graph *g, uint32_t n_bound, const uint32_t *live
         if (eid) {
             h2d_staged(pinned_for(g->device), d_eid.p, eid, n_edges * 4, st);
         } else {  // edge ids default to the position in the list: nothing to copy
-            const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_edges + BLOCK - 1) / BLOCK, 148 * 32);
+            const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_edges + BLOCK - 1) / BLOCK, (uint64_t)g->sms * 32);
             csr_iota_kernel<<<blocks, BLOCK, 0, st>>>(d_eid.p, n_edges);
         }
     }
@@ -503,23 +546,23 @@ static void device_snapshot(rxc_graph *g, uint32_t n_bound, const uint32_t *live
         csr_map_kernel<<<(n_live + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(d_live.p, n_live, n_bound, d_cmap.p, d_small.p);
     const uint32_t *d_eid_p = d_eid.p;
     if (n_edges) {
-        const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_edges + BLOCK - 1) / BLOCK, 148 * 32);
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_edges + BLOCK - 1) / BLOCK, (uint64_t)g->sms * 32);
         csr_count_kernel<<<blocks, BLOCK, 0, st>>>(d_src.p, d_dst.p, d_eid_p, n_edges, d_cmap.p, n_bound,
                                                    e_bound, d_deg_a.p, directed ? d_deg_b.p : d_deg_a.p,
                                                    d_small.p);
     }
     if (directed) {
         device_build_csr(g->out, n, d_src.p, d_dst.p, d_eid_p, n_edges, 0, d_deg_a.p,
-                         cursor, tiles, d_small.p + 1, st);
+                         cursor, tiles, d_small.p + 1, st, g->sms);
         device_build_csr(g->in, n, d_src.p, d_dst.p, d_eid_p, n_edges, 1, d_deg_b.p,
-                         cursor, tiles, d_small.p + 1, st);
+                         cursor, tiles, d_small.p + 1, st, g->sms);
     } else {
         device_build_csr(g->out, n, d_src.p, d_dst.p, d_eid_p, n_edges, 2, d_deg_a.p,
-                         cursor, tiles, d_small.p + 1, st);
+                         cursor, tiles, d_small.p + 1, st, g->sms);
     }
     tp("count+build");
-    device_sort_rows(g->out, n, long_rows, d_small.p + 2, st);
-    if (directed) device_sort_rows(g->in, n, long_rows, d_small.p + 2, st);
+    device_sort_rows(g->out, n, long_rows, d_small.p + 2, st, g->sms);
+    if (directed) device_sort_rows(g->in, n, long_rows, d_small.p + 2, st, g->sms);
     uint32_t h_err = 0, h_arcs = 0;
     RXC_CUDA(cudaMemcpyAsync(&h_err, d_small.p, 4, cudaMemcpyDeviceToHost, st));
     RXC_CUDA(cudaMemcpyAsync(&h_arcs, g->out.row.p + n, 4, cudaMemcpyDeviceToHost, st));
@@ -546,6 +589,7 @@ static void reset_stats(rxc_graph *g) {
 
 static void begin_call(rxc_graph *g) {
     RXC_CUDA(cudaSetDevice(g->device));
+    g->opt = options_now();  // a concurrent rxc_set_option never changes a running call
     g->last_bfs_entries = 0;
     reset_stats(g);
     RXC_CUDA(cudaEventRecord(g->ev[4], g->stream));
@@ -667,7 +711,7 @@ static uint64_t bc_ws_ensure(rxc_graph *g, uint64_t total_groups) {
         throw LimitError("level queues beyond 2^32 entries per group are not supported");
     // bytes per group: f64 + uint32 rows, queues, two tagged mask arrays, visited, level tables
     const double per_group = (double)n * (1024.0 + 512.0 + 20.0 * (double)qper + 64.0 + 16.0) + (double)lcap * 8.0 + 4096.0;
-    uint64_t ng = g_opt.bc_groups > 0 ? (uint64_t)g_opt.bc_groups
+    uint64_t ng = g->opt.bc_groups > 0 ? (uint64_t)g->opt.bc_groups
                                       : std::max<uint64_t>(1, (16ull << 20) / std::max<uint32_t>(n, 1));
     ng = std::min<uint64_t>(ng, 64);
     ng = std::min<uint64_t>(ng, total_groups);
@@ -686,7 +730,7 @@ static uint64_t bc_ws_ensure(rxc_graph *g, uint64_t total_groups) {
         ws.release();
         g->bfs_ws.release();  // one scratch set at a time keeps the footprint predictable
         ws.wanted = ng;
-        ng = std::min<uint64_t>(ng, std::max<uint64_t>(1, (uint64_t)((double)device_budget() / per_group)));
+        ng = std::min<uint64_t>(ng, std::max<uint64_t>(1, (uint64_t)((double)device_budget(g->opt.mem_fraction_pct) / per_group)));
         ws.sc.alloc((size_t)ng * n * BG);
         ws.sig32.alloc((size_t)ng * n * BG);
         ws.overflow.alloc(1);
@@ -726,7 +770,7 @@ static uint64_t bc_ws_ensure(rxc_graph *g, uint64_t total_groups) {
 // rows, 9 % fewer bytes per useful value in the dependency sweep, 12 % in the forward pass.
 static std::vector<uint32_t> bc_order_sources(rxc_graph *g, const std::vector<uint32_t> &sources) {
     const size_t k = sources.size();
-    if (!g_opt.bc_order || k <= (size_t)BK) return sources;
+    if (!g->opt.bc_order || k <= (size_t)BK) return sources;
     cudaStream_t st = g->stream;
     DevBuf<uint32_t> d_src;
     DevBuf<unsigned long long> d_keys;
@@ -741,7 +785,7 @@ static std::vector<uint32_t> bc_order_sources(rxc_graph *g, const std::vector<ui
     // bc_order = 2 (experimental, not the default: simulated, not yet measured -- DESIGN.md section 7):
     // large source sets are sorted by (highest-degree neighbour, key) so that siblings share a lane
     std::vector<uint32_t> hubs;
-    if (g_opt.bc_order == 2 && k >= 4096) {
+    if (g->opt.bc_order == 2 && k >= 4096) {
         DevBuf<uint32_t> d_hubs;
         d_hubs.alloc(k);
         bc_source_hubs_kernel<<<(uint32_t)((k + WARPS - 1) / WARPS), BLOCK, 0, st>>>(
@@ -807,10 +851,10 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources_in, bool e
     p.hubcap = HUB_CAP;
     p.maybe = ws.maybe.p;
     p.mwords = (n + 31) / 32;
-    p.sparse_max = (uint32_t)std::min<int64_t>(g_opt.bc_sparse_div > 0 ? n / g_opt.bc_sparse_div : 0, 0x7FFFFFFF);
+    p.sparse_max = (uint32_t)std::min<int64_t>(g->opt.bc_sparse_div > 0 ? n / g->opt.bc_sparse_div : 0, 0x7FFFFFFF);
     p.srow = g->succ().row.p;
     p.scol = g->succ().col.p;
-    p.hub_degree = (uint32_t)std::min<int64_t>(g_opt.hub_degree, 0x7FFFFFFF);
+    p.hub_degree = (uint32_t)std::min<int64_t>(g->opt.hub_degree, 0x7FFFFFFF);
     p.blocked = grp ? grp->d_blocked : nullptr;
     p.qcap = qcap;
     p.n = n;
@@ -902,8 +946,8 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources_in, bool e
                 tagbase += launched_levels + 8;
                 return (int)h_overflow;
             }
-            if (narrow) bc_group_finalize_kernel<true><<<dim3(148 * 2, bg), BLOCK, 0, st>>>(p, std::min(L + 1, lcap));
-            else bc_group_finalize_kernel<false><<<dim3(148 * 2, bg), BLOCK, 0, st>>>(p, std::min(L + 1, lcap));
+            if (narrow) bc_group_finalize_kernel<true><<<dim3(g->sms * 2, bg), BLOCK, 0, st>>>(p, std::min(L + 1, lcap));
+            else bc_group_finalize_kernel<false><<<dim3(g->sms * 2, bg), BLOCK, 0, st>>>(p, std::min(L + 1, lcap));
             g->stats.launches++;
             RXC_CUDA(cudaEventRecord(g->ev[2], st));
             RXC_CUDA(cudaStreamSynchronize(st));
@@ -978,7 +1022,7 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources_in, bool e
 
     for (uint64_t g0 = 0; g0 < total_groups; g0 += ng) {
         for (;;) {
-            const bool narrow = g_opt.bc_sigma == 2 || (g_opt.bc_sigma == 0 && !g->sigma_wide);
+            const bool narrow = g->opt.bc_sigma == 2 || (g->opt.bc_sigma == 0 && !g->sigma_wide);
             const int over = run_batch(g0, narrow);
             if (over == 0) break;
             if (over & 2) {  // a level queue outgrew its typical-case size: worst-case queues from here on
@@ -988,7 +1032,7 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources_in, bool e
                 bc_run(g, rest, endpoints, edge_mode, d_acc, grp);  // re-sizes the scratch
                 return;
             }
-            if (g_opt.bc_sigma == 2) throw std::runtime_error("path count exceeds 32 bits (bc_sigma=2 forces uint32 sigma rows)");
+            if (g->opt.bc_sigma == 2) throw std::runtime_error("path count exceeds 32 bits (bc_sigma=2 forces uint32 sigma rows)");
             g->sigma_wide = true;
         }
     }
@@ -1011,16 +1055,18 @@ static std::vector<uint32_t> to_compact(const rxc_graph *g, const uint32_t *sour
     return s;
 }
 
-// un-rescaled betweenness sums over `sources` (compact ids) into out (original indexing)
+// un-rescaled betweenness sums over `sources` (compact ids) into out (original indexing).
+// reduce_root >= 0: the partial vector is first sum-reduced over the ranks of rxc_comm_init, in
+// place in HBM on the handle's stream, and only the root reads it back (out untouched elsewhere).
 static void bc_partial(rxc_graph *g, const std::vector<uint32_t> &sources, bool endpoints,
-                       bool edge_mode, double *out) {
+                       bool edge_mode, double *out, int reduce_root = -1) {
     std::lock_guard<std::mutex> lock(g->mu);
     begin_call(g);
     const uint32_t n = g->host.n_live;
     const size_t out_len = edge_mode ? g->host.e_bound : g->host.n_bound;
     const size_t acc_len = edge_mode ? g->host.e_bound : n;
     const bool dense = edge_mode || g->host.n_bound == n;  // no holes: device order == original order
-    if (!dense || acc_len == 0) std::fill(out, out + out_len, 0.0);
+    if (out && (!dense || acc_len == 0)) std::fill(out, out + out_len, 0.0);
     if (acc_len == 0) {
         end_call(g);
         return;
@@ -1030,6 +1076,20 @@ static void bc_partial(rxc_graph *g, const std::vector<uint32_t> &sources, bool 
     RXC_CUDA(cudaMemsetAsync(acc.p, 0, acc_len * sizeof(double), g->stream));
     for (const auto &round : distinct_rounds(sources, n)) bc_run(g, round, endpoints, edge_mode, acc.p);
     end_call(g);
+    if (reduce_root >= 0 && comm_world() > 1) {
+        RXC_CUDA(cudaEventRecord(g->ev[6], g->stream));
+        if (comm_reduce_device(acc.p, acc_len, reduce_root, g->stream) != RXC_OK)
+            throw NcclError(g_err);
+        RXC_CUDA(cudaEventRecord(g->ev[7], g->stream));
+        RXC_CUDA(cudaEventSynchronize(g->ev[7]));
+        float ms = 0.f;
+        RXC_CUDA(cudaEventElapsedTime(&ms, g->ev[6], g->ev[7]));
+        g->stats.ms_reduce = ms;  // includes waiting for the slowest rank to arrive
+        if (comm_rank() != reduce_root) {
+            fetch_stats(g);
+            return;
+        }
+    }
     const double t0 = now_ms();
     if (dense) {  // 134 MB for the edge scores of config 4: through the pinned staging slots
         d2h_staged(pinned_for(g->device), out, acc.p, acc_len * sizeof(double), g->stream);
@@ -1104,7 +1164,7 @@ static void bfs_run(rxc_graph *g, const DeviceCSR &csr, const std::vector<uint32
     const uint64_t total_groups = (sources.size() + GW - 1) / GW;
     const uint32_t lcap = n + 2;
     const double per_group = (double)n * 20.0 + (rows_mode ? (double)n * GW * 8.0 : 0.0) + 1024.0;
-    uint64_t ng = g_opt.bfs_groups > 0 ? (uint64_t)g_opt.bfs_groups : 4096;
+    uint64_t ng = g->opt.bfs_groups > 0 ? (uint64_t)g->opt.bfs_groups : 4096;
     {
         const uint64_t want = std::min<uint64_t>(ng, total_groups);
         BfsWorkspace &w0 = g->bfs_ws;
@@ -1113,7 +1173,7 @@ static void bfs_run(rxc_graph *g, const DeviceCSR &csr, const std::vector<uint32
             ng = rows_mode ? std::min(w0.ng, w0.ng_rows) : w0.ng;  // clamped by memory earlier
         } else if (!have) {
             w0.wanted = want;
-            ng = std::min<uint64_t>(ng, std::max<uint64_t>(1, (uint64_t)((double)device_budget() / per_group)));
+            ng = std::min<uint64_t>(ng, std::max<uint64_t>(1, (uint64_t)((double)device_budget(g->opt.mem_fraction_pct) / per_group)));
         }
     }
     if (rows_mode)  // keep one batch of rows under 8 GiB
@@ -1185,7 +1245,7 @@ static void bfs_run(rxc_graph *g, const DeviceCSR &csr, const std::vector<uint32
         g->stats.launches += 2;
         if (rows_mode) {
             const uint64_t len = (uint64_t)bg * GW * n;
-            const uint32_t fb = (uint32_t)std::min<uint64_t>((len + BLOCK - 1) / BLOCK, 148 * 16);
+            const uint32_t fb = (uint32_t)std::min<uint64_t>((len + BLOCK - 1) / BLOCK, (uint64_t)g->sms * 16);
             bfs_fill_f64_kernel<<<fb, BLOCK, 0, st>>>(ws.rows.p, len, null_value);
             g->stats.launches++;
         }
@@ -1193,7 +1253,7 @@ static void bfs_run(rxc_graph *g, const DeviceCSR &csr, const std::vector<uint32
         // frontier sizes are only known a chunk late: size the grid from the last total seen
         // (the kernel grid-strides, so an underestimate only costs parallelism)
         uint32_t est = GW;
-        const uint32_t gx_fill = (148 * 4 + bg - 1) / bg;
+        const uint32_t gx_fill = (g->sms * 4 + bg - 1) / bg;
         const uint32_t L = run_levels(
             g, ws.lvl_total.p, n,
             [&](uint32_t level) {
@@ -1292,7 +1352,7 @@ static void bfs128_run(rxc_graph *g, const DeviceCSR &push, const DeviceCSR &pul
     p.hubcap = HUB_CAP;
     p.maybe = ws.maybe.p;
     p.mwords = (n + 31) / 32;
-    p.sparse_max = (uint32_t)std::min<int64_t>(g_opt.bc_sparse_div > 0 ? n / g_opt.bc_sparse_div : 0, 0x7FFFFFFF);
+    p.sparse_max = (uint32_t)std::min<int64_t>(g->opt.bc_sparse_div > 0 ? n / g->opt.bc_sparse_div : 0, 0x7FFFFFFF);
     p.hub_degree = 0x7FFFFFFF;
     p.qcap = ws.qper * n;
     p.n = n;
@@ -1325,7 +1385,7 @@ static void bfs128_run(rxc_graph *g, const DeviceCSR &push, const DeviceCSR &pul
         RXC_CUDA(cudaMemsetAsync(ws.overflow.p, 0, 4, st));
         if (rows_mode) {
             const uint64_t len = (uint64_t)bg * BG * n;
-            const uint32_t fb = (uint32_t)std::min<uint64_t>((len + BLOCK - 1) / BLOCK, 148 * 16);
+            const uint32_t fb = (uint32_t)std::min<uint64_t>((len + BLOCK - 1) / BLOCK, (uint64_t)g->sms * 16);
             bfs_fill_f64_kernel<<<fb, BLOCK, 0, st>>>(d_rows.p, len, null_value);
             g->stats.launches++;
         }
@@ -1427,11 +1487,11 @@ static void bfs_smem_run(rxc_graph *g, const DeviceCSR &csr, const uint32_t *sou
         RXC_CUDA(cudaStreamSynchronize(g->stream));
         mcsr.max_degree = h_max;
     }
-    if (mcsr.max_degree <= 4 && g_opt.bfs_ell && !mcsr.ell.p) {
+    if (mcsr.max_degree <= 4 && g->opt.bfs_ell && !mcsr.ell.p) {
         mcsr.ell.alloc(n);
         csr_to_ell4_kernel<<<(n + BLOCK - 1) / BLOCK, BLOCK, 0, g->stream>>>(csr.row.p, csr.col.p, n, mcsr.ell.p);
     }
-    const bool ell = mcsr.ell.p != nullptr && g_opt.bfs_ell;
+    const bool ell = mcsr.ell.p != nullptr && g->opt.bfs_ell;
     using KernelT = void (*)(SmemBfsParams);
     const KernelT table[8] = {bfs_smem_kernel<false, false, false>, bfs_smem_kernel<false, false, true>,
                               bfs_smem_kernel<false, true, false>,  bfs_smem_kernel<false, true, true>,
@@ -1445,9 +1505,9 @@ static void bfs_smem_run(rxc_graph *g, const DeviceCSR &csr, const uint32_t *sou
             RXC_CUDA(cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_done = true;
     }
-    const int threads = g_opt.bfs_threads > 0 ? (int)g_opt.bfs_threads : (n >= (1u << 18) ? 1024 : 256);
-    int per_sm = 1, sms = 148;
-    RXC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device));
+    const int threads = g->opt.bfs_threads > 0 ? (int)g->opt.bfs_threads : (n >= (1u << 18) ? 1024 : 256);
+    int per_sm = 1;
+    const int sms = g->sms;
     RXC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
     per_sm = std::max(per_sm, 1);
     cudaStream_t st = g->stream;
@@ -1497,7 +1557,7 @@ static void bfs_smem_run(rxc_graph *g, const DeviceCSR &csr, const uint32_t *sou
         RXC_CUDA(cudaMemsetAsync(d_counter.p, 0, 4, st));
         if (rows_mode) {
             const uint64_t len = (uint64_t)cnt * n;
-            const uint32_t fb = (uint32_t)std::min<uint64_t>((len + BLOCK - 1) / BLOCK, 148 * 16);
+            const uint32_t fb = (uint32_t)std::min<uint64_t>((len + BLOCK - 1) / BLOCK, (uint64_t)g->sms * 16);
             bfs_fill_f64_kernel<<<fb, BLOCK, 0, st>>>(d_rows.p, len, null_value);
             kernel<<<grid, threads, smem, st>>>(p);
             g->stats.launches += 2;
@@ -1547,7 +1607,7 @@ static void bfs_dispatch_distinct(rxc_graph *g, const DeviceCSR &csr, const std:
                                   BfsMode mode, bool wf_improved, double null_value, double *out) {
     const uint32_t n = g->host.n_live;
     const size_t stride = mode == BfsMode::Rows ? (size_t)n : (mode == BfsMode::Sums ? 2 : 1);
-    int64_t regime = g_opt.bfs_mode;  // 0 auto, 1 32-source words top-down, 2 CTA-per-source, 3 128-source bottom-up
+    int64_t regime = g->opt.bfs_mode;  // 0 auto, 1 32-source words top-down, 2 CTA-per-source, 3 128-source bottom-up
     if (regime == 0) {
         const size_t k = sources.size(), np = std::min<size_t>(8, k);
         std::vector<uint32_t> pilot(np);
@@ -1559,7 +1619,7 @@ static void bfs_dispatch_distinct(rxc_graph *g, const DeviceCSR &csr, const std:
         RXC_CUDA(cudaMemsetAsync(g->d_stats.p, 0, g->d_stats.bytes(), g->stream));
         g->stats.sources -= np;
         // shallow graphs: the 128-source bottom-up kernel once there are enough sources to fill groups
-        regime = depth > (uint32_t)g_opt.bfs_depth_switch ? 2 : (sources.size() >= 64 ? 3 : 1);
+        regime = depth > (uint32_t)g->opt.bfs_depth_switch ? 2 : (sources.size() >= 64 ? 3 : 1);
     }
     if (regime == 2)
         bfs_smem_run(g, csr, sources.data(), sources.size(), mode, wf_improved, null_value, out);
@@ -1688,7 +1748,7 @@ static void wsp_costs(rxc_graph *g, const double *edge_weight, bool invert, bool
     if (eb) RXC_CUDA(cudaMemcpyAsync(d_w.p, edge_weight, eb * 8, cudaMemcpyHostToDevice, g->stream));
     c.pull.alloc(std::max<uint64_t>(pull.arcs, 1));
     if (pull.arcs) {
-        const uint32_t blocks = (uint32_t)std::min<uint64_t>((pull.arcs + BLOCK - 1) / BLOCK, 148 * 16);
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>((pull.arcs + BLOCK - 1) / BLOCK, (uint64_t)g->sms * 16);
         wsp_arc_costs_kernel<<<blocks, BLOCK, 0, g->stream>>>(pull.eid.p, d_w.p, pull.arcs, invert ? 1 : 0, c.pull.p);
     }
     RXC_CUDA(cudaStreamSynchronize(g->stream));
@@ -1769,7 +1829,7 @@ static void wsp_run(rxc_graph *g, bool reversed, const double *d_cost, const std
         RXC_CUDA(cudaMemcpyAsync(ws.src.p, h_src.data(), (size_t)bg * BG * 4, cudaMemcpyHostToDevice, st));
         RXC_CUDA(cudaMemset2DAsync(ws.lvlcnt.p, (size_t)lcap * 4, 0, (size_t)clear_levels * 4, ws.ng, st));
         RXC_CUDA(cudaMemsetAsync(ws.lvl_total.p, 0, (size_t)clear_levels * 4, st));
-        wsp_fill_kernel<<<148 * 8, BLOCK, 0, st>>>(ws.sc.p, (uint64_t)bg * n * BG);
+        wsp_fill_kernel<<<g->sms * 8, BLOCK, 0, st>>>(ws.sc.p, (uint64_t)bg * n * BG);
         wsp_seed_kernel<<<bg, 32, 0, st>>>(p);
         g->stats.launches += 2;
         uint32_t launched = 0;
@@ -1865,7 +1925,7 @@ static const DeviceCSR &symmetric_csr(rxc_graph *g) {
             // degree = out-degree + in-degree, read off the two row arrays built at snapshot time
             csr_degree_sum_kernel<<<(n + BLOCK) / BLOCK, BLOCK, 0, g->stream>>>(g->out.row.p, g->in.row.p, n, deg.p);
             device_build_csr(g->sym, n, g->d_esrc.p, g->d_edst.p, nullptr, m, 2, deg.p, cursor, tiles,
-                             small.p + 1, g->stream);
+                             small.p + 1, g->stream, g->sms);
             g->sym.arcs = 2 * (uint64_t)g->n_arcs;
         } else {
             HostCSR h = make_symmetric(g->host);
@@ -2008,11 +2068,13 @@ static rxc_graph *snapshot_on(int device, uint32_t n_bound, const uint32_t *live
     const double t0 = now_ms();
     std::unique_ptr<rxc_graph> g(new rxc_graph());
     g->device = device;
+    g->opt = options_now();
     RXC_CUDA(cudaSetDevice(device));
+    RXC_CUDA(cudaDeviceGetAttribute(&g->sms, cudaDevAttrMultiProcessorCount, device));
     pool_setup(device);
     RXC_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
     for (auto &e : g->ev) RXC_CUDA(cudaEventCreate(&e));
-    if (g_opt.device_csr) {
+    if (g->opt.device_csr) {
         device_snapshot(g.get(), n_bound, live_nodes, n_live, e_bound, edge_src, edge_dst, edge_id,
                         n_edges, directed);
     } else {
@@ -2062,7 +2124,145 @@ int rxc_graph_snapshot(uint32_t n_bound, const uint32_t *live_nodes, uint32_t n_
     return RXC_OK;
 }
 
-void rxc_graph_free(rxc_graph *g) { delete g; }
+// ---- content-keyed snapshot cache --------------------------------------------------
+// The reference re-reads the graph on every call; a binding has no mutation counter to key on, so
+// the key is a hash of what the caller hands over.  64-bit multiply-xorshift lanes over 8-byte words,
+// two seeds (128 bits), chunks hashed by up to 8 host threads and folded in chunk order.
+static uint64_t mix64(uint64_t x) {
+    x ^= x >> 32;
+    x *= 0xD6E8FEB86659FD93ull;
+    x ^= x >> 32;
+    x *= 0xD6E8FEB86659FD93ull;
+    x ^= x >> 32;
+    return x;
+}
+
+static void hash_chunk(const uint8_t *p, size_t len, uint64_t seed, uint64_t out[2]) {
+    uint64_t a = seed ^ 0x9E3779B97F4A7C15ull, b = ~seed * 0xC2B2AE3D27D4EB4Full, c = seed + len, d = seed ^ len;
+    size_t i = 0;
+    for (; i + 32 <= len; i += 32) {  // four independent lanes: the multiplies pipeline
+        uint64_t w[4];
+        memcpy(w, p + i, 32);
+        a = (a ^ w[0]) * 0xFF51AFD7ED558CCDull; a ^= a >> 29;
+        b = (b ^ w[1]) * 0xC4CEB9FE1A85EC53ull; b ^= b >> 31;
+        c = (c ^ w[2]) * 0x9FB21C651E98DF25ull; c ^= c >> 30;
+        d = (d ^ w[3]) * 0xD6E8FEB86659FD93ull; d ^= d >> 28;
+    }
+    uint64_t tail[4] = {0, 0, 0, 0};
+    memcpy(tail, p + i, len - i);
+    a = mix64(a ^ tail[0]);
+    b = mix64(b ^ tail[1]);
+    c = mix64(c ^ tail[2]);
+    d = mix64(d ^ tail[3]);
+    out[0] = mix64(a + 3 * c) ^ mix64(b ^ (d << 1));
+    out[1] = mix64(b + 5 * d) ^ mix64(a ^ (c >> 1));
+}
+
+static void hash_fold(uint64_t key[2], const uint64_t h[2]) {
+    key[0] = mix64(key[0] ^ h[0]) + 0x9E3779B97F4A7C15ull;
+    key[1] = mix64(key[1] + h[1]) ^ 0xC2B2AE3D27D4EB4Full;
+}
+
+static void hash_array(uint64_t key[2], const void *data, size_t bytes, uint64_t tagv) {
+    constexpr size_t CHUNK = 4u << 20;
+    const size_t nchunks = (bytes + CHUNK - 1) / CHUNK;
+    std::vector<uint64_t> hs(2 * std::max<size_t>(nchunks, 1), 0);
+    auto work = [&](size_t c0, size_t c1) {
+        for (size_t c = c0; c < c1; c++)
+            hash_chunk((const uint8_t *)data + c * CHUNK, std::min(CHUNK, bytes - c * CHUNK), tagv + c, &hs[2 * c]);
+    };
+    const size_t T = std::min<size_t>(8, nchunks);
+    if (T <= 1) {
+        work(0, nchunks);
+    } else {
+        std::vector<std::thread> th;
+        for (size_t t = 0; t < T; t++) th.emplace_back(work, nchunks * t / T, nchunks * (t + 1) / T);
+        for (auto &x : th) x.join();
+    }
+    const uint64_t head[2] = {tagv, (uint64_t)bytes};
+    hash_fold(key, head);
+    for (size_t c = 0; c < nchunks; c++) hash_fold(key, &hs[2 * c]);
+}
+
+static std::mutex g_cache_mu;             // guards g_cache and every handle's `refs`
+static std::vector<rxc_graph *> g_cache;  // most recently used first
+static size_t g_cache_cap = 2;            // a handle keeps its multi-GB scratch: few entries
+
+static void graph_unref_locked(rxc_graph *g) {
+    if (g && --g->refs == 0) delete g;
+}
+
+int rxc_graph_snapshot_cached(uint32_t n_bound, const uint32_t *live_nodes, uint32_t n_live,
+                              uint32_t e_bound, const uint32_t *edge_src, const uint32_t *edge_dst,
+                              const uint32_t *edge_id, uint64_t n_edges, int directed,
+                              rxc_graph **out_graph, int *hit) {
+    if (!out_graph) return RXC_ERR_INVALID;
+    *out_graph = nullptr;
+    if (hit) *hit = 0;
+    if ((n_live && !live_nodes) || (n_edges && (!edge_src || !edge_dst))) {
+        set_error("invalid argument: null array");
+        return RXC_ERR_INVALID;
+    }
+    uint64_t key[2] = {0x243F6A8885A308D3ull, 0x13198A2E03707344ull};
+    const uint64_t head[2] = {((uint64_t)n_bound << 32) | e_bound, (n_edges << 1) | (directed ? 1u : 0u)};
+    hash_fold(key, head);
+    uint64_t devs[2] = {(uint64_t)g_device, (uint64_t)g_devices.size()};
+    for (int d : g_devices) devs[1] = mix64(devs[1] ^ (uint64_t)(d + 1));
+    hash_fold(key, devs);
+    hash_array(key, live_nodes, (size_t)n_live * 4, 1ull << 40);
+    hash_array(key, edge_src, (size_t)n_edges * 4, 2ull << 40);
+    hash_array(key, edge_dst, (size_t)n_edges * 4, 3ull << 40);
+    if (edge_id) hash_array(key, edge_id, (size_t)n_edges * 4, 4ull << 40);
+    if (key[0] == 0 && key[1] == 0) key[1] = 1;  // (0,0) means "not cached"
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mu);
+        for (size_t i = 0; i < g_cache.size(); i++) {
+            rxc_graph *c = g_cache[i];
+            if (c->cache_key[0] == key[0] && c->cache_key[1] == key[1] && c->host.n_bound == n_bound &&
+                c->host.n_live == n_live && c->host.e_bound == e_bound && c->host.n_edges == n_edges &&
+                c->host.directed == (directed != 0)) {
+                g_cache.erase(g_cache.begin() + i);
+                g_cache.insert(g_cache.begin(), c);
+                c->refs++;
+                *out_graph = c;
+                if (hit) *hit = 1;
+                return RXC_OK;
+            }
+        }
+    }
+    rxc_graph *g = nullptr;
+    const int rc = rxc_graph_snapshot(n_bound, live_nodes, n_live, e_bound, edge_src, edge_dst, edge_id, n_edges,
+                                      directed, &g);
+    if (rc != RXC_OK) return rc;
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    g->cache_key[0] = key[0];
+    g->cache_key[1] = key[1];
+    if (g_cache_cap > 0) {
+        g->refs++;  // the cache's own reference
+        g_cache.insert(g_cache.begin(), g);
+        while (g_cache.size() > g_cache_cap) {
+            rxc_graph *old = g_cache.back();
+            g_cache.pop_back();
+            graph_unref_locked(old);
+        }
+    }
+    *out_graph = g;
+    return RXC_OK;
+}
+
+int rxc_snapshot_cache_clear(void) {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    const int n = (int)g_cache.size();
+    for (rxc_graph *c : g_cache) graph_unref_locked(c);
+    g_cache.clear();
+    return n;
+}
+
+void rxc_graph_free(rxc_graph *g) {
+    if (!g) return;
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    graph_unref_locked(g);
+}
 
 int rxc_host_alloc(size_t bytes, void **out) {
     if (!out) return RXC_ERR_INVALID;
@@ -2128,6 +2328,22 @@ int rxc_edge_betweenness_partial(rxc_graph *g, const uint32_t *sources, uint64_t
                                  double *out) {
     if (!g || !out || (n_sources && !sources)) return RXC_ERR_INVALID;
     return guarded([&] { bc_partial(g, to_compact(g, sources, n_sources), false, true, out); });
+}
+
+int rxc_betweenness_partial_reduce(rxc_graph *g, const uint32_t *sources, uint64_t n_sources,
+                                   int include_endpoints, int root, double *out) {
+    if (!g || (n_sources && !sources) || root < 0 || root >= comm_world()) return RXC_ERR_INVALID;
+    if (comm_rank() == root && !out) return RXC_ERR_INVALID;
+    return guarded([&] {
+        bc_partial(g, to_compact(g, sources, n_sources), include_endpoints != 0, false, out, root);
+    });
+}
+
+int rxc_edge_betweenness_partial_reduce(rxc_graph *g, const uint32_t *sources, uint64_t n_sources,
+                                        int root, double *out) {
+    if (!g || (n_sources && !sources) || root < 0 || root >= comm_world()) return RXC_ERR_INVALID;
+    if (comm_rank() == root && !out) return RXC_ERR_INVALID;
+    return guarded([&] { bc_partial(g, to_compact(g, sources, n_sources), false, true, out, root); });
 }
 
 int rxc_betweenness(rxc_graph *g, int include_endpoints, int normalized, double *out) {
@@ -2371,6 +2587,7 @@ int rxc_get_stats(const rxc_graph *g, rxc_stats *out) {
 int rxc_set_option(const char *name, int64_t value) {
     if (!name) return RXC_ERR_INVALID;
     const std::string k(name);
+    std::lock_guard<std::mutex> lock(g_opt_mu);
     if (k == "bc_groups") g_opt.bc_groups = value;
     else if (k == "bfs_groups") g_opt.bfs_groups = value;
     else if (k == "hub_degree" && value > 0) g_opt.hub_degree = value;
@@ -2383,6 +2600,15 @@ int rxc_set_option(const char *name, int64_t value) {
     else if (k == "device_csr" && (value == 0 || value == 1)) g_opt.device_csr = value;
     else if (k == "bc_sparse_div" && value >= 0) g_opt.bc_sparse_div = value;
     else if (k == "mem_fraction_pct" && value > 0 && value <= 95) g_opt.mem_fraction_pct = value;
+    else if (k == "snapshot_cache_entries" && value >= 0 && value <= 64) {
+        std::lock_guard<std::mutex> cl(g_cache_mu);
+        g_cache_cap = (size_t)value;
+        while (g_cache.size() > g_cache_cap) {
+            rxc_graph *old = g_cache.back();
+            g_cache.pop_back();
+            graph_unref_locked(old);
+        }
+    }
     else {
         set_error("unknown option: " + k);
         return RXC_ERR_INVALID;

@@ -20,6 +20,8 @@ order (most recently added edge first).
 
 from __future__ import annotations
 
+import itertools
+
 import numpy as np
 
 _END = 0xFFFFFFFF
@@ -60,6 +62,12 @@ def _check_index(x, what="index"):
     return int(x)
 
 
+# Mutation stamps come from one process-wide counter, so a stamp is never handed out twice: not after
+# clear() re-initialises a graph, not across graphs.  The device-snapshot cache (rustworkx_b200.
+# device_snapshot) keys on it.
+_VERSIONS = itertools.count(1)
+
+
 class _StableGraph:
     _directed = False
 
@@ -84,11 +92,11 @@ class _StableGraph:
         self._node_count = 0
         self._edge_count = 0
         self._edge_lookup = None  # (a, b) -> index, only for multigraph=False
-        self._version = 0
+        self._version = next(_VERSIONS)
 
     # ------------------------------------------------------------------ internals
     def _touch(self):
-        self._version += 1
+        self._version = next(_VERSIONS)
 
     def _grow_nodes(self, need):
         if need > self._nalive.shape[0]:

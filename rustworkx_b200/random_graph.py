@@ -1,7 +1,7 @@
 """Seeded random graph generators named by BASELINE.json's configs (benchmark inputs only).
 
 Mirrors the Python names of the reference (``src/random_graph.rs:182,240,626``); the edge sets come
-from ``librxcuda``'s host-side restatement of the algorithms in
+from ``librxgen.so``'s host-side restatement of the algorithms in
 ``rustworkx-core/src/generators/random_graph.rs`` (see ``csrc/generators.cpp``).  The reference's
 RNG stream (rand_pcg / rand, un-vendored) cannot be reproduced here, so a given seed yields a graph
 from the same distribution, not the same graph.
@@ -42,7 +42,7 @@ def _gnp(num_nodes, probability, seed, directed):
     pairs = n * (n - 1) if directed else n * (n - 1) // 2
     mean = pairs * p
     cap = int(min(pairs, mean + 8.0 * np.sqrt(mean + 1.0) + 64))
-    L = _lib.lib()
+    L = _lib.gen_lib()
     while True:
         src = np.empty(max(cap, 1), dtype=np.uint32)
         dst = np.empty(max(cap, 1), dtype=np.uint32)
@@ -72,7 +72,7 @@ def _gnm(num_nodes, num_edges, seed, directed):
     cap = min(m, pairs)
     src = np.empty(max(cap, 1), dtype=np.uint32)
     dst = np.empty(max(cap, 1), dtype=np.uint32)
-    got = _lib.lib().rxc_gen_gnm(n, m, _seed(seed), int(directed), _lib.p_u32(src), _lib.p_u32(dst), cap)
+    got = _lib.gen_lib().rxc_gen_gnm(n, m, _seed(seed), int(directed), _lib.p_u32(src), _lib.p_u32(dst), cap)
     if got < 0:
         raise ValueError("gnm generation failed")
     return _make(directed, n, src, dst, int(got))
@@ -96,7 +96,7 @@ def barabasi_albert_graph(n, m, seed=None, initial_graph=None):
     cap = (m - 1) + m * (n - m)
     src = np.empty(max(cap, 1), dtype=np.uint32)
     dst = np.empty(max(cap, 1), dtype=np.uint32)
-    got = _lib.lib().rxc_gen_barabasi_albert(n, m, _seed(seed), _lib.p_u32(src), _lib.p_u32(dst), cap)
+    got = _lib.gen_lib().rxc_gen_barabasi_albert(n, m, _seed(seed), _lib.p_u32(src), _lib.p_u32(dst), cap)
     if got < 0:
         raise ValueError("barabasi_albert generation failed")
     return _make(False, n, src, dst, int(got))

@@ -11,7 +11,7 @@ from rustworkx_b200 import _lib
 N = 200_000
 cap = 8 * N
 src = np.zeros(cap, np.uint32); dst = np.zeros(cap, np.uint32)
-m = _lib.lib().rxc_gen_barabasi_albert(N, 8, 1, _lib.p_u32(src), _lib.p_u32(dst), cap)
+m = _lib.gen_lib().rxc_gen_barabasi_albert(N, 8, 1, _lib.p_u32(src), _lib.p_u32(dst), cap)
 src = src[:m].astype(np.int64); dst = dst[:m].astype(np.int64)
 A = sp.coo_matrix((np.ones(m), (src, dst)), shape=(N, N)).tocsr(); A = A + A.T
 deg = np.asarray(A.sum(axis=1)).ravel()

@@ -453,3 +453,81 @@ def test_stand_in_container_and_oracle_container_agree_under_mutation(rx, oracle
             pa, pb = ctypes.c_uint32(), ctypes.c_uint32()
             assert og._L.rxo_edge_endpoints(og._h, e, ctypes.byref(pa), ctypes.byref(pb)) == 0
             assert (pa.value, pb.value) == (a, b)
+
+
+# --------------------------------------------------------------------------------- snapshot cache
+class _FakeDeviceGraph:
+    """Counts snapshots; stands in for DeviceGraph where no GPU exists (host logic only)."""
+
+    made = 0
+
+    @classmethod
+    def from_graph(cls, graph, cached=False):
+        cls.made += 1
+        dg = cls()
+        dg.nodes = graph.num_nodes()
+        dg.edges = graph.num_edges()
+        return dg
+
+
+def test_snapshot_cache_never_resurrects_a_cleared_graph(rx, monkeypatch):
+    """clear() used to reset the mutation count to 0 while the old snapshot stayed
+    attached, so a rebuilt graph that reached the old count was answered from the old CSR."""
+    monkeypatch.setattr(rx, "DeviceGraph", _FakeDeviceGraph)
+    for cls in (rx.PyGraph, rx.PyDiGraph):
+        g = cls()
+        g.add_nodes_from(range(3))
+        g.add_edges_from_no_data([(0, 1), (1, 2)])
+        first = rx.device_snapshot(g)
+        assert rx.device_snapshot(g) is first  # unchanged graph: cache hit
+        stamp = g._version
+        g.clear()
+        assert g._version != stamp and g.num_nodes() == 0
+        g.add_nodes_from(range(5))  # the same NUMBER of mutations as before
+        second = rx.device_snapshot(g)
+        assert second is not first and second.nodes == 5
+        g.add_edge(0, 4, None)
+        assert rx.device_snapshot(g) is not second  # any mutation invalidates
+    # stamps are never handed out twice, not even across graphs
+    a, b = rx.PyGraph(), rx.PyGraph()
+    assert a._version != b._version
+
+
+def test_graphs_pickle_and_deepcopy_after_a_snapshot(rx, monkeypatch):
+    """the cached device handle used to live in the graph's __dict__, which made
+    pickle / deepcopy fail after any centrality call.  The reference containers support both."""
+    import copy
+    import pickle
+
+    monkeypatch.setattr(rx, "DeviceGraph", _FakeDeviceGraph)
+    g = rx.PyDiGraph()
+    g.add_nodes_from(["a", "b", "c"])
+    g.add_edges_from([(0, 1, 1.5), (1, 2, 2.5)])
+    dg = rx.device_snapshot(g)
+    assert not any("rxc" in k for k in g.__dict__)
+    for clone in (pickle.loads(pickle.dumps(g)), copy.deepcopy(g), g.copy()):
+        assert clone.num_nodes() == 3 and list(clone.edge_list()) == [(0, 1), (1, 2)]
+        assert rx.device_snapshot(clone) is not dg  # a clone never shares the handle
+    assert rx.device_snapshot(g) is dg
+    rx.set_snapshot_cache(False)
+    try:
+        assert rx.device_snapshot(g) is not dg
+    finally:
+        rx.set_snapshot_cache(True)
+
+
+def test_generator_library_is_separate(rx):
+    """The benchmark input generators live in librxgen.so (include/rxgen.h), not in the product
+    library: bench.py's reference arm builds its graph without mapping librxcuda.so."""
+    from rustworkx_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "rxgen.h")).read()
+    declared = set(re.findall(r"\b(rxc_gen_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.GEN_SYMBOLS) and len(declared) == 3
+    G = _lib.gen_lib()
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(G, name)
+        assert not hasattr(L, name), f"{name} must not be exported by librxcuda.so"
+    g = rx.barabasi_albert_graph(500, 3, seed=5)
+    assert g.num_nodes() == 500 and g.num_edges() == 2 + 3 * 497
