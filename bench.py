@@ -3,23 +3,37 @@
 
 Workload (config.workload): ``betweenness_centrality`` on ``barabasi_albert_graph(1_000_000, 8,
 seed=1)`` -- BASELINE.json configs[2], the configuration the metric is quoted on; it fits one GPU.
-A *step* is one pass of the hot path over one batch of synthetic input: ``--sources-per-step``
-sources per GPU (forward BFS + sigma, backward dependency sweep, accumulation into the partial
-centrality vector).  Sources are sharded across ranks (weak scaling: per-GPU work is fixed), each rank
-accumulates a partial vector, and ONE NCCL reduce at the end of the timed region combines them.
+
+A *step* is one pass of the hot path over one batch of synthetic input: a FIXED set of
+``--sources-per-step`` sources (default 16384, a seeded uniform sample of the 10^6 sources of the
+full job), whatever the number of GPUs -- **strong scaling**.  The step's sources are dealt
+round-robin to the N ranks (one process per GPU, CSR replicated); every rank runs forward BFS + sigma
+and the dependency sweep for its share and accumulates a partial centrality vector in HBM; ONE
+in-place ``ncclReduce`` over NVLink combines the partial vectors and rank 0 reads the result back
+(``rxc_betweenness_partial_reduce``).  That is exactly the shape of the full job, cut to 1.6 % of it.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]          # our arm
     python bench.py --impl reference [...]                        # the reference's CPU algorithm
 
-* ``value``  : GTEPS with the graph snapshot already resident in HBM (device time, CUDA events on the
-               library's own stream, max over ranks).  TE = (source, arc) pairs traversed, counted
+* ``value``  : GTEPS with the graph snapshot already resident in HBM: TE of the K steps / device time
+               (CUDA events on the library's own stream around each call's kernels + the reduce,
+               summed over the steps, max over ranks).  TE = (source, arc) pairs traversed, counted
                once per source although Brandes sweeps each twice.
 * ``e2e``    : the same metric through the C-ABI with HOST buffers: every step re-snapshots the graph
-               from edge arrays in pinned host memory (H2D + device CSR build), runs the step and
-               reads the partial vector back into pinned host memory (D2H); wall clock around the calls.
-* ``roofline``: algorithmic bytes of the dominant kernel / its CUDA-event time, against the measured
-               HBM copy peak in MEASURED_PEAKS.json.
-* ``cpu_baseline``: the oracle port of the reference algorithm on the box's host cores (rank 0, N=1).
+               on every rank from edge arrays in pinned host memory (H2D + device CSR build), runs the
+               sharded step incl. the reduce and reads the vector back into pinned host memory on
+               rank 0; wall clock between barriers, max over ranks.
+* ``roofline``: the dominant kernel against the measured HBM copy peak (MEASURED_PEAKS.json), twice:
+               ``frac`` on ALGORITHMIC bytes (SURVEY 8d model) and ``frac_dram`` on the DRAM bytes ncu
+               counted for the same kernel (committed capture under profiles/), both over the kernel's
+               live CUDA-event time.
+* ``parity`` : correctness of THIS run's numbers, checked on rank 0 outside the timed region:
+               sum_v reduced[v] = sum_s sum_t (d(s,t) - 1) with the right-hand side from the bit-exact
+               distance kernel; at N > 1 the reduced vector against a single-GPU recomputation of the
+               same step; and a 4-source sample against the CPU oracle.
+* ``cpu_baseline``: the oracle port of the reference algorithm on the box's host cores (rank 0).
+* ``work.full_run_s`` (N = 8, or ``--full-run``): the whole job -- all 10^6 sources -- wall clock
+               between barriers incl. snapshot on every rank, reduce and read-back, with its invariant.
 """
 
 from __future__ import annotations
@@ -41,21 +55,26 @@ sys.path.insert(0, ROOT)
 METRIC = "all_sources_betweenness_gteps"
 UNIT = "GTEPS"
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+TRAFFIC_FILES = ("r02_traffic_step.json", "r01_traffic_batch1024.json")
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nodes", type=int, default=1_000_000)
     ap.add_argument("--m", type=int, default=8)
     ap.add_argument("--seed", type=int, default=1)
-    ap.add_argument("--sources-per-step", type=int, default=1024)
+    ap.add_argument("--sources-per-step", type=int, default=16384,
+                    help="sources of one step, summed over all GPUs (strong scaling)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="sources in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--full-run", action="store_true",
+                    help="also run the whole job (every vertex a source); default at --gpus 8")
     return ap.parse_args()
 
 
@@ -64,14 +83,30 @@ def dist_env():
             int(os.environ.get("WORLD_SIZE", "1")))
 
 
-def build_graph(args):
-    import rustworkx_b200 as rx
+def host_threads():
+    """Host cores this process may run on.  NOT omp_get_max_threads(): torchrun exports
+    OMP_NUM_THREADS=1, which made round 1's N >= 2 reference arm single-threaded."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
-    return rx.barabasi_albert_graph(args.nodes, args.m, seed=args.seed)
+
+def build_graph(args):
+    # librxgen.so only: the generators are not in the product library
+    from rustworkx_b200.random_graph import barabasi_albert_graph
+
+    return barabasi_albert_graph(args.nodes, args.m, seed=args.seed)
 
 
 def source_plan(n, seed=12345):
     return np.random.default_rng(seed).permutation(n).astype(np.uint32)
+
+
+def step_sources(plan, step, total):
+    n = plan.shape[0]
+    idx = np.arange(step * total, (step + 1) * total) % n
+    return plan[idx]
 
 
 def hbm_peak():
@@ -82,19 +117,22 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kernel, sources_per_step):
-    """dram__bytes_read.sum + dram__bytes_write.sum per (non-empty) launch of `kernel`, from the
-    committed `ncu --set full` capture of one 1024-source batch of this same workload (profiles/,
-    made with scripts/ncu_traffic.py)."""
-    name = "r01_traffic_batch1024.json"
-    path = os.path.join(ROOT, "profiles", name)
-    try:
-        with open(path) as f:
-            rec = json.load(f)[kernel]
-        return (rec["dram_bytes"] / max(1, rec["launches_nonempty"]),
-                f"profiles/{name} (ncu --set full, per non-empty launch of a 1024-source batch)")
-    except Exception:
-        return None, "no ncu capture committed"
+def ncu_traffic():
+    """DRAM bytes per SOURCE and kernel from the committed `ncu --set full` capture of this workload
+    (profiles/, made with scripts/ncu_traffic.py): {kernel: bytes_per_source}, provenance."""
+    for name in TRAFFIC_FILES:
+        path = os.path.join(ROOT, "profiles", name)
+        try:
+            with open(path) as f:
+                rec = json.load(f)
+            sources = int(rec.get("_sources", 1024))
+            out = {k: {"dram_bytes_per_source": v["dram_bytes"] / sources,
+                       "launches_nonempty": v.get("launches_nonempty")}
+                   for k, v in rec.items() if isinstance(v, dict) and "dram_bytes" in v}
+            return out, f"profiles/{name} (ncu --set full, {sources}-source capture of this workload)"
+        except Exception:
+            continue
+    return {}, "no ncu capture committed"
 
 
 class ClockSampler:
@@ -150,10 +188,14 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # CPU legs: the oracle port of the reference algorithm (the only place bench.py executes oracle/)
 # --------------------------------------------------------------------------------------------------
-def workload_name(args):
-    """config.workload, identical on both arms"""
-    return (f"betweenness_centrality on barabasi_albert_graph({args.nodes}, {args.m}, "
-            f"seed={args.seed}) [BASELINE.json configs[2]]")
+def workload_config(args, graph):
+    """`config`, identical on both arms (the driver compares it key by key)"""
+    return {
+        "workload": (f"betweenness_centrality on barabasi_albert_graph({args.nodes}, {args.m}, "
+                     f"seed={args.seed}) [BASELINE.json configs[2]]"),
+        "nodes": graph.num_nodes(), "edges": graph.num_edges(),
+        "sources": "seeded uniform sample of the graph's sources (numpy default_rng(12345) permutation)",
+    }
 
 
 def cpu_oracle_graph(graph):
@@ -163,11 +205,11 @@ def cpu_oracle_graph(graph):
     return oracle, oracle.OracleGraph.from_graph(graph)
 
 
-def cpu_sample_run(oracle, og, sources, threads):
+def cpu_sample_run(og, sources, threads):
     t0 = time.perf_counter()
-    _, st = og.betweenness_partial(sources, False, threads=threads)
+    vec, st = og.betweenness_partial(sources, False, threads=threads)
     dt = time.perf_counter() - t0
-    return st["te"] / dt / 1e9, dt, st
+    return st["te"] / dt / 1e9, dt, st, vec
 
 
 def run_reference(args):
@@ -176,34 +218,34 @@ def run_reference(args):
         return  # rank 0 alone runs the CPU arm
     graph = build_graph(args)
     oracle, og = cpu_oracle_graph(graph)
-    threads = oracle.max_threads()
+    threads = host_threads()
     plan = source_plan(graph.num_nodes())
     per_step = args.cpu_sample or 2 * threads
     times, te = [], 0
     for step in range(args.warmup + args.steps):
-        src = plan[step * per_step:(step + 1) * per_step]
-        gteps, dt, st = cpu_sample_run(oracle, og, src, threads)
+        src = plan[-(step + 1) * per_step: plan.shape[0] - step * per_step]
+        gteps, dt, st, _ = cpu_sample_run(og, src, threads)
         if step >= args.warmup:
             times.append(dt)
             te += st["te"]
     total = sum(times)
     value = te / total / 1e9
-    sample = (f"{per_step} sources/step x {args.steps} steps of BA({args.nodes},{args.m}) "
-              f"(uniform random sample, seed 12345)")
+    sample = (f"{per_step} sources/step x {args.steps} steps (uniform random sample of the same graph, "
+              f"{total:.1f} s of wall clock on {threads} threads)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(args), "nodes": graph.num_nodes(),
-                   "edges": graph.num_edges(), "sources_per_step": per_step,
-                   "timing": "wall clock around the oracle call, all host threads"},
+        "config": workload_config(args, graph),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": sample},
+                         "sample": sample, "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "work": {"sources_per_step": per_step, "timing": "wall clock around the oracle call, all host threads"},
         "note": "reference Rust crate cannot be built here (no cargo/rustc); this is oracle/ (C "
-                "restatement, OpenMP over sources, one global lock as in centrality.rs:107,280)",
+                "restatement at -O3, OpenMP over sources with an explicit thread count, one global "
+                "lock as in centrality.rs:107,280)",
     }
     emit(line)
 
@@ -211,6 +253,12 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
+def rel_err(got, want):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    return float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-12))) if got.size else 0.0
+
+
 def run_b200(args):
     rank, local_rank, world = dist_env()
     from rustworkx_b200 import _lib
@@ -232,16 +280,21 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def allreduce(vals, op):
+        if dist is None:
+            return list(vals)
+        t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
+        return t.tolist()
+
     graph = build_graph(args)
     n = graph.num_nodes()
     snap = graph._snapshot_arrays()
     plan = source_plan(n)
-    S = args.sources_per_step
+    T = args.sources_per_step
 
-    def sources_for(step):
-        i = (step * world + rank) * S
-        idx = np.arange(i, i + S) % n
-        return np.ascontiguousarray(plan[idx])
+    def my_sources(step):
+        return np.ascontiguousarray(step_sources(plan, step, T)[rank::world])
 
     # Host inputs live in page-locked memory (rxc_host_alloc), as a binding that assembles the edge
     # arrays itself would hold them: the snapshot's H2D is then one DMA per array.  A graph from which
@@ -256,7 +309,7 @@ def run_b200(args):
                                 host_in["edge_src"], host_in["edge_dst"], host_in["edge_id"],
                                 snap["directed"])
 
-    # multi-GPU: our own NCCL communicator for the single end-of-run reduce
+    # multi-GPU: our own NCCL communicator for the one collective of the path
     if world > 1:
         ident = np.zeros(128, dtype=np.uint8)
         if rank == 0:
@@ -265,71 +318,58 @@ def run_b200(args):
         dist.broadcast(t, 0)
         ident = t.cpu().numpy().copy()
         _lib.check(_lib.lib().rxc_comm_init(rank, world, _lib.p_u8(ident)))
-        # The first collective of a given size class pays NCCL's lazy connection set-up (hundreds of
-        # ms; a small warm-up does not cover the protocol the 8 MB reduce uses): warm the communicator
-        # with a vector of the real length, before the timed region.
-        warm = np.zeros(max(int(snap["n_bound"]), 1), dtype=np.float64)
-        for _ in range(2):
-            _lib.check(_lib.lib().rxc_comm_reduce_sum_f64(_lib.p_f64(warm), warm.shape[0], 0))
 
     dg = make_device_graph()  # inputs resident in HBM before the timed region
-    partial = np.zeros(snap["n_bound"], dtype=np.float64)
 
+    def run_step(handle, step, out):
+        """one sharded step: this rank's share -> partial vector in HBM -> ncclReduce -> rank 0"""
+        return handle.betweenness_partial_reduce(my_sources(step), False, root=0, out=out)
+
+    # warm-up: also pays NCCL's lazy connection set-up for a vector of the real length
     for step in range(args.warmup):
-        dg.betweenness_partial(sources_for(step), False)
+        run_step(dg, step, host_out)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     agg = {"te": 0, "te_dag": 0, "v": 0, "launches": 0, "ms_total": 0.0, "ms_forward": 0.0,
-           "ms_backward": 0.0, "levels": 0, "batches": 0}
+           "ms_backward": 0.0, "ms_reduce": 0.0, "levels": 0, "batches": 0, "sources": 0}
+    last_vec = None
     barrier()
     wall0 = time.perf_counter()
     for step in range(args.warmup, args.warmup + args.steps):
-        partial += dg.betweenness_partial(sources_for(step), False)
+        vec = run_step(dg, step, host_out)
         st = dg.stats()
         for k in agg:
             agg[k] += st[k]
-    reduce_ms = 0.0
-    if world > 1:
-        t0 = time.perf_counter()
-        _lib.check(_lib.lib().rxc_comm_reduce_sum_f64(_lib.p_f64(partial), partial.shape[0], 0))
-        reduce_ms = 1e3 * (time.perf_counter() - t0)
+        if rank == 0 and step == args.warmup + args.steps - 1:
+            last_vec = np.array(vec, copy=True)
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
 
-    device_ms = agg["ms_total"] + reduce_ms  # CUDA-event time of the K steps (+ the reduce)
-    if world > 1:
-        tm = torch.tensor([device_ms, wall * 1e3], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        cnt = torch.tensor([agg["te"], agg["te_dag"], agg["v"], agg["launches"]], dtype=torch.float64,
-                           device="cuda")
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        device_ms_max, wall_ms_max = tm.tolist()
-        te_all, dag_all, v_all, launches_all = cnt.tolist()
-    else:
-        device_ms_max, wall_ms_max = device_ms, wall * 1e3
-        te_all, dag_all, v_all, launches_all = agg["te"], agg["te_dag"], agg["v"], agg["launches"]
+    device_ms = agg["ms_total"] + agg["ms_reduce"]  # CUDA-event time of the K steps incl. the reduce
+    device_ms_max, wall_ms_max = allreduce([device_ms, wall * 1e3], "MAX")
+    te_all, dag_all, v_all, launches_all, src_all = allreduce(
+        [agg["te"], agg["te_dag"], agg["v"], agg["launches"], agg["sources"]], "SUM")
     value = te_all / (device_ms_max * 1e-3) / 1e9
 
-    # ---- e2e: C-ABI with host buffers, snapshot + step + readback per step -----------------------
+    # ---- e2e: C-ABI with host buffers; snapshot + sharded step + reduce + readback per step --------
     e2e = None
     if not args.no_e2e:
         e2e_steps = max(1, args.steps)
         for step in range(2):  # warm-up: the pinned staging slots and the pool's second workspace
             g2 = make_device_graph()
-            g2.betweenness_partial(sources_for(step), False, out=host_out)
+            run_step(g2, step, host_out)
             g2.close()
         barrier()
         t0 = time.perf_counter()
         te_e2e = 0
         phase = [0.0, 0.0, 0.0]  # wall clock of snapshot / call / free, summed over the steps
         for step in range(e2e_steps):
-            src_step = sources_for(args.warmup + step)
             ta = time.perf_counter()
             g2 = make_device_graph()
             tb = time.perf_counter()
-            g2.betweenness_partial(src_step, False, out=host_out)
+            run_step(g2, args.warmup + step, host_out)
             tc_ = time.perf_counter()
             te_e2e += g2.stats()["te"]
             g2.close()
@@ -339,21 +379,63 @@ def run_b200(args):
             phase[2] += td - tc_
         barrier()
         dt = time.perf_counter() - t0
-        if world > 1:
-            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = tt.item()
-            tc = torch.tensor([float(te_e2e)], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tc, op=dist.ReduceOp.SUM)
-            te_e2e = tc.item()
-        # live nodes + (src, dst[, id]) per edge + sources
-        h2d = 4 * n + (8 if ids_are_positions else 12) * graph.num_edges() + 4 * S
-        e2e = {"value": te_e2e / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+        (dt,) = allreduce([dt], "MAX")
+        (te_e2e,) = allreduce([float(te_e2e)], "SUM")
+        # per rank: live nodes + (src, dst[, id]) per edge + its share of the sources
+        h2d = 4 * n + (8 if ids_are_positions else 12) * graph.num_edges() + 4 * len(my_sources(0))
+        e2e = {"value": te_e2e / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d * world),
                "d2h_bytes_per_step": int(8 * n), "steps": e2e_steps,
                "ms_per_step": {"snapshot": 1e3 * phase[0] / e2e_steps, "call": 1e3 * phase[1] / e2e_steps,
                                "free": 1e3 * phase[2] / e2e_steps, "total": 1e3 * dt / e2e_steps},
-               "includes": "H2D of the edge list from pinned host memory + device CSR build + kernels "
-                           "+ D2H of the partial vector into pinned host memory"}
+               "includes": "on every rank H2D of the edge list from pinned host memory + device CSR build "
+                           "+ kernels; the in-HBM ncclReduce; D2H of the vector into pinned host memory "
+                           "on rank 0"}
+
+    # ---- the whole job (every vertex a source), N = 8 or --full-run ------------------------------
+    full = None
+    if args.full_run or world == 8:
+        mine = np.ascontiguousarray(np.arange(rank, n, world, dtype=np.uint32))
+        barrier()
+        t0 = time.perf_counter()
+        g3 = make_device_graph()
+        vec = g3.betweenness_partial_reduce(mine, False, root=0, out=host_out)
+        barrier()
+        full_s = time.perf_counter() - t0
+        st = g3.stats()
+        (full_dev_ms,) = allreduce([st["ms_total"] + st["ms_reduce"]], "MAX")
+        (full_te,) = allreduce([float(st["te"])], "SUM")
+        # invariant: sum_v bc[v] = sum_s sum_t (d(s,t) - 1), right-hand side from the distance kernel
+        cc = g3.closeness_partial(mine, wf_improved=False)
+        rhs_part = float(np.sum(np.rint((n - 1) / cc) - (n - 1)))
+        (rhs,) = allreduce([rhs_part], "SUM")
+        g3.close()
+        if rank == 0:
+            got = float(np.sum(vec))
+            full = {"full_run_s": full_s, "full_run_device_s": full_dev_ms * 1e-3,
+                    "full_run_gteps_wall": full_te / full_s / 1e9, "full_run_sources": n,
+                    "full_run_invariant_rel_err": abs(got - rhs) / rhs,
+                    "full_run_includes": "snapshot on every rank, all kernels, ncclReduce, D2H on rank 0"}
+
+    # ---- parity of this run (outside the timed region) -------------------------------------------
+    parity = None
+    if not args.no_parity:
+        last = args.warmup + args.steps - 1
+        cc = dg.closeness_partial(my_sources(last), wf_improved=False)  # bit-exact distance kernel
+        (rhs,) = allreduce([float(np.sum(np.rint((n - 1) / cc) - (n - 1)))], "SUM")
+        if rank == 0:
+            parity = {"invariant": "sum_v reduced[v] == sum_s sum_t (d(s,t)-1) over the last step's sources",
+                      "invariant_rel_err": abs(float(np.sum(last_vec)) - rhs) / rhs, "n_ranks": world}
+            if world > 1:  # the reduced vector of N ranks against one GPU doing the whole step alone
+                alone = dg.betweenness_partial(step_sources(plan, last, T), False)
+                parity["vs_single_gpu_max_rel_err"] = rel_err(last_vec, alone)
+            oracle, og = cpu_oracle_graph(graph)
+            src4 = np.ascontiguousarray(step_sources(plan, last, T)[:4])
+            want, _ = og.betweenness_partial(src4, False, threads=min(4, host_threads()))
+            parity["oracle_sample"] = {"sources": 4, "max_rel_err": rel_err(dg.betweenness_partial(src4, False), want)}
+            errs = [parity["invariant_rel_err"], parity["oracle_sample"]["max_rel_err"],
+                    parity.get("vs_single_gpu_max_rel_err", 0.0)]
+            parity["tolerance"] = 1e-9
+            parity["ok"] = bool(all(e <= 1e-9 for e in errs))
 
     if rank != 0:
         if dist is not None:
@@ -365,59 +447,82 @@ def run_b200(args):
     te, dag, v = agg["te"], agg["te_dag"], agg["v"]  # this rank's counts / times
     bytes_fwd = 8 * te + 8 * dag + 20 * v
     bytes_bwd = 8 * te + 16 * dag + 24 * v
+    useful_fwd = 4 * te + 4 * dag + 8 * v     # col; one uint32 path count per DAG arc; own count + mask
+    useful_bwd = 4 * te + 8 * dag + 20 * v    # col; one f64 coefficient per DAG arc; own sigma, row, score
+    traffic, traffic_src = ncu_traffic()
     kernels = {
-        "bc_forward_kernel": {"ms": agg["ms_forward"], "bytes": bytes_fwd},
-        "bc_backward_kernel": {"ms": agg["ms_backward"], "bytes": bytes_bwd},
+        "bc_forward_kernel": {"ms": agg["ms_forward"], "bytes": bytes_fwd, "useful": useful_fwd},
+        "bc_backward_kernel": {"ms": agg["ms_backward"], "bytes": bytes_bwd, "useful": useful_bwd},
     }
+    for k, kv in kernels.items():
+        per_src = traffic.get(k, {}).get("dram_bytes_per_source")
+        kv["dram"] = per_src * agg["sources"] if per_src else None
     dom = max(kernels, key=lambda k: kernels[k]["ms"])
-    achieved = kernels[dom]["bytes"] / (kernels[dom]["ms"] * 1e-3) / 1e9
-    whole = (bytes_fwd + bytes_bwd) / (agg["ms_total"] * 1e-3) / 1e9
-    traffic, traffic_src = ncu_traffic(dom, S)
+
+    def gbs(b, ms):
+        return b / (ms * 1e-3) / 1e9 if (b is not None and ms) else None
+
+    achieved = gbs(kernels[dom]["bytes"], kernels[dom]["ms"])
+    dram_rate = gbs(kernels[dom]["dram"], kernels[dom]["ms"])
+    whole = gbs(bytes_fwd + bytes_bwd, agg["ms_total"])
+    dram_all = None if any(kv["dram"] is None for kv in kernels.values()) else sum(kv["dram"] for kv in kernels.values())
+    launches_dom = max(1, agg["levels"])
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-        "algorithmic_bytes_per_launch": kernels[dom]["bytes"] / max(1, agg["levels"]),
+        "frac": achieved / peak,
+        "frac_dram": dram_rate / peak if dram_rate else None,
+        "achieved_dram": dram_rate,
+        "traffic": kernels[dom]["dram"] / launches_dom if kernels[dom]["dram"] else None,
+        "traffic_source": traffic_src,
+        "algorithmic_bytes_per_launch": kernels[dom]["bytes"] / launches_dom,
+        "useful_bytes_per_launch": kernels[dom]["useful"] / launches_dom,
+        "launches": launches_dom,
         "peak_source": peak_src,
+        "note": "frac = SURVEY 8d algorithmic bytes / live CUDA-event time / peak (a MODEL fraction: the "
+                "uint32 path counts and 128-source rows move fewer bytes than the per-source model); "
+                "frac_dram = DRAM bytes ncu counted for this kernel (per source, committed capture) / the "
+                "same live time / peak = how busy HBM really is; useful = bytes of values actually consumed",
         "whole_step": {"achieved": whole, "frac": whole / peak,
+                       "frac_dram": gbs(dram_all, agg["ms_total"]) / peak if dram_all else None,
                        "bytes_model": "16*TE + 24*TE_dag + 44*V"},
         "frac_of_8TBs_nominal": achieved / 8000.0,
-        "per_kernel": {k: {"GBs": kv["bytes"] / (kv["ms"] * 1e-3) / 1e9 if kv["ms"] else None,
-                           "ms": kv["ms"]} for k, kv in kernels.items()},
+        "per_kernel": {k: {"ms": kv["ms"], "GBs_model": gbs(kv["bytes"], kv["ms"]),
+                           "GBs_dram": gbs(kv["dram"], kv["ms"]), "GBs_useful": gbs(kv["useful"], kv["ms"])}
+                       for k, kv in kernels.items()},
     }
 
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
+    if not args.no_cpu_baseline:
         oracle, og = cpu_oracle_graph(graph)
-        threads = oracle.max_threads()
+        threads = host_threads()
         k = args.cpu_sample or 2 * threads
-        src = plan[-k:]
-        gteps, dt, st = cpu_sample_run(oracle, og, src, threads)
+        gteps, dt, st, _ = cpu_sample_run(og, plan[-k:], threads)
         if dt < 8.0:  # grow the sample to roughly 10-30 s of CPU work
             k2 = int(min(n, max(k, k * 15.0 / max(dt, 1e-3))))
-            k2 = max(threads, (k2 // threads) * threads)
-            src = plan[-k2:]
-            gteps, dt, st = cpu_sample_run(oracle, og, src, threads)
-            k = k2
+            k = max(threads, (k2 // threads) * threads)
+            gteps, dt, st, _ = cpu_sample_run(og, plan[-k:], threads)
         cpu_baseline = {"value": gteps, "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": f"{k} uniformly sampled sources of the same graph, {dt:.1f} s",
                         "extrapolated_full_run_s": n * 2.0 * graph.num_edges() / (gteps * 1e9)}
 
+    work = {"te": te_all, "te_dag": dag_all, "v": v_all, "levels": agg["levels"],
+            "batches": agg["batches"], "wall_ms": wall_ms_max, "reduce_ms_per_step": agg["ms_reduce"] / max(args.steps, 1),
+            "sources_per_step": T, "sources_per_step_per_gpu": int(src_all / max(args.steps, 1) / world),
+            "host_gap_ms_per_step": (wall_ms_max - device_ms_max) / max(args.steps, 1),
+            "sharding": f"each step's {T} sources dealt round-robin to {world} rank(s), CSR replicated, "
+                        "one in-HBM ncclReduce per step",
+            "l2": "inputs larger than L2 (per-batch state >= 2 GB vs 126 MB L2)",
+            "timing": "CUDA events on the library stream (rxc_stats.ms_total + ms_reduce), max over ranks"}
+    if full:
+        work.update(full)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": device_ms_max / max(args.steps, 1),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {
-            "workload": workload_name(args),
-            "nodes": n, "edges": graph.num_edges(), "sources_per_step_per_gpu": S,
-            "sharding": f"sources sharded over {world} rank(s), CSR replicated, one NCCL reduce at end",
-            "l2": "inputs larger than L2 (per-batch state >= 2 GB vs 126 MB L2)",
-            "timing": "CUDA events on the library stream (rxc_stats.ms_total), max over ranks",
-        },
+        "config": workload_config(args, graph),
         "e2e": e2e, "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roofline,
-        "cpu_baseline": cpu_baseline,
-        "work": {"te": te_all, "te_dag": dag_all, "v": v_all, "levels": agg["levels"],
-                 "batches": agg["batches"], "wall_ms": wall_ms_max, "reduce_ms": reduce_ms},
+        "cpu_baseline": cpu_baseline, "parity": parity, "work": work,
     }
     emit(line)
     if dist is not None:
