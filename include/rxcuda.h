@@ -209,10 +209,10 @@ int rxc_get_stats(const rxc_graph *g, rxc_stats *out);
  *                      2 CTA-per-source in shared memory, 3 128-source masks bottom-up
  *   bfs_depth_switch N auto: pilot BFS deeper than N levels -> regime 2 (48)
  *   bfs_ell 0|1        regime 2: one uint4 per vertex when no vertex has more than 4 arcs (1)
- *   bc_order 0|1|2     betweenness: sort the sources of a call by two-hop neighbourhood size so that
- *                      sources with similar level structure share a group and a DRAM sector (1);
- *                      2 (experimental): calls with >= 4096 sources sort by (highest-degree
- *                      neighbour, that key) -- simulated, not yet measured
+ *   bc_order 0|1|2     betweenness: which sources share a group and a DRAM sector.  1: sort the
+ *                      sources of a call by two-hop neighbourhood size (similar level structure);
+ *                      2 (default): the same, and calls with >= 4096 sources sort by (highest-degree
+ *                      neighbour, that key) so that siblings of a hub share a lane; 0: caller's order
  *   bfs_threads N      regime 2: threads per CTA (0: 1024 for n >= 2^18, else 256)
  *   bfs_groups N       regime 1: groups of 32 sources per batch (0: up to 4096)
  *   device_csr 0|1     build the CSR on the device (1) or with the host counting sort (0)

@@ -817,11 +817,16 @@ __device__ __forceinline__ void bc_bwd_finish(const BcParams &p, uint32_t v, con
                                               const double (&sig)[BK], const double (&acc)[BK],
                                               double *rows, PEntry *Pcur, uint32_t tag_cur,
                                               uint32_t level, int lane) {
+    // The sums start at -0.0 and every gathered term is +0.0, positive or NaN, so a sum that is still
+    // -0.0 had NO successor on the next level: the reference never touches delta[v] then and it stays
+    // 0 (centrality.rs:271-279) -- even when sigma[v] overflowed to +inf, where sigma * 0 would be NaN
+    // (tests: test_sigma_overflow_to_infinity_matches_the_reference_nan_pattern).
     double contrib = 0.0;
 #pragma unroll
     for (int k = 0; k < BK; k++) {
         if ((fm.w[k] >> lane) & 1u) {
-            const double delta = EDGE ? acc[k] : sig[k] * acc[k];
+            const bool leaf = acc[k] == 0.0 && signbit(acc[k]);
+            const double delta = leaf ? 0.0 : (EDGE ? acc[k] : sig[k] * acc[k]);
             rows[(size_t)v * BG + lane * BK + k] = (1.0 + delta) / sig[k];
             if (!EDGE && level > 0) contrib += ENDPOINTS ? delta + 1.0 : delta;
         }
@@ -871,7 +876,7 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) bc_backward_kernel(BcPar
         }
         if (e1 - e0 > p.hub_degree && bc_defer_hub(p, level, g, v, fm)) continue;
         const Row4 sg = bc_load_sigma<NARROW>(p, gn, v, lane, (mask_or(fm) >> lane) & 1u);
-        double acc[BK] = {0.0, 0.0, 0.0, 0.0};
+        double acc[BK] = {-0.0, -0.0, -0.0, -0.0};  // -0.0: "nothing added yet", see bc_bwd_finish
         bc_bwd_scan<EDGE>(p, rows, Pnext, tag_next, e0, e1, 0, 32, fm, sg.x, lane, stage, acc, dag);
         bc_bwd_finish<EDGE, ENDPOINTS>(p, v, fm, sg.x, acc, rows, Pcur, tag_cur, level, lane);
     }
@@ -910,7 +915,7 @@ __global__ void __launch_bounds__(BLOCK) bc_backward_hub_kernel(BcParams p, uint
         const Mask128 fm = mask_load(&p.hubm[(size_t)g * p.hubcap + h]);
         const uint32_t e0 = p.row[v], e1 = p.row[v + 1];
         const Row4 sg = bc_load_sigma<NARROW>(p, gn, v, lane, (mask_or(fm) >> lane) & 1u);
-        double acc[BK] = {0.0, 0.0, 0.0, 0.0};
+        double acc[BK] = {-0.0, -0.0, -0.0, -0.0};
         unsigned long long dag = 0;
         bc_bwd_scan<EDGE>(p, rows, Pnext, tag_next, e0, e1, wid * 32, WARPS * 32, fm, sg.x, lane,
                           stage, acc, dag);
@@ -921,7 +926,7 @@ __global__ void __launch_bounds__(BLOCK) bc_backward_hub_kernel(BcParams p, uint
         if (lane == 0) s_dag[wid] = dag;
         __syncthreads();
         if (wid == 0) {
-            double tot[BK] = {0.0, 0.0, 0.0, 0.0};
+            double tot[BK] = {-0.0, -0.0, -0.0, -0.0};  // stays -0.0 only if every warp's sum is -0.0
             unsigned long long d = 0;
             for (int q = 0; q < WARPS; q++) {
 #pragma unroll

@@ -6,8 +6,10 @@ contributions are additive over sources, so here every rank
 
 1. snapshots the whole graph onto its own GPU (the CSR is small: 68 MB for the 1M-node config),
 2. runs ``rxc_*_partial`` on its round-robin shard of the live sources,
-3. takes part in a single sum-reduce of the partial vector (``rxc_comm_reduce_sum_f64`` = ncclReduce
-   over NVLink; with a ``gloo`` process group -- the CPU tests -- ``torch.distributed.reduce``),
+3. takes part in a single sum-reduce of the partial vector: on GPUs the fused
+   ``rxc_*_partial_reduce`` (the vector stays in HBM, one in-place ncclReduce over NVLink on the
+   handle's stream, only the root reads it back); with a ``gloo`` process group -- the CPU tests --
+   ``torch.distributed.reduce`` of the host vector,
 
 and rank 0 applies ``_rescale`` (``centrality.rs:221-252``).  Closeness and distance-matrix outputs
 are disjoint per source, so they need no reduction, only a gather of slices.
@@ -77,6 +79,23 @@ def reduce_partial(partial, root=0):
     return t.numpy()
 
 
+def _nccl_group():
+    dist = _dist()
+    return dist is not None and dist.get_world_size() > 1 and dist.get_backend() == "nccl"
+
+
+def _reduced_on_device(graph, kind, mine, endpoints):
+    """The fused call: shard -> partial vector in HBM -> in-place ncclReduce -> root reads it back
+    (``rxc_*_partial_reduce``); the vector never visits the host before it is combined."""
+    from . import device_snapshot
+
+    init_nccl_comm()
+    dg = device_snapshot(graph)
+    if kind == "node":
+        return dg.betweenness_partial_reduce(mine, endpoints, root=0)
+    return dg.edge_betweenness_partial_reduce(mine, root=0)
+
+
 def _device_partial(graph, kind):
     from . import device_snapshot
 
@@ -101,9 +120,11 @@ def betweenness_centrality(graph, normalized=True, endpoints=False, *, rank=None
         world = dist.get_world_size() if dist else 1
     snap = graph._snapshot_arrays()
     mine = shard_sources(snap["live_nodes"], rank, world)
-    fn = compute_partial or _device_partial(graph, "node")
-    partial = fn(mine, bool(endpoints))
-    total = reduce_partial(partial)
+    if compute_partial is None and _nccl_group():
+        total = _reduced_on_device(graph, "node", mine, bool(endpoints))
+    else:
+        fn = compute_partial or _device_partial(graph, "node")
+        total = reduce_partial(fn(mine, bool(endpoints)))
     if rank != 0:
         return None
     return _lib.rescale(total.copy(), snap["live_nodes"].shape[0], normalized, snap["directed"],
@@ -120,8 +141,11 @@ def edge_betweenness_centrality(graph, normalized=True, *, rank=None, world=None
         world = dist.get_world_size() if dist else 1
     snap = graph._snapshot_arrays()
     mine = shard_sources(snap["live_nodes"], rank, world)
-    fn = compute_partial or _device_partial(graph, "edge")
-    total = reduce_partial(fn(mine, False))
+    if compute_partial is None and _nccl_group():
+        total = _reduced_on_device(graph, "edge", mine, False)
+    else:
+        fn = compute_partial or _device_partial(graph, "edge")
+        total = reduce_partial(fn(mine, False))
     if rank != 0:
         return None
     # edge betweenness always rescales with include_endpoints=true (centrality.rs:211-217)
