@@ -5,12 +5,13 @@ Workload (config.workload): ``betweenness_centrality`` on ``barabasi_albert_grap
 seed=1)`` -- BASELINE.json configs[2], the configuration the metric is quoted on; it fits one GPU.
 
 A *step* is one pass of the hot path over one batch of synthetic input: a FIXED set of
-``--sources-per-step`` sources (default 16384, a seeded uniform sample of the 10^6 sources of the
-full job), whatever the number of GPUs -- **strong scaling**.  The step's sources are dealt
-round-robin to the N ranks (one process per GPU, CSR replicated); every rank runs forward BFS + sigma
+``--sources-per-step`` sources (default 65536, a seeded uniform sample of the 10^6 sources of the
+full job), whatever the number of GPUs -- **strong scaling**.  The step's sources are put into the
+library's grouping order and cut into N contiguous slices, one per rank (one process per GPU, CSR
+replicated); every rank runs forward BFS + sigma
 and the dependency sweep for its share and accumulates a partial centrality vector in HBM; ONE
 in-place ``ncclReduce`` over NVLink combines the partial vectors and rank 0 reads the result back
-(``rxc_betweenness_partial_reduce``).  That is exactly the shape of the full job, cut to 1.6 % of it.
+(``rxc_betweenness_partial_reduce``).  That is exactly the shape of the full job, cut to 6.5 % of it.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]          # our arm
     python bench.py --impl reference [...]                        # the reference's CPU algorithm
@@ -67,7 +68,7 @@ def parse_args():
     ap.add_argument("--nodes", type=int, default=1_000_000)
     ap.add_argument("--m", type=int, default=8)
     ap.add_argument("--seed", type=int, default=1)
-    ap.add_argument("--sources-per-step", type=int, default=16384,
+    ap.add_argument("--sources-per-step", type=int, default=65536,
                     help="sources of one step, summed over all GPUs (strong scaling)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="sources in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -293,8 +294,13 @@ def run_b200(args):
     plan = source_plan(n)
     T = args.sources_per_step
 
-    def my_sources(step):
-        return np.ascontiguousarray(step_sources(plan, step, T)[rank::world])
+    def my_sources(step, handle=None):
+        """This rank's share of the step: a contiguous slice of the library's grouping order of the
+        step's sources (every rank computes the same order), so sibling clusters stay on one rank."""
+        from rustworkx_b200.distributed import contiguous_shard
+
+        ordered = (handle or dg).betweenness_source_order(step_sources(plan, step, T))
+        return contiguous_shard(ordered, rank, world)
 
     # Host inputs live in page-locked memory (rxc_host_alloc), as a binding that assembles the edge
     # arrays itself would hold them: the snapshot's H2D is then one DMA per array.  A graph from which
@@ -321,9 +327,14 @@ def run_b200(args):
 
     dg = make_device_graph()  # inputs resident in HBM before the timed region
 
+    order_ms = [0.0]
+
     def run_step(handle, step, out):
-        """one sharded step: this rank's share -> partial vector in HBM -> ncclReduce -> rank 0"""
-        return handle.betweenness_partial_reduce(my_sources(step), False, root=0, out=out)
+        """one sharded step: order the step's sources, take this rank's slice -> partial vector in
+        HBM -> ncclReduce -> rank 0"""
+        mine = my_sources(step, handle)
+        order_ms[0] = handle.stats()["ms_total"]  # device time of the ordering kernels
+        return handle.betweenness_partial_reduce(mine, False, root=0, out=out)
 
     # warm-up: also pays NCCL's lazy connection set-up for a vector of the real length
     for step in range(args.warmup):
@@ -341,6 +352,7 @@ def run_b200(args):
         st = dg.stats()
         for k in agg:
             agg[k] += st[k]
+        agg["ms_total"] += order_ms[0]
         if rank == 0 and step == args.warmup + args.steps - 1:
             last_vec = np.array(vec, copy=True)
     barrier()
@@ -394,10 +406,12 @@ def run_b200(args):
     # ---- the whole job (every vertex a source), N = 8 or --full-run ------------------------------
     full = None
     if args.full_run or world == 8:
-        mine = np.ascontiguousarray(np.arange(rank, n, world, dtype=np.uint32))
+        from rustworkx_b200.distributed import contiguous_shard
+
         barrier()
         t0 = time.perf_counter()
         g3 = make_device_graph()
+        mine = contiguous_shard(g3.betweenness_source_order(np.arange(n, dtype=np.uint32)), rank, world)
         vec = g3.betweenness_partial_reduce(mine, False, root=0, out=host_out)
         barrier()
         full_s = time.perf_counter() - t0
@@ -509,8 +523,8 @@ def run_b200(args):
             "batches": agg["batches"], "wall_ms": wall_ms_max, "reduce_ms_per_step": agg["ms_reduce"] / max(args.steps, 1),
             "sources_per_step": T, "sources_per_step_per_gpu": int(src_all / max(args.steps, 1) / world),
             "host_gap_ms_per_step": (wall_ms_max - device_ms_max) / max(args.steps, 1),
-            "sharding": f"each step's {T} sources dealt round-robin to {world} rank(s), CSR replicated, "
-                        "one in-HBM ncclReduce per step",
+            "sharding": f"each step's {T} sources in the library's grouping order, cut into {world} contiguous "
+                        "slice(s), CSR replicated, one in-HBM ncclReduce per step",
             "l2": "inputs larger than L2 (per-batch state >= 2 GB vs 126 MB L2)",
             "timing": "CUDA events on the library stream (rxc_stats.ms_total + ms_reduce), max over ranks"}
     if full:

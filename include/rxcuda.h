@@ -193,6 +193,14 @@ int rxc_comm_reduce_sum_f64(double *host_inout, uint64_t len, int root);
  * without a communicator it is rxc_*_partial.  rxc_stats.ms_reduce times the collective. */
 int rxc_betweenness_partial_reduce(rxc_graph *g, const uint32_t *sources, uint64_t n_sources,
                                    int include_endpoints, int root, double *out);
+/* The order in which the betweenness calls group a source list (option bc_order): sources whose
+ * searches have a similar level structure -- siblings of a hub first -- end up next to each other and
+ * share a group and a DRAM sector.  Contributions are additive over sources, so the order never
+ * changes results.  A multi-process run orders the whole list once and gives every rank a CONTIGUOUS
+ * slice of it (rustworkx_b200/distributed.py), which keeps the clusters intact on every rank;
+ * ordering a slice again changes nothing.  ordered[n_sources]: original node indices. */
+int rxc_betweenness_source_order(rxc_graph *g, const uint32_t *sources, uint64_t n_sources,
+                                 uint32_t *ordered);
 int rxc_edge_betweenness_partial_reduce(rxc_graph *g, const uint32_t *sources, uint64_t n_sources,
                                         int root, double *out);
 int rxc_comm_barrier(void);
@@ -209,10 +217,10 @@ int rxc_get_stats(const rxc_graph *g, rxc_stats *out);
  *                      2 CTA-per-source in shared memory, 3 128-source masks bottom-up
  *   bfs_depth_switch N auto: pilot BFS deeper than N levels -> regime 2 (48)
  *   bfs_ell 0|1        regime 2: one uint4 per vertex when no vertex has more than 4 arcs (1)
- *   bc_order 0|1|2     betweenness: which sources share a group and a DRAM sector.  1: sort the
- *                      sources of a call by two-hop neighbourhood size (similar level structure);
- *                      2 (default): the same, and calls with >= 4096 sources sort by (highest-degree
- *                      neighbour, that key) so that siblings of a hub share a lane; 0: caller's order
+ *   bc_order 0|1|2     betweenness: which sources share a group and a DRAM sector.  0: caller's
+ *                      order; 1: sorted by two-hop neighbourhood size (similar level structure);
+ *                      2 (default): sources that hang off the same hub (at least 2 lanes' worth of
+ *                      them in the call) form clusters that come first, the rest in order 1
  *   bfs_threads N      regime 2: threads per CTA (0: 1024 for n >= 2^18, else 256)
  *   bfs_groups N       regime 1: groups of 32 sources per batch (0: up to 4096)
  *   device_csr 0|1     build the CSR on the device (1) or with the host counting sort (0)

@@ -92,6 +92,7 @@ SYMBOLS = {
     "rxc_comm_init": (C.c_int, [C.c_int, C.c_int, _u8p]),
     "rxc_comm_reduce_sum_f64": (C.c_int, [_f64p, C.c_uint64, C.c_int]),
     "rxc_betweenness_partial_reduce": (C.c_int, [_vp, _u32p, C.c_uint64, C.c_int, C.c_int, _f64p]),
+    "rxc_betweenness_source_order": (C.c_int, [_vp, _u32p, C.c_uint64, _u32p]),
     "rxc_edge_betweenness_partial_reduce": (C.c_int, [_vp, _u32p, C.c_uint64, C.c_int, _f64p]),
     "rxc_comm_barrier": (C.c_int, []),
     "rxc_comm_destroy": (None, []),
@@ -387,6 +388,13 @@ class DeviceGraph:
         check(lib().rxc_betweenness_partial(self._h, p_u32(src), src.shape[0],
                                             int(include_endpoints), p_f64(out)))
         return out[: self.n_bound]
+
+    def betweenness_source_order(self, sources):
+        """The library's grouping order of ``sources`` (siblings of a hub next to each other)."""
+        src = np.ascontiguousarray(sources, dtype=np.uint32)
+        out = np.empty(max(src.shape[0], 1), dtype=np.uint32)
+        check(lib().rxc_betweenness_source_order(self._h, p_u32(src), src.shape[0], p_u32(out)))
+        return out[: src.shape[0]]
 
     def betweenness_partial_reduce(self, sources, include_endpoints=False, root=0, out=None):
         """This rank's shard; the partial vector is reduced in HBM over the ranks of ``rxc_comm_init``

@@ -33,45 +33,72 @@
 
 namespace rxc {
 
-constexpr int BG = 128;  // sources per betweenness group
-constexpr int BK = 4;    // sources per lane (one 32-byte sector of f64)
+// Group width.  RXC_BK = sources per lane: 4 (groups of 128: a lane's f64 values are one 32-byte
+// sector) or 8 (groups of 256: two sectors of f64, one of uint32 path counts).  Wider groups gather
+// fewer rows, look up fewer level masks and queue fewer entries per source at the same sector bytes
+// (scripts/sim_group_width.py: -43 % / -46 % / -47 % on BA graphs) for more registers per thread.
+#ifndef RXC_BK
+#define RXC_BK 4
+#endif
+constexpr int BK = RXC_BK;   // sources per lane
+constexpr int BG = 32 * BK;  // sources per betweenness group
+constexpr int MQ = BK / 4;   // 16-byte quads per source mask
+static_assert(BK == 4 || BK == 8, "RXC_BK must be 4 or 8");
 
-struct __align__(16) Mask128 {
+struct __align__(16) SrcMask {  // one bit per source of a group: word k, bit l <-> lane l, slot k
     uint32_t w[BK];
 };
 
-struct __align__(32) PEntry {
+struct __align__(8 * BK) PEntry {  // 32 bytes (BK = 4) / 64 bytes (BK = 8)
     uint32_t tag;
-    uint32_t pad[3];
-    Mask128 m;
+    uint32_t pad[BK - 1];
+    SrcMask m;
 };
 
-__device__ __forceinline__ Mask128 mask_zero() {
-    Mask128 r;
-    r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0;
+__device__ __forceinline__ SrcMask mask_zero() {
+    SrcMask r;
+#pragma unroll
+    for (int k = 0; k < BK; k++) r.w[k] = 0;
     return r;
 }
-__device__ __forceinline__ uint32_t mask_or(const Mask128 &a) {
-    return a.w[0] | a.w[1] | a.w[2] | a.w[3];
-}
-__device__ __forceinline__ bool mask_any(const Mask128 &a) { return mask_or(a) != 0; }
-__device__ __forceinline__ uint32_t mask_popc(const Mask128 &a) {
-    return __popc(a.w[0]) + __popc(a.w[1]) + __popc(a.w[2]) + __popc(a.w[3]);
-}
-__device__ __forceinline__ Mask128 mask_load(const Mask128 *p) {
-    const uint4 t = *reinterpret_cast<const uint4 *>(p);
-    Mask128 r;
-    r.w[0] = t.x;
-    r.w[1] = t.y;
-    r.w[2] = t.z;
-    r.w[3] = t.w;
+__device__ __forceinline__ uint32_t mask_or(const SrcMask &a) {
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < BK; k++) r |= a.w[k];
     return r;
 }
-__device__ __forceinline__ void mask_store(Mask128 *p, const Mask128 &a) {
-    *reinterpret_cast<uint4 *>(p) = make_uint4(a.w[0], a.w[1], a.w[2], a.w[3]);
+__device__ __forceinline__ bool mask_any(const SrcMask &a) { return mask_or(a) != 0; }
+__device__ __forceinline__ uint32_t mask_popc(const SrcMask &a) {
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < BK; k++) r += __popc(a.w[k]);
+    return r;
 }
-__device__ __forceinline__ Mask128 mask_shfl(const Mask128 &a, int src) {
-    Mask128 r;
+__device__ __forceinline__ bool mask_eq(const SrcMask &a, const SrcMask &b) {
+    uint32_t d = 0;
+#pragma unroll
+    for (int k = 0; k < BK; k++) d |= a.w[k] ^ b.w[k];
+    return d == 0;
+}
+__device__ __forceinline__ SrcMask mask_load(const SrcMask *p) {
+    SrcMask r;
+#pragma unroll
+    for (int q = 0; q < MQ; q++) {
+        const uint4 t = reinterpret_cast<const uint4 *>(p)[q];
+        r.w[4 * q] = t.x;
+        r.w[4 * q + 1] = t.y;
+        r.w[4 * q + 2] = t.z;
+        r.w[4 * q + 3] = t.w;
+    }
+    return r;
+}
+__device__ __forceinline__ void mask_store(SrcMask *p, const SrcMask &a) {
+#pragma unroll
+    for (int q = 0; q < MQ; q++)
+        reinterpret_cast<uint4 *>(p)[q] = make_uint4(a.w[4 * q], a.w[4 * q + 1], a.w[4 * q + 2], a.w[4 * q + 3]);
+}
+__device__ __forceinline__ SrcMask mask_shfl(const SrcMask &a, int src) {
+    SrcMask r;
 #pragma unroll
     for (int k = 0; k < BK; k++) r.w[k] = __shfl_sync(FULL, a.w[k], src);
     return r;
@@ -91,14 +118,16 @@ struct BcParams {
                           // queue outgrew qcap (the host redoes the batch with worst-case queues)
     PEntry *P0;           // [NG][n] tagged level masks, even levels
     PEntry *P1;           // [NG][n] tagged level masks, odd levels
-    Mask128 *visited;     // [NG][n]
+    SrcMask *visited;     // [NG][n]
     uint32_t *qv;         // [NG][qcap] level queues: vertex
-    Mask128 *qm;          // [NG][qcap] level queues: source mask
+    SrcMask *qm;          // [NG][qcap] level queues: source mask
+    uint2 *qe;            // [NG][qcap] level queues: the vertex's arc range in the SUCCESSOR structure, so
+                          // that the dependency sweep starts its arc scan without a dependent look-up
     uint32_t *loff;       // [NG][lcap] queue offset of each level
     uint32_t *lvlcnt;     // [NG][lcap] entries of each level
     uint32_t *lvl_total;  // [lcap] entries of each level summed over groups
     uint32_t *hubv;       // [NG][hubcap] deferred high-degree work items: vertex
-    Mask128 *hubm;        // [NG][hubcap] deferred high-degree work items: mask
+    SrcMask *hubm;        // [NG][hubcap] deferred high-degree work items: mask
     uint32_t *hubcnt;     // [2][NG] number of deferred items, by level parity
     unsigned long long *reach;  // [NG][128] vertices reached per source, excluding the source
     unsigned long long *stats;  // [ST_COUNT]
@@ -128,29 +157,27 @@ __device__ __forceinline__ uint32_t *bc_hubcnt(const BcParams &p, uint32_t level
 }
 
 // Mask of vertex v if it sits on the level `tag` names, else empty; one sector per look-up.
-__device__ __forceinline__ Mask128 bc_level_mask(const PEntry *P, uint32_t v, uint32_t tag) {
+__device__ __forceinline__ SrcMask bc_level_mask(const PEntry *P, uint32_t v, uint32_t tag) {
     const uint4 *q = reinterpret_cast<const uint4 *>(&P[v]);
-    const uint4 t = q[0], mm = q[1];
-    Mask128 m;
+    const uint4 t = q[0];
+    SrcMask m = mask_load(reinterpret_cast<const SrcMask *>(q + MQ));  // the mask sits BK words in
     const bool ok = t.x == tag;
-    m.w[0] = ok ? mm.x : 0u;
-    m.w[1] = ok ? mm.y : 0u;
-    m.w[2] = ok ? mm.z : 0u;
-    m.w[3] = ok ? mm.w : 0u;
+#pragma unroll
+    for (int k = 0; k < BK; k++) m.w[k] = ok ? m.w[k] : 0u;
     return m;
 }
 
 __device__ __forceinline__ void bc_store_level(PEntry *P, uint32_t v, uint32_t tag,
-                                               const Mask128 &m) {
+                                               const SrcMask &m) {
     uint4 *q = reinterpret_cast<uint4 *>(&P[v]);
     q[0] = make_uint4(tag, 0, 0, 0);
-    q[1] = make_uint4(m.w[0], m.w[1], m.w[2], m.w[3]);
+    mask_store(reinterpret_cast<SrcMask *>(q + MQ), m);
 }
 
 // Defer a high-degree work item (warp-uniform v, mask) to the CTA-per-vertex kernel; called by
 // the whole warp, appended once by lane 0.  False when the list is full.
 __device__ __forceinline__ bool bc_defer_hub(const BcParams &p, uint32_t level, uint32_t g,
-                                             uint32_t v, const Mask128 &mask) {
+                                             uint32_t v, const SrcMask &mask) {
     int ok = 0;
     if (lane_id() == 0) {
         const uint32_t h = atomicAdd(bc_hubcnt(p, level, g), 1u);
@@ -163,8 +190,8 @@ __device__ __forceinline__ bool bc_defer_hub(const BcParams &p, uint32_t level, 
     return __shfl_sync(FULL, ok, 0) != 0;
 }
 
-__device__ __forceinline__ Mask128 bc_valid_mask(const BcParams &p, uint32_t g) {
-    Mask128 valid;
+__device__ __forceinline__ SrcMask bc_valid_mask(const BcParams &p, uint32_t g) {
+    SrcMask valid;
 #pragma unroll
     for (int k = 0; k < BK; k++)
         valid.w[k] = __ballot_sync(FULL, p.src[(size_t)g * BG + k * 32 + lane_id()] != NO_SOURCE);
@@ -174,10 +201,10 @@ __device__ __forceinline__ Mask128 bc_valid_mask(const BcParams &p, uint32_t g) 
 // visited[g][*] = ~valid(g): slots without a source count as "reached everywhere".
 __global__ void __launch_bounds__(BLOCK) bc_init_kernel(BcParams p) {
     const uint32_t g = blockIdx.y;
-    const Mask128 valid = bc_valid_mask(p, g);
+    const SrcMask valid = bc_valid_mask(p, g);
     const uint32_t w = blockIdx.x * BLOCK + threadIdx.x;
     if (w < p.n) {
-        Mask128 nv;
+        SrcMask nv;
 #pragma unroll
         for (int k = 0; k < BK; k++) nv.w[k] = ~valid.w[k];
         mask_store(&p.visited[(size_t)g * p.n + w], nv);
@@ -189,16 +216,16 @@ template <bool NARROW>
 __global__ void __launch_bounds__(32) bc_seed_kernel(BcParams p) {
     const uint32_t g = blockIdx.x;
     const int lane = lane_id();
-    const Mask128 valid = bc_valid_mask(p, g);
+    const SrcMask valid = bc_valid_mask(p, g);
     uint32_t base = 0;
 #pragma unroll
     for (int k = 0; k < BK; k++) {
         const uint32_t s = p.src[(size_t)g * BG + k * 32 + lane];
         if (s != NO_SOURCE) {
             const size_t gv = (size_t)g * p.n + s;
-            Mask128 bit = mask_zero();
+            SrcMask bit = mask_zero();
             bit.w[k] = 1u << lane;
-            Mask128 vis;
+            SrcMask vis;
 #pragma unroll
             for (int j = 0; j < BK; j++) vis.w[j] = ~valid.w[j] | bit.w[j];
             mask_store(&p.visited[gv], vis);  // sources of a group are distinct vertices
@@ -208,6 +235,7 @@ __global__ void __launch_bounds__(32) bc_seed_kernel(BcParams p) {
             const uint32_t i = base + __popc(valid.w[k] & lanemask_lt());
             p.qv[(size_t)g * p.qcap + i] = s;
             mask_store(&p.qm[(size_t)g * p.qcap + i], bit);
+            p.qe[(size_t)g * p.qcap + i] = make_uint2(p.srow[s], p.srow[s + 1]);
         }
         base += __popc(valid.w[k]);
         p.reach[(size_t)g * BG + k * 32 + lane] = 0ull;
@@ -222,115 +250,168 @@ __global__ void __launch_bounds__(32) bc_seed_kernel(BcParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// row gathers: lane = sector of four sources
+// row gathers: lane l owns the BK consecutive values [BK*l, BK*l + BK) of every row
 // ---------------------------------------------------------------------------------------------
-struct Row4 {
+struct RowK {
     double x[BK];
 };
 
-__device__ __forceinline__ Row4 row_load(const double *rows, uint32_t v, int lane, bool on) {
-    Row4 r;
+__device__ __forceinline__ RowK row_load(const double *rows, uint32_t v, int lane, bool on) {
+    RowK r;
+#pragma unroll
+    for (int k = 0; k < BK; k++) r.x[k] = 0.0;
     if (on) {
         const double2 *q = reinterpret_cast<const double2 *>(rows + (size_t)v * BG + lane * BK);
-        const double2 a = q[0], b = q[1];
-        r.x[0] = a.x;
-        r.x[1] = a.y;
-        r.x[2] = b.x;
-        r.x[3] = b.y;
-    } else {
-        r.x[0] = r.x[1] = r.x[2] = r.x[3] = 0.0;
+#pragma unroll
+        for (int c = 0; c < BK / 2; c++) {
+            const double2 a = q[c];
+            r.x[2 * c] = a.x;
+            r.x[2 * c + 1] = a.y;
+        }
     }
     return r;
 }
 
-// Staging area: every warp owns STAGE row slots of 1 KB in (dynamic) shared memory and fills them
-// with cp.async (LDGSTS, 16-byte, L1-bypassing), so up to STAGE KB per warp are in flight without
-// holding registers (32 warps/SM x 4 KB = 128 KB); sectors none of whose four sources needs the arc
-// are not fetched.  Measured on BA(1M,8), 1024 sources, f64 rows (GTEPS): STAGE 8 x 3 CTAs/SM 169,
-// 4 x 4 176, 4 x 5 172, 4 x 6 162, 2 x 6 165, 2 x 8 148 with the first slot layout; the same ranking
-// with the conflict-free layout below (4 x 4: 204).
+// Staging area: every warp owns a few row slots in (dynamic) shared memory and fills them with
+// cp.async (LDGSTS, 16-byte, L1-bypassing), so several KB per warp are in flight without holding
+// registers; sectors none of whose sources needs the arc are not fetched.  Measured on BA(1M,8),
+// 1024 sources, groups of 128, f64 rows (GTEPS): STAGE 8 x 3 CTAs/SM 169, 4 x 4 176, 4 x 5 172,
+// 4 x 6 162, 2 x 6 165, 2 x 8 148 with the first slot layout; the same ranking with the
+// conflict-free layout below (4 x 4: 204).
 #ifndef RXC_STAGE
 #define RXC_STAGE 4
 #endif
 #ifndef RXC_MINBLOCKS
-#define RXC_MINBLOCKS 4
+#define RXC_MINBLOCKS (BK == 4 ? 4 : 2)
+#endif
+#ifndef RXC_FWD_MINBLOCKS
+#define RXC_FWD_MINBLOCKS (BK == 4 ? 4 : 2)
 #endif
 #ifndef RXC_FWD32_MINBLOCKS
-#define RXC_FWD32_MINBLOCKS 5  // 46 registers, no spills: 28.0 -> 25.9 ms per 1024 sources
+#define RXC_FWD32_MINBLOCKS (BK == 4 ? 5 : 3)  // BK = 4: 46 registers, no spills: 28.0 -> 25.9 ms per 1024 sources
 #endif
-constexpr int STAGE = RXC_STAGE;
-constexpr int BC_SMEM_BYTES = WARPS * STAGE * BG * 8;  // 32 KB per CTA (forward, edge mode, weighted)
+#ifndef RXC_FWD32_SLOTS
+#define RXC_FWD32_SLOTS (BK == 4 ? 8 : 6)
+#endif
+constexpr int STAGE = RXC_STAGE;  // f64 row slots per warp in the forward / edge / weighted kernels
+constexpr int BC_SMEM_BYTES = WARPS * STAGE * BG * 8;  // BK = 4: 32 KB per CTA
+constexpr int FWD32_SLOTS = RXC_FWD32_SLOTS;  // uint32 row slots per warp in the narrow forward kernels
+constexpr int BC_FWD32_SMEM_BYTES = WARPS * FWD32_SLOTS * BG * 4;
 // The dependency kernels have no static shared memory, so 6 row slots per warp still fit 4 CTAs per
-// SM (4 x 48 KB): measured 45.3 -> 43.3 ms per 1024 sources; the forward kernels (10 KB static)
-// would drop to 3 CTAs per SM with 6 slots and lose 3 ms.
+// SM (4 x 48 KB) with groups of 128: measured 45.3 -> 43.3 ms per 1024 sources; the forward kernels
+// (10 KB static) would drop to 3 CTAs per SM with 6 slots and lose 3 ms.
 #ifndef RXC_BSTAGE
-#define RXC_BSTAGE 6
+#define RXC_BSTAGE (BK == 4 ? 6 : 5)
 #endif
 constexpr int BSTAGE = RXC_BSTAGE;
 constexpr int BC_BWD_SMEM_BYTES = WARPS * BSTAGE * BG * 8;
 
-// Staging a row (1 KB = 64 chunks of 16 bytes) without shared-memory bank conflicts on either side.
-// Copy: instruction 1 moves chunk `lane`, instruction 2 chunk `32 + lane`, so the global side of each
-// warp-wide LDGSTS is 512 contiguous bytes (ncu: the sector-per-lane form, lane l copying chunks 2l
-// and 2l+1, cost 12.4 shared wavefronts per LDGSTS against an ideal of 4-5, and the shared-memory
-// data pipe sat at 65-85 % of peak in all four big launches).  Read: lane l owns sector l = chunks 2l
-// and 2l+1.  Chunk c is stored at position (c & ~7) | ((c + (c >> 3)) & 7) -- a rotation inside its
-// 128-byte line by the line number -- which makes the 8 lanes of every quarter warp hit 8 different
-// 16-byte bank groups for the writes (8 consecutive chunks) and for both reads (8 even or 8 odd
-// chunks of two neighbouring lines).  A chunk is only fetched when its sector is needed (`any` bit
-// of the sector); the others are zero-filled without touching memory.
+// Geometry of one staged row of BG elements: CPL 16-byte chunks per lane (1, 2 or 4), i.e. CPL
+// warp-wide copy instructions whose global side is 512 contiguous bytes each.
+//   CPL = 1 (uint32 rows, BK = 4): a lane copies and reads back its own chunk; nothing to swizzle.
+//   CPL = 2 (f64 rows, BK = 4; uint32 rows, BK = 8): a lane's values are one 32-byte sector.
+//   CPL = 4 (f64 rows, BK = 8): a lane's values are two sectors (slots 0..3 and 4..7).
+// Copy instruction j moves chunk 32 j + lane; lane l reads back chunks CPL l .. CPL l + CPL - 1.
+// Chunk c is stored at position (c & ~7) | ((c + (c >> 3)) & 7) -- a rotation inside its 128-byte
+// line by the line number -- which makes the 8 lanes of every quarter warp hit 8 different 16-byte
+// bank groups for the writes (8 consecutive chunks of one line) and for every read (CPL = 2: 8 even
+// or 8 odd chunks of two neighbouring lines; CPL = 4: two chunks 4 apart in each of four
+// consecutive lines).  ncu on the first layout (lane l copying its own chunks): 12.4 shared
+// wavefronts per LDGSTS against an ideal of 4-5, shared-memory pipe at 65-85 % in the big launches.
+// A chunk is only fetched when its SECTOR is needed (CPL = 1: its half sector); stale bytes of
+// skipped chunks are never used, because a lane only adds values whose mask bit is set.
+template <class Elem>
+struct RowGeom {
+    static constexpr int ROW_BYTES = BG * (int)sizeof(Elem);
+    static constexpr int CPL = ROW_BYTES / 512;
+    static constexpr int SPL = CPL >= 2 ? CPL / 2 : 1;  // sector-need words per arc (see row_need)
+    static constexpr int VPC = 16 / (int)sizeof(Elem);  // values per chunk
+    static_assert(CPL == 1 || CPL == 2 || CPL == 4, "row geometry");
+};
+
 __device__ __forceinline__ int stage_pos(int c) { return (c & ~7) | ((c + (c >> 3)) & 7); }
-__device__ __forceinline__ const double2 *stage_chunk(const double *slot, int c) {
-    return reinterpret_cast<const double2 *>(slot) + stage_pos(c);
-}
-__device__ __forceinline__ void cp_async_row(double *slot, int lane, const double *grow, uint32_t any) {
-    const uint32_t base = (uint32_t)__cvta_generic_to_shared(slot);
-    const uint32_t d1 = base + 16u * stage_pos(lane), d2 = base + 16u * stage_pos(32 + lane);
-    // chunks of sectors nobody needs are not copied at all (their stale bytes are never used:
-    // a lane only adds values whose mask bit is set, and those sectors were fetched)
-    const uint32_t on1 = (any >> (lane >> 1)) & 1u, on2 = (any >> (16 + (lane >> 1))) & 1u;
-    asm volatile(
-        "{\n"
-        ".reg .pred p1, p2;\n"
-        "setp.ne.u32 p1, %2, 0;\n"
-        "setp.ne.u32 p2, %5, 0;\n"
-        "@p1 cp.async.cg.shared.global [%0], [%1], 16;\n"
-        "@p2 cp.async.cg.shared.global [%3], [%4], 16;\n"
-        "}\n" ::"r"(d1),
-        "l"(grow + 2 * lane), "r"(on1), "r"(d2), "l"(grow + 64 + 2 * lane), "r"(on2)
-        : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.wait_all;\n" ::: "memory");
-}
-__device__ __forceinline__ void cp_async_commit() {
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-}
-// wait until at most n (warp-uniform, < 8) of this thread's cp.async groups are still pending
-__device__ __forceinline__ void cp_async_wait_pending(int n) {
-    switch (n) {
-        case 0: asm volatile("cp.async.wait_group 0;\n" ::: "memory"); break;
-        case 1: asm volatile("cp.async.wait_group 1;\n" ::: "memory"); break;
-        case 2: asm volatile("cp.async.wait_group 2;\n" ::: "memory"); break;
-        case 3: asm volatile("cp.async.wait_group 3;\n" ::: "memory"); break;
-        case 4: asm volatile("cp.async.wait_group 4;\n" ::: "memory"); break;
-        case 5: asm volatile("cp.async.wait_group 5;\n" ::: "memory"); break;
-        case 6: asm volatile("cp.async.wait_group 6;\n" ::: "memory"); break;
-        default: asm volatile("cp.async.wait_group 7;\n" ::: "memory"); break;
+
+// Which lanes' sectors an arc with source mask m needs: need[h] bit l <-> sector h of lane l.
+template <int SPL>
+__device__ __forceinline__ void row_need(const SrcMask &m, uint32_t (&need)[SPL]) {
+#pragma unroll
+    for (int h = 0; h < SPL; h++) {
+        need[h] = 0;
+#pragma unroll
+        for (int k = h * (BK / SPL); k < (h + 1) * (BK / SPL); k++) need[h] |= m.w[k];
     }
 }
 
+template <class Elem>
+__device__ __forceinline__ void cp_async_row(uint32_t slot_smem, int lane, const Elem *grow,
+                                             const uint32_t (&need)[RowGeom<Elem>::SPL]) {
+    constexpr int CPL = RowGeom<Elem>::CPL;
+#pragma unroll
+    for (int j = 0; j < CPL; j++) {
+        const int c = 32 * j + lane;
+        uint32_t on, dst;
+        if (CPL == 1) {
+            on = (need[0] >> lane) & 1u;
+            dst = slot_smem + 16u * lane;
+        } else if (CPL == 2) {
+            on = (need[0] >> (c >> 1)) & 1u;
+            dst = slot_smem + 16u * stage_pos(c);
+        } else {
+            on = ((((c >> 1) & 1) ? need[RowGeom<Elem>::SPL - 1] : need[0]) >> (c >> 2)) & 1u;
+            dst = slot_smem + 16u * stage_pos(c);
+        }
+        asm volatile(
+            "{\n"
+            ".reg .pred p1;\n"
+            "setp.ne.u32 p1, %2, 0;\n"
+            "@p1 cp.async.cg.shared.global [%0], [%1], 16;\n"
+            "}\n" ::"r"(dst),
+            "l"(reinterpret_cast<const char *>(grow) + 16 * c), "r"(on)
+            : "memory");
+    }
+}
+
+// the BK values of this lane out of a staged row
+template <class Elem>
+__device__ __forceinline__ void stage_read(const char *slot, int lane, Elem (&x)[BK]) {
+    constexpr int CPL = RowGeom<Elem>::CPL, VPC = RowGeom<Elem>::VPC;
+#pragma unroll
+    for (int i = 0; i < CPL; i++) {
+        const int c = CPL * lane + i;
+        const char *at = slot + 16 * (CPL == 1 ? c : stage_pos(c));
+        if constexpr (VPC == 4) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(at);
+            x[4 * i] = q.x;
+            x[4 * i + 1] = q.y;
+            x[4 * i + 2] = q.z;
+            x[4 * i + 3] = q.w;
+        } else {
+            const double2 q = *reinterpret_cast<const double2 *>(at);
+            x[2 * i] = q.x;
+            x[2 * i + 1] = q.y;
+        }
+    }
+}
+
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+}
+
 // acc[k] += rows[v][lane][k] over the arcs in nz (lanes of v_lane / m_lane with a non-empty mask)
-// for the sources the arc's mask names, arc order preserved; up to STAGE rows in flight per warp.
+// for the sources the arc's mask names, arc order preserved; up to NS rows in flight per warp.
 // Per-row bookkeeping is kept out of this loop (ncu: ~80 issued instructions per gathered row made
 // the big launches co-limited by issue slots): the union of the masks and the DAG-arc count are
 // formed once per look-up from the lanes' own masks by the callers.
-template <int NS = STAGE>
-__device__ __forceinline__ void bc_gather(const double *rows, uint32_t v_lane, const Mask128 &m_lane,
-                                          uint32_t nz, int lane, double *stage, double (&acc)[BK]) {
-    // Batches of STAGE rows.  (A ring that tops itself up row by row, so that STAGE rows stay in
-    // flight for the whole arc list, was measured: 80 -> 86 ms per 1024 sources -- its bookkeeping
-    // costs more issue slots than the shorter waits give back.)
+// Batches of NS rows.  (A ring that tops itself up row by row, so that NS rows stay in flight for
+// the whole arc list, was measured: 80 -> 86 ms per 1024 sources -- its bookkeeping costs more issue
+// slots than the shorter waits give back.)
+template <int NS, class Elem, class Acc>
+__device__ __forceinline__ void bc_gather(const Elem *rows, uint32_t v_lane, const SrcMask &m_lane,
+                                          uint32_t nz, int lane, char *stage, Acc (&acc)[BK]) {
+    using G = RowGeom<Elem>;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage);
+    uint32_t need_lane[G::SPL];
+    row_need<G::SPL>(m_lane, need_lane);
     while (nz) {
         uint32_t todo = nz;
         int cnt = 0;
@@ -340,43 +421,43 @@ __device__ __forceinline__ void bc_gather(const double *rows, uint32_t v_lane, c
                 const int a = __ffs(nz) - 1;
                 nz &= nz - 1;
                 const uint32_t vj = __shfl_sync(FULL, v_lane, a);
-                const uint32_t any = __shfl_sync(FULL, mask_or(m_lane), a);
-                cp_async_row(stage + i * BG, lane, rows + (size_t)vj * BG, any);
+                uint32_t need[G::SPL];
+#pragma unroll
+                for (int h = 0; h < G::SPL; h++) need[h] = __shfl_sync(FULL, need_lane[h], a);
+                cp_async_row<Elem>(sbase + i * G::ROW_BYTES, lane, rows + (size_t)vj * BG, need);
                 cnt = i + 1;
             }
         }
         cp_async_wait_all();
-        __syncwarp();  // the chunks a lane reads were copied by other lanes
+        if (G::CPL > 1) __syncwarp();  // the chunks a lane reads were copied by other lanes
 #pragma unroll
         for (int i = 0; i < NS; i++) {
             if (i < cnt) {
                 const int a = __ffs(todo) - 1;
                 todo &= todo - 1;
-                const Mask128 mj = mask_shfl(m_lane, a);
-                const double2 x0 = *stage_chunk(stage + i * BG, 2 * lane);
-                const double2 x1 = *stage_chunk(stage + i * BG, 2 * lane + 1);
-                if ((mj.w[0] >> lane) & 1u) acc[0] += x0.x;
-                if ((mj.w[1] >> lane) & 1u) acc[1] += x0.y;
-                if ((mj.w[2] >> lane) & 1u) acc[2] += x1.x;
-                if ((mj.w[3] >> lane) & 1u) acc[3] += x1.y;
+                const SrcMask mj = mask_shfl(m_lane, a);
+                Elem x[BK];
+                stage_read<Elem>(stage + i * G::ROW_BYTES, lane, x);
+#pragma unroll
+                for (int k = 0; k < BK; k++)
+                    if ((mj.w[k] >> lane) & 1u) acc[k] += x[k];
             }
         }
-        __syncwarp();  // the slots may be refilled by other lanes from here on
+        if (G::CPL > 1) __syncwarp();  // the slots may be refilled by other lanes from here on
     }
 }
-
 
 // ---------------------------------------------------------------------------------------------
 // narrow sigma rows
 //
 // sigma counts shortest paths: exact integers.  On small-world graphs they are tiny (BA(1M,8): below
-// 10^5), so the forward pass keeps them as uint32 -- a 512-byte row per vertex, 8 sources per DRAM
-// sector instead of 4 -- and accumulates in uint64.  That halves the bytes, the LDGSTS/LDS
-// wavefronts and the copy instructions of every gathered row, and leaves room for 8 rows in flight
-// per warp in the same shared memory.  The dependency sweep needs (1+delta)/sigma in f64 and writes
-// it to the f64 rows.  A path count that does not fit 32 bits (lattices: binomially many paths)
-// raises `overflow`; the host then redoes the batch with f64 sigma rows (the "wide" mode, which is
-// the layout described at the top of this file) and stays wide for the handle.
+// 10^5), so the forward pass keeps them as uint32 -- half the row bytes, 8 sources per DRAM sector
+// instead of 4 -- and accumulates in uint64.  That halves the bytes, the LDGSTS/LDS wavefronts and
+// the copy instructions of every gathered row, and leaves room for twice the rows in flight per
+// warp in the same shared memory.  The dependency sweep needs (1+delta)/sigma in f64 and writes it
+// to the f64 rows.  A path count that does not fit 32 bits (lattices: binomially many paths) raises
+// `overflow`; the host then redoes the batch with f64 sigma rows (the "wide" mode, which is the
+// layout described at the top of this file) and stays wide for the handle.
 // ---------------------------------------------------------------------------------------------
 template <bool NARROW>
 struct SigmaRows;
@@ -384,62 +465,16 @@ template <>
 struct SigmaRows<false> {
     using Elem = double;
     using Acc = double;
+    static constexpr int SLOTS = STAGE;
     static __device__ __forceinline__ Elem *rows(const BcParams &p, size_t gn) { return p.sc + gn * BG; }
 };
 template <>
 struct SigmaRows<true> {
     using Elem = uint32_t;
     using Acc = unsigned long long;
+    static constexpr int SLOTS = FWD32_SLOTS;  // half-size rows: more slots in the same shared memory
     static __device__ __forceinline__ Elem *rows(const BcParams &p, size_t gn) { return p.sig32 + gn * BG; }
 };
-constexpr int STAGE32 = 2 * STAGE;  // 512-byte rows: twice as many slots in the same shared memory
-
-__device__ __forceinline__ void bc_gather(const uint32_t *rows, uint32_t v_lane, const Mask128 &m_lane,
-                                          uint32_t nz, int lane, double *stage_f64,
-                                          unsigned long long (&acc)[BK]) {
-    // lane l copies and reads back its own 16-byte chunk: contiguous on both sides, no swizzle, and
-    // cp.async.wait_all is the only synchronisation a lane needs for bytes it copied itself
-    uint4 *stage = reinterpret_cast<uint4 *>(stage_f64);
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage) + 16u * lane;
-    while (nz) {
-        uint32_t todo = nz;
-        int cnt = 0;
-#pragma unroll
-        for (int i = 0; i < STAGE32; i++) {
-            if (nz) {  // warp-uniform
-                const int a = __ffs(nz) - 1;
-                nz &= nz - 1;
-                const uint32_t vj = __shfl_sync(FULL, v_lane, a);
-                const uint32_t any = __shfl_sync(FULL, mask_or(m_lane), a);
-                const uint32_t on = (any >> lane) & 1u;
-                const uint32_t *src = rows + (size_t)vj * BG + lane * BK;
-                asm volatile(
-                    "{\n"
-                    ".reg .pred p1;\n"
-                    "setp.ne.u32 p1, %2, 0;\n"
-                    "@p1 cp.async.cg.shared.global [%0], [%1], 16;\n"
-                    "}\n" ::"r"(sbase + 512u * i),
-                    "l"(src), "r"(on)
-                    : "memory");
-                cnt = i + 1;
-            }
-        }
-        cp_async_wait_all();
-#pragma unroll
-        for (int i = 0; i < STAGE32; i++) {
-            if (i < cnt) {
-                const int a = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const Mask128 mj = mask_shfl(m_lane, a);
-                const uint4 x = stage[i * 32 + lane];
-                if ((mj.w[0] >> lane) & 1u) acc[0] += x.x;
-                if ((mj.w[1] >> lane) & 1u) acc[1] += x.y;
-                if ((mj.w[2] >> lane) & 1u) acc[2] += x.z;
-                if ((mj.w[3] >> lane) & 1u) acc[3] += x.w;
-            }
-        }
-    }
-}
 
 // sigma of a newly discovered (vertex, source); narrow mode flags counts beyond 32 bits
 template <bool NARROW>
@@ -453,18 +488,23 @@ __device__ __forceinline__ void bc_store_sigma(const BcParams &p, typename Sigma
     }
 }
 
-// own sigma of the four sources of a lane, as f64
+// own sigma of the BK sources of a lane, as f64
 template <bool NARROW>
-__device__ __forceinline__ Row4 bc_load_sigma(const BcParams &p, size_t gn, uint32_t v, int lane, bool on) {
+__device__ __forceinline__ RowK bc_load_sigma(const BcParams &p, size_t gn, uint32_t v, int lane, bool on) {
     if (NARROW) {
-        Row4 r;
-        r.x[0] = r.x[1] = r.x[2] = r.x[3] = 0.0;
+        RowK r;
+#pragma unroll
+        for (int k = 0; k < BK; k++) r.x[k] = 0.0;
         if (on) {
-            const uint4 q = *reinterpret_cast<const uint4 *>(p.sig32 + (gn + v) * BG + lane * BK);
-            r.x[0] = (double)q.x;
-            r.x[1] = (double)q.y;
-            r.x[2] = (double)q.z;
-            r.x[3] = (double)q.w;
+            const uint4 *q = reinterpret_cast<const uint4 *>(p.sig32 + (gn + v) * BG + lane * BK);
+#pragma unroll
+            for (int c = 0; c < MQ; c++) {
+                const uint4 t = q[c];
+                r.x[4 * c] = (double)t.x;
+                r.x[4 * c + 1] = (double)t.y;
+                r.x[4 * c + 2] = (double)t.z;
+                r.x[4 * c + 3] = (double)t.w;
+            }
         }
         return r;
     }
@@ -505,13 +545,13 @@ __global__ void __launch_bounds__(BLOCK) bc_mark_kernel(BcParams p, uint32_t lev
 template <class Elem, class Acc>
 __device__ __forceinline__ void bc_fwd_scan(const BcParams &p, const Elem *rows, const PEntry *Pcur,
                                             uint32_t tag_cur, uint32_t e0, uint32_t e1,
-                                            uint32_t first, uint32_t step, const Mask128 &unv,
-                                            int lane, double *stage, Acc (&acc)[BK],
-                                            Mask128 &newm) {
+                                            uint32_t first, uint32_t step, const SrcMask &unv,
+                                            int lane, char *stage, Acc (&acc)[BK],
+                                            SrcMask &newm) {
     for (uint32_t e = e0 + first; e < e1; e += step) {
         const uint32_t idx = e + lane;
         uint32_t v = 0;
-        Mask128 m = mask_zero();
+        SrcMask m = mask_zero();
         if (idx < e1) {
             v = p.col[idx];
             m = bc_level_mask(Pcur, v, tag_cur);
@@ -522,7 +562,7 @@ __device__ __forceinline__ void bc_fwd_scan(const BcParams &p, const Elem *rows,
         if (nz) {
 #pragma unroll
             for (int k = 0; k < BK; k++) newm.w[k] |= __reduce_or_sync(FULL, m.w[k]);
-            bc_gather(rows, v, m, nz, lane, stage, acc);
+            bc_gather<SigmaRows<sizeof(Elem) == 4>::SLOTS>(rows, v, m, nz, lane, stage, acc);
         }
     }
 }
@@ -531,7 +571,7 @@ __device__ __forceinline__ void bc_fwd_scan(const BcParams &p, const Elem *rows,
 // their in-arcs -- the bottom-up form of centrality.rs:427-437.  No early exit: every frontier
 // parent contributes to sigma.
 template <bool NARROW>
-__global__ void __launch_bounds__(BLOCK, (NARROW ? RXC_FWD32_MINBLOCKS : RXC_MINBLOCKS)) bc_forward_kernel(BcParams p, uint32_t level) {
+__global__ void __launch_bounds__(BLOCK, (NARROW ? RXC_FWD32_MINBLOCKS : RXC_FWD_MINBLOCKS)) bc_forward_kernel(BcParams p, uint32_t level) {
     using Acc = typename SigmaRows<NARROW>::Acc;
     const uint32_t g = blockIdx.y;
     uint32_t *lc = p.lvlcnt + (size_t)g * p.lcap;
@@ -540,11 +580,12 @@ __global__ void __launch_bounds__(BLOCK, (NARROW ? RXC_FWD32_MINBLOCKS : RXC_MIN
     const uint32_t fcnt = lc[level];
     if (fcnt == 0) return;  // this group's BFS has finished
 
-    __shared__ Mask128 s_unv[BLOCK], s_om[BLOCK];
+    __shared__ SrcMask s_unv[BLOCK], s_om[BLOCK];
     __shared__ uint32_t s_w[BLOCK], s_ov[BLOCK];
+    __shared__ uint2 s_e[BLOCK];  // arc range of every candidate, read coalesced while compacting
     __shared__ uint32_t s_ncand, s_next, s_nout, s_base;
-    extern __shared__ __align__(16) double s_dyn_stage[];
-    double *stage = s_dyn_stage + (size_t)(threadIdx.x >> 5) * STAGE * BG;
+    extern __shared__ __align__(16) char s_dyn_stage[];
+    char *stage = s_dyn_stage + (size_t)(threadIdx.x >> 5) * ((NARROW ? BC_FWD32_SMEM_BYTES : BC_SMEM_BYTES) / WARPS);
     const int tid = threadIdx.x, lane = lane_id();
     if (tid == 0) {
         s_ncand = 0;
@@ -554,7 +595,7 @@ __global__ void __launch_bounds__(BLOCK, (NARROW ? RXC_FWD32_MINBLOCKS : RXC_MIN
     __syncthreads();
 
     const size_t gn = (size_t)g * p.n;
-    Mask128 *visited = p.visited + gn;
+    SrcMask *visited = p.visited + gn;
     const PEntry *Pcur = bc_P(p, level) + gn;
     PEntry *Pnext = bc_P(p, level + 1) + gn;
     auto *rows = SigmaRows<NARROW>::rows(p, gn);
@@ -563,7 +604,7 @@ __global__ void __launch_bounds__(BLOCK, (NARROW ? RXC_FWD32_MINBLOCKS : RXC_MIN
     // 1. coalesced read of this CTA's 256 visited masks; compact the unfinished vertices
     {
         const uint32_t w = blockIdx.x * BLOCK + tid;
-        Mask128 unv = mask_zero();
+        SrcMask unv = mask_zero();
         bool look = w < p.n;
         if (fcnt <= p.sparse_max) {  // sparse level: only neighbours of the frontier can be reached
             uint32_t *word = p.maybe + (size_t)g * p.mwords + (w >> 5);
@@ -573,7 +614,7 @@ __global__ void __launch_bounds__(BLOCK, (NARROW ? RXC_FWD32_MINBLOCKS : RXC_MIN
             if (lane == 0 && bits) *word = 0;  // consumed: clean for the next level
         }
         if (look) {
-            const Mask128 vis = mask_load(&visited[w]);
+            const SrcMask vis = mask_load(&visited[w]);
 #pragma unroll
             for (int k = 0; k < BK; k++) unv.w[k] = ~vis.w[k];
         }
@@ -586,6 +627,9 @@ __global__ void __launch_bounds__(BLOCK, (NARROW ? RXC_FWD32_MINBLOCKS : RXC_MIN
             const uint32_t i = wbase + __popc(bal & lanemask_lt());
             s_w[i] = w;
             s_unv[i] = unv;
+            // consecutive vertices: the offsets come in with coalesced loads here instead of one
+            // dependent look-up per candidate at the head of the warp's chain below
+            s_e[i] = make_uint2(p.row[w], p.row[w + 1]);
         }
     }
     __syncthreads();
@@ -598,18 +642,18 @@ __global__ void __launch_bounds__(BLOCK, (NARROW ? RXC_FWD32_MINBLOCKS : RXC_MIN
         i = __shfl_sync(FULL, i, 0);
         if (i >= ncand) break;
         const uint32_t w = s_w[i];
-        const Mask128 unv = s_unv[i];
-        const uint32_t e0 = p.row[w], e1 = p.row[w + 1];
+        const SrcMask unv = s_unv[i];
+        const uint32_t e0 = s_e[i].x, e1 = s_e[i].y;
         if (e1 - e0 > p.hub_degree && bc_defer_hub(p, level, g, w, unv)) continue;
-        Acc acc[BK] = {0, 0, 0, 0};
-        Mask128 newm = mask_zero();
+        Acc acc[BK] = {};
+        SrcMask newm = mask_zero();
         bc_fwd_scan(p, rows, Pcur, tag_cur, e0, e1, 0, 32, unv, lane, stage, acc, newm);
         if (mask_any(newm)) {
 #pragma unroll
             for (int k = 0; k < BK; k++)
                 if ((newm.w[k] >> lane) & 1u) bc_store_sigma<NARROW>(p, &rows[(size_t)w * BG + lane * BK + k], acc[k]);
             if (lane == 0) {
-                Mask128 vis;
+                SrcMask vis;
 #pragma unroll
                 for (int k = 0; k < BK; k++) vis.w[k] = ~unv.w[k] | newm.w[k];
                 mask_store(&visited[w], vis);
@@ -639,8 +683,10 @@ __global__ void __launch_bounds__(BLOCK, (NARROW ? RXC_FWD32_MINBLOCKS : RXC_MIN
         const uint64_t pos = (uint64_t)s_base + tid;
         if (pos < p.qcap) {
             const size_t q = (size_t)g * p.qcap + pos;
-            p.qv[q] = s_ov[tid];
+            const uint32_t w = s_ov[tid];
+            p.qv[q] = w;
             mask_store(&p.qm[q], s_om[tid]);
+            p.qe[q] = make_uint2(p.srow[w], p.srow[w + 1]);
         } else {
             atomicOr(p.overflow, 2u);
         }
@@ -659,30 +705,30 @@ __global__ void __launch_bounds__(BLOCK) bc_forward_hub_kernel(BcParams p, uint3
     if (fcnt == 0 || nh == 0) return;
     const int tid = threadIdx.x, lane = lane_id(), wid = tid >> 5;
     const size_t gn = (size_t)g * p.n;
-    Mask128 *visited = p.visited + gn;
+    SrcMask *visited = p.visited + gn;
     const PEntry *Pcur = bc_P(p, level) + gn;
     PEntry *Pnext = bc_P(p, level + 1) + gn;
     auto *rows = SigmaRows<NARROW>::rows(p, gn);
     const uint32_t tag_cur = p.tagbase + level + 1, tag_next = tag_cur + 1;
     __shared__ Acc s_acc[WARPS][BG];
-    __shared__ Mask128 s_new[WARPS];
-    extern __shared__ __align__(16) double s_dyn_stage[];
-    double *stage = s_dyn_stage + (size_t)(threadIdx.x >> 5) * STAGE * BG;
+    __shared__ SrcMask s_new[WARPS];
+    extern __shared__ __align__(16) char s_dyn_stage[];
+    char *stage = s_dyn_stage + (size_t)(threadIdx.x >> 5) * ((NARROW ? BC_FWD32_SMEM_BYTES : BC_SMEM_BYTES) / WARPS);
 
     for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
         const uint32_t w = p.hubv[(size_t)g * p.hubcap + h];
-        const Mask128 unv = mask_load(&p.hubm[(size_t)g * p.hubcap + h]);
+        const SrcMask unv = mask_load(&p.hubm[(size_t)g * p.hubcap + h]);
         const uint32_t e0 = p.row[w], e1 = p.row[w + 1];
-        Acc acc[BK] = {0, 0, 0, 0};
-        Mask128 newm = mask_zero();
+        Acc acc[BK] = {};
+        SrcMask newm = mask_zero();
         bc_fwd_scan(p, rows, Pcur, tag_cur, e0, e1, wid * 32, WARPS * 32, unv, lane, stage, acc, newm);
 #pragma unroll
         for (int k = 0; k < BK; k++) s_acc[wid][lane * BK + k] = acc[k];
         if (lane == 0) s_new[wid] = newm;
         __syncthreads();
         if (wid == 0) {
-            Acc tot[BK] = {0, 0, 0, 0};
-            Mask128 nm = mask_zero();
+            Acc tot[BK] = {};
+            SrcMask nm = mask_zero();
             for (int q = 0; q < WARPS; q++) {
 #pragma unroll
                 for (int k = 0; k < BK; k++) {
@@ -695,7 +741,7 @@ __global__ void __launch_bounds__(BLOCK) bc_forward_hub_kernel(BcParams p, uint3
                 for (int k = 0; k < BK; k++)
                     if ((nm.w[k] >> lane) & 1u) bc_store_sigma<NARROW>(p, &rows[(size_t)w * BG + lane * BK + k], tot[k]);
                 if (lane == 0) {
-                    Mask128 vis;
+                    SrcMask vis;
 #pragma unroll
                     for (int k = 0; k < BK; k++) vis.w[k] = ~unv.w[k] | nm.w[k];
                     mask_store(&visited[w], vis);
@@ -707,6 +753,7 @@ __global__ void __launch_bounds__(BLOCK) bc_forward_hub_kernel(BcParams p, uint3
                         const size_t q = (size_t)g * p.qcap + qpos;
                         p.qv[q] = w;
                         mask_store(&p.qm[q], nm);
+                        p.qe[q] = make_uint2(p.srow[w], p.srow[w + 1]);
                     } else {
                         atomicOr(p.overflow, 2u);
                     }
@@ -728,13 +775,13 @@ template <bool EDGE>
 __device__ __forceinline__ void bc_bwd_scan(const BcParams &p, const double *rows,
                                             const PEntry *Pnext, uint32_t tag_next, uint32_t e0,
                                             uint32_t e1, uint32_t first, uint32_t step,
-                                            const Mask128 &fm, const double (&sig)[BK], int lane,
-                                            double *stage, double (&acc)[BK],
+                                            const SrcMask &fm, const double (&sig)[BK], int lane,
+                                            char *stage, double (&acc)[BK],
                                             unsigned long long &dag) {
     for (uint32_t e = e0 + first; e < e1; e += step) {
         const uint32_t idx = e + lane;
         uint32_t w = 0, ed = 0;
-        Mask128 m = mask_zero();
+        SrcMask m = mask_zero();
         if (idx < e1) {
             w = p.col[idx];
             m = bc_level_mask(Pnext, w, tag_next);
@@ -747,8 +794,12 @@ __device__ __forceinline__ void bc_bwd_scan(const BcParams &p, const double *row
         if (!EDGE) {
             bc_gather<BSTAGE>(rows, w, m, nz, lane, stage, acc);
         } else {
+            using G = RowGeom<double>;
+            const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage);
+            uint32_t need_lane[G::SPL];
+            row_need<G::SPL>(m, need_lane);
             while (nz) {
-                // stage up to STAGE successor rows, then form per-arc sums over all 128 sources
+                // stage up to STAGE successor rows, then form per-arc sums over all sources of the group
                 uint32_t todo = nz;
                 int cnt = 0;
 #pragma unroll
@@ -757,12 +808,15 @@ __device__ __forceinline__ void bc_bwd_scan(const BcParams &p, const double *row
                         const int a = __ffs(nz) - 1;
                         nz &= nz - 1;
                         const uint32_t wj = __shfl_sync(FULL, w, a);
-                        const uint32_t any = __shfl_sync(FULL, mask_or(m), a);
-                        cp_async_row(stage + i * BG, lane, rows + (size_t)wj * BG, any);
+                        uint32_t need[G::SPL];
+#pragma unroll
+                        for (int h = 0; h < G::SPL; h++) need[h] = __shfl_sync(FULL, need_lane[h], a);
+                        cp_async_row<double>(sbase + i * G::ROW_BYTES, lane, rows + (size_t)wj * BG, need);
                         cnt = i + 1;
                     }
                 }
                 cp_async_wait_all();
+                __syncwarp();  // the chunks a lane reads were copied by other lanes
                 double c[STAGE];
                 uint32_t my_e = 0;
 #pragma unroll
@@ -771,12 +825,11 @@ __device__ __forceinline__ void bc_bwd_scan(const BcParams &p, const double *row
                     if (i < cnt) {
                         const int a = __ffs(todo) - 1;
                         todo &= todo - 1;
-                        const Mask128 mj = mask_shfl(m, a);
+                        const SrcMask mj = mask_shfl(m, a);
                         const uint32_t ej = __shfl_sync(FULL, ed, a);
                         if (lane / (32 / STAGE) == i) my_e = ej;
-                        const double2 x0 = *stage_chunk(stage + i * BG, 2 * lane);
-                        const double2 x1 = *stage_chunk(stage + i * BG, 2 * lane + 1);
-                        const double xs[BK] = {x0.x, x0.y, x1.x, x1.y};
+                        double xs[BK];
+                        stage_read<double>(stage + i * G::ROW_BYTES, lane, xs);
 #pragma unroll
                         for (int k = 0; k < BK; k++) {
                             if ((mj.w[k] >> lane) & 1u) {
@@ -787,6 +840,7 @@ __device__ __forceinline__ void bc_bwd_scan(const BcParams &p, const double *row
                         }
                     }
                 }
+                __syncwarp();  // the slots may be refilled by other lanes from here on
                 // reduce the STAGE per-arc sums over the warp at once: log2(STAGE) halving exchanges
                 // leave lane l with arc l / (32/STAGE); the remaining butterfly steps finish the sum
                 static_assert(STAGE == 8 || STAGE == 4 || STAGE == 2, "exchange network: STAGE must be 2, 4 or 8");
@@ -813,7 +867,7 @@ __device__ __forceinline__ void bc_bwd_scan(const BcParams &p, const double *row
 // Finish one queue entry (v, fm): rewrite the row with (1+delta)/sigma, add the vertex score,
 // restore P for the level above.  centrality.rs:274-279 (coeff) and :281-298 (accumulation).
 template <bool EDGE, bool ENDPOINTS>
-__device__ __forceinline__ void bc_bwd_finish(const BcParams &p, uint32_t v, const Mask128 &fm,
+__device__ __forceinline__ void bc_bwd_finish(const BcParams &p, uint32_t v, const SrcMask &fm,
                                               const double (&sig)[BK], const double (&acc)[BK],
                                               double *rows, PEntry *Pcur, uint32_t tag_cur,
                                               uint32_t level, int lane) {
@@ -855,17 +909,19 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) bc_backward_kernel(BcPar
     double *rows = p.sc + gn * BG;
     const uint32_t tag_cur = p.tagbase + level + 1, tag_next = tag_cur + 1;
     const uint32_t *qv = p.qv + (size_t)g * p.qcap + off;
-    const Mask128 *qm = p.qm + (size_t)g * p.qcap + off;
+    const SrcMask *qm = p.qm + (size_t)g * p.qcap + off;
+    const uint2 *qe = p.qe + (size_t)g * p.qcap + off;
 
-    extern __shared__ __align__(16) double s_dyn_stage[];
-    double *stage = s_dyn_stage + (size_t)(threadIdx.x >> 5) * BSTAGE * BG;
+    extern __shared__ __align__(16) char s_dyn_stage[];
+    char *stage = s_dyn_stage + (size_t)(threadIdx.x >> 5) * (BC_BWD_SMEM_BYTES / WARPS);
     unsigned long long te = 0, vv = 0, dag = 0;
-    unsigned long long reach[BK] = {0, 0, 0, 0};
+    unsigned long long reach[BK] = {};
     const uint32_t warp = blockIdx.x * WARPS + (threadIdx.x >> 5);
     for (uint32_t i = warp; i < cnt; i += gridDim.x * WARPS) {
         const uint32_t v = qv[i];
-        const Mask128 fm = mask_load(&qm[i]);
-        const uint32_t e0 = p.row[v], e1 = p.row[v + 1];
+        const SrcMask fm = mask_load(&qm[i]);
+        const uint2 ee = qe[i];  // = (row[v], row[v + 1]), stored at discovery
+        const uint32_t e0 = ee.x, e1 = ee.y;
         if (lane == 0) {
             te += (unsigned long long)mask_popc(fm) * (e1 - e0);
             vv += mask_popc(fm);
@@ -875,8 +931,10 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) bc_backward_kernel(BcPar
             for (int k = 0; k < BK; k++) reach[k] += (fm.w[k] >> lane) & 1u;
         }
         if (e1 - e0 > p.hub_degree && bc_defer_hub(p, level, g, v, fm)) continue;
-        const Row4 sg = bc_load_sigma<NARROW>(p, gn, v, lane, (mask_or(fm) >> lane) & 1u);
-        double acc[BK] = {-0.0, -0.0, -0.0, -0.0};  // -0.0: "nothing added yet", see bc_bwd_finish
+        const RowK sg = bc_load_sigma<NARROW>(p, gn, v, lane, (mask_or(fm) >> lane) & 1u);
+        double acc[BK];  // -0.0: "nothing added yet", see bc_bwd_finish
+#pragma unroll
+        for (int k = 0; k < BK; k++) acc[k] = -0.0;
         bc_bwd_scan<EDGE>(p, rows, Pnext, tag_next, e0, e1, 0, 32, fm, sg.x, lane, stage, acc, dag);
         bc_bwd_finish<EDGE, ENDPOINTS>(p, v, fm, sg.x, acc, rows, Pcur, tag_cur, level, lane);
     }
@@ -907,15 +965,17 @@ __global__ void __launch_bounds__(BLOCK) bc_backward_hub_kernel(BcParams p, uint
     const uint32_t tag_cur = p.tagbase + level + 1, tag_next = tag_cur + 1;
     __shared__ double s_acc[WARPS][BG];
     __shared__ unsigned long long s_dag[WARPS];
-    extern __shared__ __align__(16) double s_dyn_stage[];
-    double *stage = s_dyn_stage + (size_t)(threadIdx.x >> 5) * BSTAGE * BG;
+    extern __shared__ __align__(16) char s_dyn_stage[];
+    char *stage = s_dyn_stage + (size_t)(threadIdx.x >> 5) * (BC_BWD_SMEM_BYTES / WARPS);
 
     for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
         const uint32_t v = p.hubv[(size_t)g * p.hubcap + h];
-        const Mask128 fm = mask_load(&p.hubm[(size_t)g * p.hubcap + h]);
+        const SrcMask fm = mask_load(&p.hubm[(size_t)g * p.hubcap + h]);
         const uint32_t e0 = p.row[v], e1 = p.row[v + 1];
-        const Row4 sg = bc_load_sigma<NARROW>(p, gn, v, lane, (mask_or(fm) >> lane) & 1u);
-        double acc[BK] = {-0.0, -0.0, -0.0, -0.0};
+        const RowK sg = bc_load_sigma<NARROW>(p, gn, v, lane, (mask_or(fm) >> lane) & 1u);
+        double acc[BK];
+#pragma unroll
+        for (int k = 0; k < BK; k++) acc[k] = -0.0;
         unsigned long long dag = 0;
         bc_bwd_scan<EDGE>(p, rows, Pnext, tag_next, e0, e1, wid * 32, WARPS * 32, fm, sg.x, lane,
                           stage, acc, dag);
@@ -926,7 +986,9 @@ __global__ void __launch_bounds__(BLOCK) bc_backward_hub_kernel(BcParams p, uint
         if (lane == 0) s_dag[wid] = dag;
         __syncthreads();
         if (wid == 0) {
-            double tot[BK] = {-0.0, -0.0, -0.0, -0.0};  // stays -0.0 only if every warp's sum is -0.0
+            double tot[BK];  // stays -0.0 only if every warp's sum is -0.0
+#pragma unroll
+            for (int k = 0; k < BK; k++) tot[k] = -0.0;
             unsigned long long d = 0;
             for (int q = 0; q < WARPS; q++) {
 #pragma unroll
@@ -1010,9 +1072,10 @@ __global__ void __launch_bounds__(BLOCK)
     const uint32_t g = blockIdx.y;
     const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
     if (i >= nmem) return;
-    Mask128 *q = &p.visited[(size_t)g * p.n + members[i]];
-    Mask128 m = mask_load(q);
-    m.w[2] = m.w[3] = 0xFFFFFFFFu;
+    SrcMask *q = &p.visited[(size_t)g * p.n + members[i]];
+    SrcMask m = mask_load(q);
+#pragma unroll
+    for (int k = BK / 2; k < BK; k++) m.w[k] = 0xFFFFFFFFu;
     mask_store(q, m);
 }
 
@@ -1021,30 +1084,31 @@ template <bool NARROW>
 __global__ void __launch_bounds__(32) bc_seed_pair_kernel(BcParams p) {
     const uint32_t g = blockIdx.x;
     const int lane = lane_id();
-    const Mask128 valid = bc_valid_mask(p, g);
+    const SrcMask valid = bc_valid_mask(p, g);
     uint32_t base = 0;
 #pragma unroll
     for (int k = 0; k < BK / 2; k++) {
         const uint32_t s = p.src[(size_t)g * BG + k * 32 + lane];
         if (s != NO_SOURCE) {
             const size_t gv = (size_t)g * p.n + s;
-            Mask128 bit = mask_zero();
-            bit.w[k] = bit.w[k + 2] = 1u << lane;
-            Mask128 vis;
+            SrcMask bit = mask_zero();
+            bit.w[k] = bit.w[k + BK / 2] = 1u << lane;
+            SrcMask vis;
 #pragma unroll
             for (int j = 0; j < BK; j++) vis.w[j] = ~valid.w[j] | bit.w[j];
             mask_store(&p.visited[gv], vis);  // sources are distinct vertices outside the group
             bc_store_level(p.P0 + (size_t)g * p.n, s, p.tagbase + 1, bit);
             if (NARROW) {
                 p.sig32[gv * BG + lane * BK + k] = 1u;
-                p.sig32[gv * BG + lane * BK + k + 2] = 1u;
+                p.sig32[gv * BG + lane * BK + k + BK / 2] = 1u;
             } else {
                 p.sc[gv * BG + lane * BK + k] = 1.0;
-                p.sc[gv * BG + lane * BK + k + 2] = 1.0;
+                p.sc[gv * BG + lane * BK + k + BK / 2] = 1.0;
             }
             const uint32_t i = base + __popc(valid.w[k] & lanemask_lt());
             p.qv[(size_t)g * p.qcap + i] = s;
             mask_store(&p.qm[(size_t)g * p.qcap + i], bit);
+            p.qe[(size_t)g * p.qcap + i] = make_uint2(p.srow[s], p.srow[s + 1]);
         }
         base += __popc(valid.w[k]);
     }
@@ -1075,24 +1139,26 @@ __global__ void __launch_bounds__(BLOCK) bc_group_finalize_kernel(BcParams p, ui
     const uint32_t end = s_end, first = lc[0];  // entries [0, first) are the sources themselves
     const int lane = lane_id();
     const uint32_t *qv = p.qv + (size_t)g * p.qcap;
-    const Mask128 *qm = p.qm + (size_t)g * p.qcap;
+    const SrcMask *qm = p.qm + (size_t)g * p.qcap;
     double sum = 0.0;
     unsigned long long te = 0, vv = 0;
     for (uint32_t i = blockIdx.x * WARPS + (threadIdx.x >> 5); i < end; i += gridDim.x * WARPS) {
         const uint32_t t = qv[i];
-        const Mask128 fm = mask_load(&qm[i]);
+        const SrcMask fm = mask_load(&qm[i]);
         if (lane == 0) {
             te += (unsigned long long)mask_popc(fm) * (p.srow[t + 1] - p.srow[t]);
             vv += mask_popc(fm);
         }
         if (i < first || ((p.blocked[t >> 5] >> (t & 31)) & 1u)) continue;
-        const uint32_t full = fm.w[0] | fm.w[1];
-        const Row4 r = bc_load_sigma<NARROW>(p, (size_t)g * p.n, t, lane, (full >> lane) & 1u);
+        uint32_t full = 0;
+#pragma unroll
+        for (int k = 0; k < BK / 2; k++) full |= fm.w[k];
+        const RowK r = bc_load_sigma<NARROW>(p, (size_t)g * p.n, t, lane, (full >> lane) & 1u);
 #pragma unroll
         for (int k = 0; k < BK / 2; k++) {
             if ((fm.w[k] >> lane) & 1u) {
                 const double sf = r.x[k];
-                const double sa = ((fm.w[k + 2] >> lane) & 1u) ? r.x[k + 2] : 0.0;
+                const double sa = ((fm.w[k + BK / 2] >> lane) & 1u) ? r.x[k + BK / 2] : 0.0;
                 sum += (sf - sa) / sf;
             }
         }
@@ -1120,14 +1186,14 @@ __global__ void __launch_bounds__(BLOCK) bc_group_finalize_kernel(BcParams p, ui
 // (lane l owns bit l of the four mask words), reduced in shared memory and added once per CTA.
 // ---------------------------------------------------------------------------------------------
 template <bool ROWS>
-__global__ void __launch_bounds__(BLOCK, 5) bfs128_level_kernel(BcParams p, uint32_t level) {
+__global__ void __launch_bounds__(BLOCK, (BK == 4 ? 5 : 3)) bfs128_level_kernel(BcParams p, uint32_t level) {
     const uint32_t g = blockIdx.y;
     uint32_t *lc = p.lvlcnt + (size_t)g * p.lcap;
     uint32_t *lo = p.loff + (size_t)g * p.lcap;
     const uint32_t fcnt = lc[level];
     if (fcnt == 0) return;  // this group's BFS has finished
 
-    __shared__ Mask128 s_unv[BLOCK];
+    __shared__ SrcMask s_unv[BLOCK];
     __shared__ uint32_t s_w[BLOCK], s_ov[BLOCK], s_cnt[BG];
     __shared__ uint32_t s_ncand, s_next, s_nout, s_base;
     __shared__ unsigned long long s_te;
@@ -1142,7 +1208,7 @@ __global__ void __launch_bounds__(BLOCK, 5) bfs128_level_kernel(BcParams p, uint
     __syncthreads();
 
     const size_t gn = (size_t)g * p.n;
-    Mask128 *visited = p.visited + gn;
+    SrcMask *visited = p.visited + gn;
     const PEntry *Pcur = bc_P(p, level) + gn;
     PEntry *Pnext = bc_P(p, level + 1) + gn;
     const uint32_t tag_cur = p.tagbase + level + 1, tag_next = tag_cur + 1;
@@ -1150,7 +1216,7 @@ __global__ void __launch_bounds__(BLOCK, 5) bfs128_level_kernel(BcParams p, uint
     // 1. this CTA's 256 vertices: compact the unfinished ones (sparse levels: only marked ones)
     {
         const uint32_t w = blockIdx.x * BLOCK + tid;
-        Mask128 unv = mask_zero();
+        SrcMask unv = mask_zero();
         bool look = w < p.n;
         if (fcnt <= p.sparse_max) {
             uint32_t *word = p.maybe + (size_t)g * p.mwords + (w >> 5);
@@ -1160,7 +1226,7 @@ __global__ void __launch_bounds__(BLOCK, 5) bfs128_level_kernel(BcParams p, uint
             if (lane == 0 && bits) *word = 0;
         }
         if (look) {
-            const Mask128 vis = mask_load(&visited[w]);
+            const SrcMask vis = mask_load(&visited[w]);
 #pragma unroll
             for (int k = 0; k < BK; k++) unv.w[k] = ~vis.w[k];
         }
@@ -1179,7 +1245,7 @@ __global__ void __launch_bounds__(BLOCK, 5) bfs128_level_kernel(BcParams p, uint
     const uint32_t ncand = s_ncand;
 
     // 2. warps take candidates dynamically
-    uint32_t cnt[BK] = {0, 0, 0, 0};
+    uint32_t cnt[BK] = {};
     unsigned long long te = 0;
     for (;;) {
         uint32_t i = 0;
@@ -1187,12 +1253,12 @@ __global__ void __launch_bounds__(BLOCK, 5) bfs128_level_kernel(BcParams p, uint
         i = __shfl_sync(FULL, i, 0);
         if (i >= ncand) break;
         const uint32_t w = s_w[i];
-        const Mask128 unv = s_unv[i];
+        const SrcMask unv = s_unv[i];
         const uint32_t e0 = p.row[w], e1 = p.row[w + 1];
-        Mask128 newm = mask_zero();
+        SrcMask newm = mask_zero();
         for (uint32_t e = e0; e < e1; e += 32) {
             const uint32_t idx = e + lane;
-            Mask128 m = mask_zero();
+            SrcMask m = mask_zero();
             if (idx < e1) {
                 m = bc_level_mask(Pcur, p.col[idx], tag_cur);
 #pragma unroll
@@ -1202,9 +1268,7 @@ __global__ void __launch_bounds__(BLOCK, 5) bfs128_level_kernel(BcParams p, uint
 #pragma unroll
                 for (int k = 0; k < BK; k++) newm.w[k] |= __reduce_or_sync(FULL, m.w[k]);
                 // every missing source found: the remaining arcs cannot add anything
-                if (newm.w[0] == unv.w[0] && newm.w[1] == unv.w[1] && newm.w[2] == unv.w[2] &&
-                    newm.w[3] == unv.w[3])
-                    break;
+                if (mask_eq(newm, unv)) break;
             }
         }
         if (!mask_any(newm)) continue;
@@ -1215,7 +1279,7 @@ __global__ void __launch_bounds__(BLOCK, 5) bfs128_level_kernel(BcParams p, uint
             if (ROWS && bit) p.drows[((size_t)g * BG + 32 * k + lane) * p.n_cols + w] = (double)(level + 1);
         }
         if (lane == 0) {
-            Mask128 vis;
+            SrcMask vis;
 #pragma unroll
             for (int k = 0; k < BK; k++) vis.w[k] = ~unv.w[k] | newm.w[k];
             mask_store(&visited[w], vis);

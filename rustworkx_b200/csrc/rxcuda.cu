@@ -157,7 +157,8 @@ struct BcWorkspace {
     DevBuf<double> sc;
     DevBuf<uint32_t> sig32, overflow;  // narrow sigma rows (bc_kernels.cuh) and their overflow flag
     DevBuf<PEntry> P0, P1;
-    DevBuf<Mask128> visited, qm, hubm;
+    DevBuf<SrcMask> visited, qm, hubm;
+    DevBuf<uint2> qe;
     DevBuf<uint32_t> qv, loff, lvlcnt, lvl_total, src, hubv, hubcnt, maybe;
     DevBuf<unsigned long long> reach;
     uint64_t ng = 0;        // capacity in groups
@@ -166,7 +167,7 @@ struct BcWorkspace {
     uint32_t tagbase = 0;   // tags already used in P0/P1
     uint32_t dirty_levels = 0;  // prefix of the level tables the last batch wrote
     void release() {
-        sc.release(); sig32.release(); overflow.release(); P0.release(); P1.release(); visited.release(); qv.release(); qm.release();
+        sc.release(); sig32.release(); overflow.release(); P0.release(); P1.release(); visited.release(); qv.release(); qm.release(); qe.release();
         loff.release(); lvlcnt.release(); lvl_total.release(); src.release(); reach.release();
         hubv.release(); hubm.release(); hubcnt.release(); maybe.release();
         ng = 0;
@@ -675,7 +676,7 @@ static void bc_enable_smem() {
     if (done) return;
     auto attr = [&](const void *fn) {
         RXC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      std::max(BC_SMEM_BYTES, BC_BWD_SMEM_BYTES)));
+                                      std::max(std::max(BC_SMEM_BYTES, BC_FWD32_SMEM_BYTES), BC_BWD_SMEM_BYTES)));
     };
     attr((const void *)bc_forward_kernel<false>);
     attr((const void *)bc_forward_kernel<true>);
@@ -710,9 +711,12 @@ static uint64_t bc_ws_ensure(rxc_graph *g, uint64_t total_groups) {
     if (qcap >= 0xFFFFFFFFull)  // queue offsets are 32-bit (unreachable below ~140 GB per group)
         throw LimitError("level queues beyond 2^32 entries per group are not supported");
     // bytes per group: f64 + uint32 rows, queues, two tagged mask arrays, visited, level tables
-    const double per_group = (double)n * (1024.0 + 512.0 + 20.0 * (double)qper + 64.0 + 16.0) + (double)lcap * 8.0 + 4096.0;
+    const double per_group = (double)n * ((double)BG * 12.0 + (double)(12 + sizeof(SrcMask)) * (double)qper +
+                                          2.0 * sizeof(PEntry) + (double)sizeof(SrcMask)) +
+                             (double)lcap * 8.0 + 4096.0;
+    // default batch: 2048 sources at n = 2^20 (24 GB of rows), fewer on larger graphs
     uint64_t ng = g->opt.bc_groups > 0 ? (uint64_t)g->opt.bc_groups
-                                      : std::max<uint64_t>(1, (16ull << 20) / std::max<uint32_t>(n, 1));
+                                      : std::max<uint64_t>(1, ((16ull << 20) / std::max<uint32_t>(n, 1)) * 128 / BG);
     ng = std::min<uint64_t>(ng, 64);
     ng = std::min<uint64_t>(ng, total_groups);
     BcWorkspace &ws = g->bc_ws;
@@ -739,6 +743,7 @@ static uint64_t bc_ws_ensure(rxc_graph *g, uint64_t total_groups) {
         ws.visited.alloc((size_t)ng * n);
         ws.qv.alloc((size_t)ng * qcap);
         ws.qm.alloc((size_t)ng * qcap);
+        ws.qe.alloc((size_t)ng * qcap);
         ws.loff.alloc((size_t)ng * lcap);
         ws.lvlcnt.alloc((size_t)ng * lcap);
         ws.lvl_total.alloc(lcap);
@@ -772,7 +777,7 @@ static std::vector<uint32_t> bc_order_sources(rxc_graph *g, const std::vector<ui
     const size_t k = sources.size();
     if (!g->opt.bc_order || k <= (size_t)BK) return sources;
     cudaStream_t st = g->stream;
-    DevBuf<uint32_t> d_src;
+    DevBuf<uint32_t> d_src, d_hubs;
     DevBuf<unsigned long long> d_keys;
     d_src.alloc(k);
     d_keys.alloc(k);
@@ -782,25 +787,37 @@ static std::vector<uint32_t> bc_order_sources(rxc_graph *g, const std::vector<ui
     g->stats.launches++;
     std::vector<unsigned long long> keys(k);
     RXC_CUDA(cudaMemcpyAsync(keys.data(), d_keys.p, k * 8, cudaMemcpyDeviceToHost, st));
-    // bc_order = 2 (default): large source sets are sorted by (highest-degree neighbour, key), so that
-    // BFS-tree siblings -- children of the same hub agree on the level of almost every vertex -- share
-    // a lane.  Measured on BA(10^6,8): 16384 sources 976 -> 951 ms, 65536 sources 3911 -> 3667 ms.
+    // bc_order = 2 (default): BFS-tree siblings -- children of the same hub agree on the level of
+    // almost every vertex -- share a lane.  Every source names its highest-degree neighbour; a hub
+    // named by at least SIBLINGS sources of the call forms a cluster, clusters come first (by hub,
+    // then key), everything else follows in key order.  On a small random pool no hub has that many
+    // children and this IS the key order; on a full run nearly every source sits in a cluster.  The
+    // order is a total order on (cluster, hub, key, id): sorting a contiguous slice of a sorted list
+    // again changes nothing, so ranks can take contiguous slices of rxc_betweenness_source_order.
+    // Measured on BA(10^6,8): 16384 sources 976 -> 951 ms, 65536 sources 3911 -> 3667 ms.
     std::vector<uint32_t> hubs;
-    if (g->opt.bc_order == 2 && k >= 4096) {
-        DevBuf<uint32_t> d_hubs;
+    if (g->opt.bc_order == 2) {
         d_hubs.alloc(k);
         bc_source_hubs_kernel<<<(uint32_t)((k + WARPS - 1) / WARPS), BLOCK, 0, st>>>(
             g->succ().row.p, g->succ().col.p, d_src.p, (uint32_t)k, d_hubs.p);
         g->stats.launches++;
         hubs.resize(k);
         RXC_CUDA(cudaMemcpyAsync(hubs.data(), d_hubs.p, k * 4, cudaMemcpyDeviceToHost, st));
-        RXC_CUDA(cudaStreamSynchronize(st));  // before d_hubs goes back to the pool
     }
-    RXC_CUDA(cudaStreamSynchronize(st));
+    RXC_CUDA(cudaStreamSynchronize(st));  // also: before the device buffers go back to the pool
+    constexpr uint32_t SIBLINGS = 2 * BK;
+    if (!hubs.empty()) {  // hubs with too few children in this call do not form a cluster
+        std::vector<uint32_t> by_hub(hubs);
+        std::sort(by_hub.begin(), by_hub.end());
+        for (size_t i = 0; i < k; i++) {
+            const auto range = std::equal_range(by_hub.begin(), by_hub.end(), hubs[i]);
+            if ((size_t)(range.second - range.first) < SIBLINGS) hubs[i] = 0xFFFFFFFFu;
+        }
+    }
     std::vector<uint32_t> idx(k);
     for (size_t i = 0; i < k; i++) idx[i] = (uint32_t)i;
     std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {
-        if (!hubs.empty() && hubs[a] != hubs[b]) return hubs[a] < hubs[b];
+        if (!hubs.empty() && hubs[a] != hubs[b]) return hubs[a] < hubs[b];  // 0xFFFFFFFF (no cluster) last
         return keys[a] != keys[b] ? keys[a] > keys[b] : sources[a] < sources[b];
     });
     std::vector<uint32_t> out(k);
@@ -839,6 +856,7 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources_in, bool e
     p.visited = ws.visited.p;
     p.qv = ws.qv.p;
     p.qm = ws.qm.p;
+    p.qe = ws.qe.p;
     p.loff = ws.loff.p;
     p.lvlcnt = ws.lvlcnt.p;
     p.lvl_total = ws.lvl_total.p;
@@ -921,8 +939,8 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources_in, bool e
             [&](uint32_t level) {
                 if (p.sparse_max) bc_mark_kernel<<<dim3(MARK_CTAS, bg), BLOCK, 0, st>>>(p, level);
                 if (narrow) {
-                    bc_forward_kernel<true><<<dim3(vblocks, bg), BLOCK, BC_SMEM_BYTES, st>>>(p, level);
-                    bc_forward_hub_kernel<true><<<dim3(HUB_CTAS, bg), BLOCK, BC_SMEM_BYTES, st>>>(p, level);
+                    bc_forward_kernel<true><<<dim3(vblocks, bg), BLOCK, BC_FWD32_SMEM_BYTES, st>>>(p, level);
+                    bc_forward_hub_kernel<true><<<dim3(HUB_CTAS, bg), BLOCK, BC_FWD32_SMEM_BYTES, st>>>(p, level);
                 } else {
                     bc_forward_kernel<false><<<dim3(vblocks, bg), BLOCK, BC_SMEM_BYTES, st>>>(p, level);
                     bc_forward_hub_kernel<false><<<dim3(HUB_CTAS, bg), BLOCK, BC_SMEM_BYTES, st>>>(p, level);
@@ -1338,6 +1356,7 @@ static void bfs128_run(rxc_graph *g, const DeviceCSR &push, const DeviceCSR &pul
     p.visited = ws.visited.p;
     p.qv = ws.qv.p;
     p.qm = ws.qm.p;
+    p.qe = ws.qe.p;
     p.loff = ws.loff.p;
     p.lvlcnt = ws.lvlcnt.p;
     p.lvl_total = ws.lvl_total.p;
@@ -2329,6 +2348,18 @@ int rxc_edge_betweenness_partial(rxc_graph *g, const uint32_t *sources, uint64_t
                                  double *out) {
     if (!g || !out || (n_sources && !sources)) return RXC_ERR_INVALID;
     return guarded([&] { bc_partial(g, to_compact(g, sources, n_sources), false, true, out); });
+}
+
+int rxc_betweenness_source_order(rxc_graph *g, const uint32_t *sources, uint64_t n_sources,
+                                 uint32_t *ordered) {
+    if (!g || (n_sources && (!sources || !ordered))) return RXC_ERR_INVALID;
+    return guarded([&] {
+        std::lock_guard<std::mutex> lock(g->mu);
+        begin_call(g);
+        const std::vector<uint32_t> o = bc_order_sources(g, to_compact(g, sources, n_sources));
+        end_call(g);
+        for (uint64_t i = 0; i < n_sources; i++) ordered[i] = g->host.orig_of(o[i]);
+    });
 }
 
 int rxc_betweenness_partial_reduce(rxc_graph *g, const uint32_t *sources, uint64_t n_sources,

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(32) wsp_seed_kernel(WspParams p) {
         const uint32_t valid = __ballot_sync(FULL, s != NO_SOURCE);
         if (s != NO_SOURCE) {
             const size_t gv = (size_t)g * p.n + s;
-            Mask128 bit = mask_zero();
+            SrcMask bit = mask_zero();
             bit.w[k] = 1u << lane;
             bc_store_level(p.C0 + (size_t)g * p.n, s, p.tagbase + 1, bit);  // sources of a group are distinct
             p.dist[gv * BG + lane * BK + k] = 0.0;
@@ -117,8 +117,10 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) wsp_relax_kernel(WspPara
 
     __shared__ uint32_t s_w[BLOCK], s_e0[BLOCK], s_e1[BLOCK], s_ov[BLOCK];
     __shared__ uint32_t s_ncand, s_next, s_nout, s_base;
-    extern __shared__ __align__(16) double s_dyn_stage[];
-    double *stage = s_dyn_stage + (size_t)(threadIdx.x >> 5) * STAGE * BG;
+    extern __shared__ __align__(16) char s_dyn_stage[];
+    char *stage = s_dyn_stage + (size_t)(threadIdx.x >> 5) * (BC_SMEM_BYTES / WARPS);
+    using G = RowGeom<double>;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage);
     const int tid = threadIdx.x, lane = lane_id();
     if (tid == 0) {
         s_ncand = 0;
@@ -171,12 +173,12 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) wsp_relax_kernel(WspPara
         double best[BK];
 #pragma unroll
         for (int k = 0; k < BK; k++) best[k] = wsp_inf();
-        Mask128 touched = mask_zero();
+        SrcMask touched = mask_zero();
         for (uint32_t e = e0; e < e1; e += 32) {
             const uint32_t idx = e + lane;
             uint32_t v = 0;
             double c = 0.0;
-            Mask128 m = mask_zero();
+            SrcMask m = mask_zero();
             if (idx < e1) {
                 v = p.col[idx];
                 c = p.cost[idx];
@@ -188,6 +190,8 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) wsp_relax_kernel(WspPara
                 for (int k = 0; k < BK; k++) touched.w[k] |= __reduce_or_sync(FULL, m.w[k]);
                 relaxed += mask_popc(m);  // per lane; summed over the warp at the end
             }
+            uint32_t need_lane[G::SPL];
+            row_need<G::SPL>(m, need_lane);
             while (nz) {
                 uint32_t todo = nz;
                 int cnt = 0;
@@ -197,8 +201,10 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) wsp_relax_kernel(WspPara
                         const int a = __ffs(nz) - 1;
                         nz &= nz - 1;
                         const uint32_t vj = __shfl_sync(FULL, v, a);
-                        const uint32_t any = __shfl_sync(FULL, mask_or(m), a);
-                        cp_async_row(stage + j * BG, lane, rows + (size_t)vj * BG, any);
+                        uint32_t need[G::SPL];
+#pragma unroll
+                        for (int h = 0; h < G::SPL; h++) need[h] = __shfl_sync(FULL, need_lane[h], a);
+                        cp_async_row<double>(sbase + j * G::ROW_BYTES, lane, rows + (size_t)vj * BG, need);
                         cnt = j + 1;
                     }
                 }
@@ -209,15 +215,14 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) wsp_relax_kernel(WspPara
                     if (j < cnt) {
                         const int a = __ffs(todo) - 1;
                         todo &= todo - 1;
-                        const Mask128 mj = mask_shfl(m, a);
+                        const SrcMask mj = mask_shfl(m, a);
                         const double cj = __shfl_sync(FULL, c, a);
-                        const double2 x0 = *stage_chunk(stage + j * BG, 2 * lane);
-                        const double2 x1 = *stage_chunk(stage + j * BG, 2 * lane + 1);
+                        double xs[BK];
+                        stage_read<double>(stage + j * G::ROW_BYTES, lane, xs);
                         // next_score = node_score + cost, dijkstra.rs:128
-                        if ((mj.w[0] >> lane) & 1u) best[0] = fmin(best[0], x0.x + cj);
-                        if ((mj.w[1] >> lane) & 1u) best[1] = fmin(best[1], x0.y + cj);
-                        if ((mj.w[2] >> lane) & 1u) best[2] = fmin(best[2], x1.x + cj);
-                        if ((mj.w[3] >> lane) & 1u) best[3] = fmin(best[3], x1.y + cj);
+#pragma unroll
+                        for (int k = 0; k < BK; k++)
+                            if ((mj.w[k] >> lane) & 1u) best[k] = fmin(best[k], xs[k] + cj);
                     }
                 }
                 __syncwarp();
@@ -226,7 +231,7 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) wsp_relax_kernel(WspPara
         if (!mask_any(touched)) continue;
         // 3. compare with the vertex's own row; keep strict improvements (dijkstra.rs:131)
         const bool mine = (mask_or(touched) >> lane) & 1u;
-        const Row4 own = row_load(rows, w, lane, mine);
+        const RowK own = row_load(rows, w, lane, mine);
         uint32_t imp[BK];
 #pragma unroll
         for (int k = 0; k < BK; k++) {
@@ -234,9 +239,12 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) wsp_relax_kernel(WspPara
             if (better) rows[(size_t)w * BG + lane * BK + k] = best[k];
             imp[k] = __ballot_sync(FULL, better);
         }
-        if (imp[0] | imp[1] | imp[2] | imp[3]) {
+        uint32_t imp_any = 0;
+#pragma unroll
+        for (int k = 0; k < BK; k++) imp_any |= imp[k];
+        if (imp_any) {
             if (lane == 0) {
-                Mask128 nm;
+                SrcMask nm;
 #pragma unroll
                 for (int k = 0; k < BK; k++) nm.w[k] = imp[k];
                 bc_store_level(Cnext, w, tag_next, nm);

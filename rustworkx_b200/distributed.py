@@ -31,6 +31,17 @@ def shard_sources(sources, rank, world):
     return np.ascontiguousarray(np.asarray(sources)[rank::world])
 
 
+def contiguous_shard(ordered, rank, world):
+    """Rank r's contiguous slice of an ORDERED source list (``rxc_betweenness_source_order``): the
+    clusters of sibling sources the order forms stay together on one rank.  Every BFS of a connected
+    graph costs the same, so equal counts are equal work."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad shard {rank}/{world}")
+    ordered = np.asarray(ordered)
+    k = ordered.shape[0]
+    return np.ascontiguousarray(ordered[k * rank // world: k * (rank + 1) // world])
+
+
 def _dist():
     import torch.distributed as dist
 
@@ -84,13 +95,15 @@ def _nccl_group():
     return dist is not None and dist.get_world_size() > 1 and dist.get_backend() == "nccl"
 
 
-def _reduced_on_device(graph, kind, mine, endpoints):
+def _reduced_on_device(graph, kind, live, rank, world, endpoints):
     """The fused call: shard -> partial vector in HBM -> in-place ncclReduce -> root reads it back
     (``rxc_*_partial_reduce``); the vector never visits the host before it is combined."""
     from . import device_snapshot
 
     init_nccl_comm()
     dg = device_snapshot(graph)
+    # every rank computes the same grouping order and takes a contiguous slice of it
+    mine = contiguous_shard(dg.betweenness_source_order(live), rank, world)
     if kind == "node":
         return dg.betweenness_partial_reduce(mine, endpoints, root=0)
     return dg.edge_betweenness_partial_reduce(mine, root=0)
@@ -121,7 +134,7 @@ def betweenness_centrality(graph, normalized=True, endpoints=False, *, rank=None
     snap = graph._snapshot_arrays()
     mine = shard_sources(snap["live_nodes"], rank, world)
     if compute_partial is None and _nccl_group():
-        total = _reduced_on_device(graph, "node", mine, bool(endpoints))
+        total = _reduced_on_device(graph, "node", snap["live_nodes"], rank, world, bool(endpoints))
     else:
         fn = compute_partial or _device_partial(graph, "node")
         total = reduce_partial(fn(mine, bool(endpoints)))
@@ -142,7 +155,7 @@ def edge_betweenness_centrality(graph, normalized=True, *, rank=None, world=None
     snap = graph._snapshot_arrays()
     mine = shard_sources(snap["live_nodes"], rank, world)
     if compute_partial is None and _nccl_group():
-        total = _reduced_on_device(graph, "edge", mine, False)
+        total = _reduced_on_device(graph, "edge", snap["live_nodes"], rank, world, False)
     else:
         fn = compute_partial or _device_partial(graph, "edge")
         total = reduce_partial(fn(mine, False))

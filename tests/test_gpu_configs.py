@@ -280,3 +280,29 @@ def test_options_are_snapshotted_per_call(rx, oracle):
         t.join()
         for name, val in (("bc_sigma", 0), ("bc_order", 2), ("bc_groups", 0), ("hub_degree", 512)):
             _lib.set_option(name, val)
+
+
+def test_source_order_is_a_permutation_and_stable_on_slices(rx, oracle):
+    """rxc_betweenness_source_order: what a multi-process run cuts into contiguous per-rank slices.
+    It must be a permutation of the input (holes respected), ordering a slice again must change
+    nothing (so the clusters survive the per-rank call), and the sliced sums must add up to the
+    single-call result."""
+    from rustworkx_b200 import device_snapshot
+    from rustworkx_b200.distributed import contiguous_shard
+
+    g = rx.barabasi_albert_graph(9000, 4, seed=21)
+    for node in (5, 77, 4000):
+        g.remove_node(node)
+    dg = device_snapshot(g)
+    live = np.asarray(g.node_indices(), dtype=np.uint32)
+    order = dg.betweenness_source_order(live)
+    assert sorted(order.tolist()) == live.tolist()
+    assert not np.array_equal(order, live)  # it does reorder
+    total = np.zeros(dg.n_bound)
+    for rank in range(3):
+        mine = contiguous_shard(order, rank, 3)
+        assert np.array_equal(dg.betweenness_source_order(mine), mine)
+        total += dg.betweenness_partial(mine, False)
+    assert_close(total, dg.betweenness_partial(live, False))
+    want, _ = oracle.OracleGraph.from_graph(g).betweenness_partial(live, False, threads=host_threads())
+    assert_close(total, want)
