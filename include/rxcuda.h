@@ -197,8 +197,9 @@ int rxc_betweenness_partial_reduce(rxc_graph *g, const uint32_t *sources, uint64
  * searches have a similar level structure -- siblings of a hub first -- end up next to each other and
  * share a group and a DRAM sector.  Contributions are additive over sources, so the order never
  * changes results.  A multi-process run orders the whole list once and gives every rank a CONTIGUOUS
- * slice of it (rustworkx_b200/distributed.py), which keeps the clusters intact on every rank;
- * ordering a slice again changes nothing.  ordered[n_sources]: original node indices. */
+ * slice of it (rustworkx_b200/distributed.py), which keeps the clusters together on one rank (the
+ * per-rank call orders its slice again and finds the same clusters, except one that a slice
+ * boundary cut below the cluster size).  ordered[n_sources]: original node indices. */
 int rxc_betweenness_source_order(rxc_graph *g, const uint32_t *sources, uint64_t n_sources,
                                  uint32_t *ordered);
 int rxc_edge_betweenness_partial_reduce(rxc_graph *g, const uint32_t *sources, uint64_t n_sources,
