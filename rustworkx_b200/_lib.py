@@ -177,31 +177,81 @@ def device_count():
     return int(lib().rxc_device_count())
 
 
+# Page-locked blocks that went out of use, by (rounded) size.  Large RESULTS (a 333 MB distance matrix,
+# 134 MB of edge scores) are handed out in page-locked memory so that the DMA engine writes them at
+# PCIe speed; page-locking itself costs more than the copy, so released blocks are kept for the next
+# result of that size (at most POOL_CAP bytes in total; RXCUDA_PINNED_RESULTS=0 turns it all off).
+_POOL = {}
+_POOL_BYTES = 0
+POOL_CAP = int(os.environ.get("RXCUDA_PINNED_POOL_BYTES", 4 << 30))
+POOL_GRAIN = 1 << 20
+PINNED_RESULTS = os.environ.get("RXCUDA_PINNED_RESULTS", "1") != "0"
+PINNED_RESULT_MIN = 4 << 20
+
+
 class _PinnedBlock:
     """Owner of one ``rxc_host_alloc`` block; arrays made by :func:`pinned_empty` keep it alive."""
 
-    def __init__(self, nbytes):
-        self.ptr = _vp()
-        check(lib().rxc_host_alloc(int(nbytes), C.byref(self.ptr)))
+    def __init__(self, nbytes, pooled=False):
+        global _POOL_BYTES
+        self.pooled = bool(pooled)
         self.nbytes = int(nbytes)
+        self.ptr = _vp()
+        if self.pooled:
+            self.nbytes = (self.nbytes + POOL_GRAIN - 1) // POOL_GRAIN * POOL_GRAIN
+            free = _POOL.get(self.nbytes)
+            if free:
+                self.ptr = _vp(free.pop())
+                _POOL_BYTES -= self.nbytes
+                return
+        check(lib().rxc_host_alloc(self.nbytes, C.byref(self.ptr)))
 
     def __del__(self):
+        global _POOL_BYTES
         try:
             if self.ptr:
-                lib().rxc_host_free(self.ptr)
+                if self.pooled and _POOL_BYTES + self.nbytes <= POOL_CAP:
+                    _POOL.setdefault(self.nbytes, []).append(self.ptr.value)
+                    _POOL_BYTES += self.nbytes
+                else:
+                    lib().rxc_host_free(self.ptr)
                 self.ptr = None
         except Exception:
             pass
 
 
-def pinned_empty(shape, dtype):
+def pinned_pool_clear():
+    """Give every pooled page-locked block back to the driver."""
+    global _POOL_BYTES
+    for blocks in _POOL.values():
+        for ptr in blocks:
+            lib().rxc_host_free(_vp(ptr))
+    _POOL.clear()
+    _POOL_BYTES = 0
+
+
+def result_empty(shape, dtype=np.float64):
+    """Buffer for a result the library writes: page-locked (pooled) when it is large and a device is
+    there, plain numpy otherwise."""
+    dtype = np.dtype(dtype)
+    shape = (int(shape),) if np.isscalar(shape) else tuple(int(x) for x in shape)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    if PINNED_RESULTS and nbytes >= PINNED_RESULT_MIN:
+        try:
+            return pinned_empty(shape, dtype, pooled=True)
+        except (RxCudaError, MemoryError):
+            pass
+    return np.empty(shape, dtype=dtype)
+
+
+def pinned_empty(shape, dtype, pooled=False):
     """numpy array in page-locked host memory (``rxc_host_alloc``): the library copies such buffers
     by direct DMA instead of staging them through its own pinned slots."""
     dtype = np.dtype(dtype)
     shape = (int(shape),) if np.isscalar(shape) else tuple(int(x) for x in shape)
     nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
-    block = _PinnedBlock(max(nbytes, 1))
-    buf = (C.c_char * max(nbytes, 1)).from_address(block.ptr.value)
+    block = _PinnedBlock(max(nbytes, 1), pooled)
+    buf = (C.c_char * max(nbytes, 1)).from_address(block.ptr.value)  # (a pooled block may be larger)
     buf._rxc_owner = block  # the ctypes buffer is the array's base: ties the block's lifetime to it
     return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
 
@@ -307,7 +357,7 @@ class DeviceGraph:
         return out[: self.n_bound]
 
     def edge_betweenness(self, normalized):
-        out = np.zeros(max(self.e_bound, 1), dtype=np.float64)
+        out = result_empty(max(self.e_bound, 1))  # the library writes all e_bound entries
         check(lib().rxc_edge_betweenness(self._h, int(normalized), p_f64(out)))
         return out[: self.e_bound]
 
@@ -317,7 +367,7 @@ class DeviceGraph:
         return out[: self.n_bound]
 
     def distance_matrix(self, as_undirected, null_value):
-        out = np.empty((self.n_live, self.n_live), dtype=np.float64)
+        out = result_empty((self.n_live, self.n_live))
         if self.n_live:
             check(lib().rxc_distance_matrix(self._h, int(as_undirected), float(null_value), p_f64(out)))
         return out
@@ -371,7 +421,7 @@ class DeviceGraph:
                                         unreachable_value=float("nan")):
         w = self._edge_weights(edge_weight)
         row_end = self.n_live if row_end is None else row_end
-        out = np.empty((row_end - row_begin, self.n_live), dtype=np.float64)
+        out = result_empty((row_end - row_begin, self.n_live))
         if out.size:
             check(lib().rxc_all_pairs_dijkstra_lengths_rows(self._h, p_f64(w), float(unreachable_value),
                                                             int(row_begin), int(row_end), p_f64(out)))
@@ -415,7 +465,7 @@ class DeviceGraph:
 
     def edge_betweenness_partial(self, sources):
         src = np.ascontiguousarray(sources, dtype=np.uint32)
-        out = np.zeros(max(self.e_bound, 1), dtype=np.float64)
+        out = result_empty(max(self.e_bound, 1))  # the library writes all e_bound entries
         check(lib().rxc_edge_betweenness_partial(self._h, p_u32(src), src.shape[0], p_f64(out)))
         return out[: self.e_bound]
 
@@ -427,7 +477,7 @@ class DeviceGraph:
         return out[: src.shape[0]]
 
     def distance_matrix_rows(self, row_begin, row_end, as_undirected=False, null_value=0.0):
-        out = np.empty((row_end - row_begin, self.n_live), dtype=np.float64)
+        out = result_empty((row_end - row_begin, self.n_live))
         if out.size:
             check(lib().rxc_distance_matrix_rows(self._h, int(as_undirected), float(null_value),
                                                  int(row_begin), int(row_end), p_f64(out)))

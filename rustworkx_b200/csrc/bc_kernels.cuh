@@ -305,6 +305,13 @@ constexpr int BC_FWD32_SMEM_BYTES = WARPS * FWD32_SLOTS * BG * 4;
 #endif
 constexpr int BSTAGE = RXC_BSTAGE;
 constexpr int BC_BWD_SMEM_BYTES = WARPS * BSTAGE * BG * 8;
+// edge mode: rows in flight per warp, and arcs per pass of the cross-lane exchange network
+#ifndef RXC_ESTAGE
+#define RXC_ESTAGE BSTAGE
+#endif
+constexpr int ESTAGE = RXC_ESTAGE;
+constexpr int ER = 4;
+static_assert(ESTAGE <= BSTAGE, "edge mode stages into the dependency kernels' slots");
 
 // Geometry of one staged row of BG elements: CPL 16-byte chunks per lane (1, 2 or 4), i.e. CPL
 // warp-wide copy instructions whose global side is 512 contiguous bytes each.
@@ -799,11 +806,12 @@ __device__ __forceinline__ void bc_bwd_scan(const BcParams &p, const double *row
             uint32_t need_lane[G::SPL];
             row_need<G::SPL>(m, need_lane);
             while (nz) {
-                // stage up to STAGE successor rows, then form per-arc sums over all sources of the group
+                // stage up to ESTAGE successor rows, then form per-arc sums over all sources of the
+                // group, ER arcs per pass of the exchange network
                 uint32_t todo = nz;
                 int cnt = 0;
 #pragma unroll
-                for (int i = 0; i < STAGE; i++) {
+                for (int i = 0; i < ESTAGE; i++) {
                     if (nz) {  // warp-uniform
                         const int a = __ffs(nz) - 1;
                         nz &= nz - 1;
@@ -817,48 +825,52 @@ __device__ __forceinline__ void bc_bwd_scan(const BcParams &p, const double *row
                 }
                 cp_async_wait_all();
                 __syncwarp();  // the chunks a lane reads were copied by other lanes
-                double c[STAGE];
-                uint32_t my_e = 0;
 #pragma unroll
-                for (int i = 0; i < STAGE; i++) {
-                    c[i] = 0.0;
-                    if (i < cnt) {
-                        const int a = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        const SrcMask mj = mask_shfl(m, a);
-                        const uint32_t ej = __shfl_sync(FULL, ed, a);
-                        if (lane / (32 / STAGE) == i) my_e = ej;
-                        double xs[BK];
-                        stage_read<double>(stage + i * G::ROW_BYTES, lane, xs);
+                for (int b = 0; b < ESTAGE; b += ER) {
+                    if (b < cnt) {  // warp-uniform
+                        double c[ER];
+                        uint32_t my_e = 0;
 #pragma unroll
-                        for (int k = 0; k < BK; k++) {
-                            if ((mj.w[k] >> lane) & 1u) {
-                                const double ck = sig[k] * xs[k];  // sigma[v]*coeff, centrality.rs:322
-                                acc[k] += ck;
-                                c[i] += ck;
+                        for (int i = 0; i < ER; i++) {
+                            c[i] = 0.0;
+                            if (b + i < ESTAGE && b + i < cnt) {
+                                const int a = __ffs(todo) - 1;
+                                todo &= todo - 1;
+                                const SrcMask mj = mask_shfl(m, a);
+                                const uint32_t ej = __shfl_sync(FULL, ed, a);
+                                if (lane / (32 / ER) == i) my_e = ej;
+                                double xs[BK];
+                                stage_read<double>(stage + (b + i) * G::ROW_BYTES, lane, xs);
+#pragma unroll
+                                for (int k = 0; k < BK; k++) {
+                                    if ((mj.w[k] >> lane) & 1u) {
+                                        const double ck = sig[k] * xs[k];  // sigma[v]*coeff, centrality.rs:322
+                                        acc[k] += ck;
+                                        c[i] += ck;
+                                    }
+                                }
                             }
                         }
+                        // reduce the ER per-arc sums over the warp at once: log2(ER) halving exchanges
+                        // leave lane l with arc l / (32/ER); the remaining butterfly steps finish the sum
+                        int off = 16;
+#pragma unroll
+                        for (int half = ER / 2; half >= 1; half >>= 1, off >>= 1) {
+                            const bool upper = lane & off;
+#pragma unroll
+                            for (int j = 0; j < half; j++) {
+                                const double send = upper ? c[j] : c[j + half];
+                                const double recv = __shfl_xor_sync(FULL, send, off);
+                                c[j] = (upper ? c[j + half] : c[j]) + recv;
+                            }
+                        }
+                        double tot = c[0];
+#pragma unroll
+                        for (; off >= 1; off >>= 1) tot += __shfl_xor_sync(FULL, tot, off);
+                        if (lane % (32 / ER) == 0 && b + lane / (32 / ER) < cnt) atomicAdd(&p.acc[my_e], tot);
                     }
                 }
                 __syncwarp();  // the slots may be refilled by other lanes from here on
-                // reduce the STAGE per-arc sums over the warp at once: log2(STAGE) halving exchanges
-                // leave lane l with arc l / (32/STAGE); the remaining butterfly steps finish the sum
-                static_assert(STAGE == 8 || STAGE == 4 || STAGE == 2, "exchange network: STAGE must be 2, 4 or 8");
-                int off = 16;
-#pragma unroll
-                for (int half = STAGE / 2; half >= 1; half >>= 1, off >>= 1) {
-                    const bool upper = lane & off;
-#pragma unroll
-                    for (int j = 0; j < half; j++) {
-                        const double send = upper ? c[j] : c[j + half];
-                        const double recv = __shfl_xor_sync(FULL, send, off);
-                        c[j] = (upper ? c[j + half] : c[j]) + recv;
-                    }
-                }
-                double tot = c[0];
-#pragma unroll
-                for (; off >= 1; off >>= 1) tot += __shfl_xor_sync(FULL, tot, off);
-                if (lane % (32 / STAGE) == 0 && lane / (32 / STAGE) < cnt) atomicAdd(&p.acc[my_e], tot);
             }
         }
     }

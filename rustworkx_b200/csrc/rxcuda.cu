@@ -132,6 +132,7 @@ struct Options {
     int64_t bc_sigma = 0;           // betweenness sigma rows: 0 auto (uint32, f64 on overflow), 1 f64, 2 uint32
     int64_t bfs_threads = 0;        // CTA-per-source BFS: threads per CTA (0: 1024 for n >= 2^18, else 256)
     int64_t bfs_ell = 1;            // CTA-per-source BFS: ELL adjacency when every vertex has <= 4 arcs
+    int64_t bc_siblings = 2;        // bc_order 2: a hub named by at least this many sources of the call forms a cluster
     int64_t bc_order = 2;           // betweenness source grouping: 0 off, 1 two-hop key, 2 key + hub siblings for >= 4096 sources
 };
 static Options g_opt;      // process-wide defaults (rxc_set_option), guarded by g_opt_mu
@@ -789,7 +790,7 @@ static std::vector<uint32_t> bc_order_sources(rxc_graph *g, const std::vector<ui
     RXC_CUDA(cudaMemcpyAsync(keys.data(), d_keys.p, k * 8, cudaMemcpyDeviceToHost, st));
     // bc_order = 2 (default): BFS-tree siblings -- children of the same hub agree on the level of
     // almost every vertex -- share a lane.  Every source names its highest-degree neighbour; a hub
-    // named by at least SIBLINGS sources of the call forms a cluster, clusters come first (by hub,
+    // named by at least `bc_siblings` sources of the call forms a cluster, clusters come first (by hub,
     // then key), everything else follows in key order.  On a small random pool no hub has that many
     // children and this IS the key order; on a full run nearly every source sits in a cluster.  Ranks
     // of a multi-process run take contiguous slices of this order (rxc_betweenness_source_order):
@@ -805,7 +806,7 @@ static std::vector<uint32_t> bc_order_sources(rxc_graph *g, const std::vector<ui
         RXC_CUDA(cudaMemcpyAsync(hubs.data(), d_hubs.p, k * 4, cudaMemcpyDeviceToHost, st));
     }
     RXC_CUDA(cudaStreamSynchronize(st));  // also: before the device buffers go back to the pool
-    constexpr uint32_t SIBLINGS = 2 * BK;
+    const uint32_t SIBLINGS = (uint32_t)std::max<int64_t>(1, g->opt.bc_siblings);
     if (!hubs.empty()) {  // hubs with too few children in this call do not form a cluster
         std::vector<uint32_t> by_hub(hubs);
         std::sort(by_hub.begin(), by_hub.end());
@@ -2625,6 +2626,7 @@ int rxc_set_option(const char *name, int64_t value) {
     else if (k == "hub_degree" && value > 0) g_opt.hub_degree = value;
     else if (k == "bfs_mode" && value >= 0 && value <= 3) g_opt.bfs_mode = value;
     else if (k == "bc_order" && value >= 0 && value <= 2) g_opt.bc_order = value;
+    else if (k == "bc_siblings" && value >= 1) g_opt.bc_siblings = value;
     else if (k == "bfs_depth_switch" && value >= 0) g_opt.bfs_depth_switch = value;
     else if (k == "bfs_threads" && (value == 0 || value == 128 || value == 256 || value == 512 || value == 1024)) g_opt.bfs_threads = value;
     else if (k == "bc_sigma" && value >= 0 && value <= 2) g_opt.bc_sigma = value;

@@ -7,10 +7,12 @@ import numpy as np
 import rustworkx_b200 as rx
 from rustworkx_b200 import _lib
 n = int(os.environ.get("N", 1_000_000)); reps = int(os.environ.get("REPS", 2))
-g = rx.barabasi_albert_graph(n, 8, seed=1)
+g = (rx.directed_gnm_random_graph(2**20, 2**24, seed=7) if os.environ.get("GRAPH") == "gnm"
+     else rx.barabasi_albert_graph(n, 8, seed=1))
+n = g.num_nodes()
 dg = rx.device_snapshot(g)
 plan = np.random.default_rng(12345).permutation(n).astype(np.uint32)
-DEFAULTS = {"bc_order": 2, "bc_groups": 0, "bc_sigma": 0, "hub_degree": 512, "bc_sparse_div": 16}
+DEFAULTS = {"bc_order": 2, "bc_groups": 0, "bc_sigma": 0, "hub_degree": 512, "bc_sparse_div": 16, "bc_siblings": 2}
 ref = {}
 for spec in sys.argv[1:]:
     kv = dict(x.split("=") for x in spec.split(";") if x)

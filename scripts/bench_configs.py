@@ -1,44 +1,166 @@
-"""Timing of the other BASELINE.json configs (closeness / distance_matrix / edge BC) on one GPU."""
-import sys, time, os, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
-import rustworkx_b200 as rx
-from rustworkx_b200 import _lib
+"""The other BASELINE.json configs (everything except configs[2], which is bench.py's line), one JSON
+record per case with the same evidence fields as the bench line: device time, e2e through the public
+API, roofline against the measured HBM peak on SURVEY 8d's algorithmic bytes, and the CPU oracle
+timed beside it on the box's host cores.
 
-def timed(label, fn, dg, te_bytes=None):
-    t0 = time.perf_counter(); out = fn(); wall = time.perf_counter() - t0
-    st = dg.stats()
-    gteps = st["te"] / (st["ms_total"] * 1e-3) / 1e9 if st["ms_total"] else 0
-    print(json.dumps({"case": label, "wall_s": round(wall, 4), "device_ms": round(st["ms_total"], 3),
-                      "gteps_device": round(gteps, 2), "te": st["te"], "v": st["v"], "levels": st["levels"],
-                      "launches": st["launches"], "batches": st["batches"], "d2h_ms": round(st["ms_d2h"], 2)}), flush=True)
+    python scripts/bench_configs.py [c1] [c2a] [c2b] [c4] [c5] > profiles/r02_configs.json
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import numpy as np  # noqa: E402
+
+import oracle  # noqa: E402
+import rustworkx_b200 as rx  # noqa: E402
+from rustworkx_b200 import _lib  # noqa: E402
+
+THREADS = max(1, len(os.sched_getaffinity(0)))
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    PEAK = 6650.0
+
+BYTES = {
+    "bc": lambda te, dag, v, n: 16 * te + 24 * dag + 44 * v,
+    "ebc": lambda te, dag, v, n: 16 * te + 36 * dag + 36 * v,
+    "cc": lambda te, dag, v, n: 8 * te + 20 * v,
+    "dm": lambda te, dag, v, n: 8 * te + 12 * v + 8 * n * n,
+}
+
+
+def best_of(fn, dg, reps=3):
+    best, out = None, None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        out = fn()
+        wall = time.perf_counter() - t0
+        st = dg.stats()
+        if best is None or st["ms_total"] < best[1]["ms_total"]:
+            best = (wall, st)
+    return best[0], best[1], out
+
+
+def record(case, config, op, kind, dg, fn, cpu_fn, cpu_note, n, e2e_fn=None, sources=None):
+    wall, st, out = best_of(fn, dg)
+    te, dag, v = st["te"], st["te_dag"], st["v"]
+    algo = BYTES[kind](te, dag, v, n)
+    dev_s = st["ms_total"] * 1e-3
+    rec = {"case": case, "config": config, "op": op, "sources": sources, "device_ms": round(st["ms_total"], 3),
+           "call_wall_ms": round(wall * 1e3, 3), "gteps_device": round(te / dev_s / 1e9, 2) if dev_s else None,
+           "te": te, "te_dag": dag, "v": v, "launches": st["launches"], "batches": st["batches"],
+           "d2h_ms": round(st["ms_d2h"], 2),
+           "roofline": {"bound": "hbm", "achieved": round(algo / dev_s / 1e9, 1), "peak": PEAK, "unit": "GB/s",
+                        "frac": round(algo / dev_s / 1e9 / PEAK, 4), "bytes_model": kind,
+                        "note": "algorithmic bytes (SURVEY 8d) / device time of the whole call"}}
+    if e2e_fn is not None:  # public API: snapshot from host arrays + call + result on the host
+        e2e_fn()
+        t0 = time.perf_counter()
+        e2e_fn()
+        e2e = time.perf_counter() - t0
+        rec["e2e_ms"] = round(e2e * 1e3, 3)
+        rec["gteps_e2e"] = round(te / e2e / 1e9, 2)
+    t0 = time.perf_counter()
+    cpu_te = cpu_fn()
+    cpu_s = time.perf_counter() - t0
+    rec["cpu_baseline"] = {"value": round(cpu_te / cpu_s / 1e9, 4), "unit": "GTEPS", "cores": THREADS,
+                           "kind": "port", "sample": f"{cpu_note}, {cpu_s:.1f} s"}
+    print(json.dumps(rec), flush=True)
     return out
 
-for kv in os.environ.get("OPT", "").split(","):
-    if "=" in kv:
-        _lib.set_option(kv.split("=")[0], int(kv.split("=")[1]))
-which = sys.argv[1:] or ["hh", "grid", "gnm"]
-if "hh" in which:
+
+which = sys.argv[1:] or ["c1", "c2a", "c2b", "c4", "c5"]
+
+if "c1" in which:
+    cfg = "configs[0]: betweenness_centrality on undirected_gnp_random_graph(5000, 0.002, seed=42)"
+    g = rx.undirected_gnp_random_graph(5000, 0.002, seed=42)
+    og = oracle.OracleGraph.from_graph(g)
+    dg = rx.device_snapshot(g)
+    for normalized, endpoints in ((True, False), (True, True), (False, False), (False, True)):
+        def cpu():
+            _, st = og.betweenness_centrality(endpoints, normalized, 50, return_stats=True, as_arrays=True)
+            return st["te"]
+
+        def e2e():
+            rx.set_snapshot_cache(False)
+            try:
+                return rx.betweenness_centrality(g, normalized=normalized, endpoints=endpoints)
+            finally:
+                rx.set_snapshot_cache(True)
+
+        record(f"gnp(5000,0.002) betweenness normalized={normalized} endpoints={endpoints}", cfg,
+               "betweenness_centrality", "bc", dg, lambda: dg.betweenness(endpoints, normalized), cpu,
+               "the full call, all 5000 sources (oracle, parallel_threshold=50)", g.num_nodes(), e2e, 5000)
+
+if "c2a" in which:
+    cfg = "configs[1]: distance_matrix + closeness_centrality on heavy_hex_graph(51)"
     g = rx.generators.heavy_hex_graph(51)
+    n = g.num_nodes()
+    og = oracle.OracleGraph.from_graph(g)
     dg = rx.device_snapshot(g)
-    for rep in range(2):
-        timed("heavy_hex(51) closeness", lambda: dg.closeness(True), dg)
-    for rep in range(2):
-        timed("heavy_hex(51) distance_matrix", lambda: dg.distance_matrix(True, 0.0), dg)
-if "grid" in which:
-    side = int(os.environ.get("GRID", "1000"))
-    g = rx.generators.grid_graph(side, side)
+
+    def uncached(fn):
+        def run():
+            rx.set_snapshot_cache(False)
+            try:
+                return fn()
+            finally:
+                rx.set_snapshot_cache(True)
+        return run
+
+    for wf in (True, False):
+        record(f"heavy_hex(51) closeness wf_improved={wf}", cfg, "closeness_centrality", "cc", dg,
+               lambda: dg.closeness(wf),
+               lambda: og.closeness_centrality(wf, 50, return_stats=True, as_arrays=True)[1]["te"],
+               "the full call, all 6451 sources", n, uncached(lambda: rx.closeness_centrality(g, wf_improved=wf)), n)
+    record("heavy_hex(51) distance_matrix", cfg, "distance_matrix", "dm", dg, lambda: dg.distance_matrix(True, 0.0),
+           lambda: og.distance_matrix(300, True, 0.0, return_stats=True)[1]["te"],
+           "the full call (n x n bitset algorithm, distance_matrix.rs:107-157)", n,
+           uncached(lambda: rx.distance_matrix(g)), n)
+
+if "c2b" in which:
+    cfg = "configs[1]: closeness_centrality on grid_graph(1000, 1000)"
+    g = rx.generators.grid_graph(1000, 1000)
+    n = g.num_nodes()
+    og = oracle.OracleGraph.from_graph(g)
     dg = rx.device_snapshot(g)
-    nsrc = int(os.environ.get("GRID_SOURCES", "131072"))
-    src = np.random.default_rng(0).choice(side * side, size=min(nsrc, side * side), replace=False).astype(np.uint32)
-    src.sort()
-    for rep in range(2):
-        timed(f"grid({side},{side}) closeness, {len(src)} sampled sources", lambda: dg.closeness_partial(src, True), dg)
-if "gnm" in which:
+    src = np.sort(np.random.default_rng(0).choice(n, size=65536, replace=False)).astype(np.uint32)
+    k = 4 * THREADS
+    record("grid(1000,1000) closeness, 65536 sampled sources (full call = 15.3x)", cfg, "closeness_centrality",
+           "cc", dg, lambda: dg.closeness_partial(src, True),
+           lambda: og.closeness_partial(src[:k], True, threads=THREADS)[1]["te"], f"{k} of those sources", n,
+           None, 65536)
+
+if "c4" in which:
+    cfg = "configs[3]: edge_betweenness_centrality on directed_gnm_random_graph(2**20, 2**24, seed=7)"
     g = rx.directed_gnm_random_graph(2**20, 2**24, seed=7)
+    n = g.num_nodes()
+    og = oracle.OracleGraph.from_graph(g)
     dg = rx.device_snapshot(g)
-    src = np.random.default_rng(0).choice(2**20, size=512, replace=False).astype(np.uint32)
-    for rep in range(2):
-        timed("directed_gnm(2^20,2^24) edge betweenness, 512 sources", lambda: dg.edge_betweenness_partial(src), dg)
-    for rep in range(2):
-        timed("directed_gnm(2^20,2^24) node betweenness, 512 sources", lambda: dg.betweenness_partial(src), dg)
+    src = np.random.default_rng(0).choice(n, size=4096, replace=False).astype(np.uint32)
+    k = 2 * THREADS
+    record("directed_gnm(2^20,2^24) edge betweenness, 4096 sampled sources", cfg, "edge_betweenness_centrality",
+           "ebc", dg, lambda: dg.edge_betweenness_partial(src),
+           lambda: og.edge_betweenness_partial(src[:k], threads=THREADS)[1]["te"], f"{k} of those sources", n,
+           None, 4096)
+    record("directed_gnm(2^20,2^24) node betweenness, 4096 sampled sources", cfg, "betweenness_centrality",
+           "bc", dg, lambda: dg.betweenness_partial(src, False),
+           lambda: og.betweenness_partial(src[:k], False, threads=THREADS)[1]["te"], f"{k} of those sources", n,
+           None, 4096)
+
+if "c5" in which:
+    cfg = "configs[4]: all-sources betweenness on a 4M-node power-law graph (barabasi_albert_graph(4_000_000, 8, seed=3))"
+    g = rx.barabasi_albert_graph(4_000_000, 8, seed=3)
+    n = g.num_nodes()
+    og = oracle.OracleGraph.from_graph(g)
+    dg = rx.device_snapshot(g)
+    src = np.random.default_rng(0).choice(n, size=4096, replace=False).astype(np.uint32)
+    k = THREADS
+    record("BA(4M,8) betweenness, 4096 sampled sources", cfg, "betweenness_centrality", "bc", dg,
+           lambda: dg.betweenness_partial(src, False),
+           lambda: og.betweenness_partial(src[:k], False, threads=THREADS)[1]["te"], f"{k} of those sources", n,
+           None, 4096)
