@@ -7,7 +7,8 @@ seed=1)`` -- BASELINE.json configs[2], the configuration the metric is quoted on
 A *step* is one pass of the hot path over one batch of synthetic input: a FIXED set of
 ``--sources-per-step`` sources (default 65536, a seeded uniform sample of the 10^6 sources of the
 full job), whatever the number of GPUs -- **strong scaling**.  The step's sources are put into the
-library's grouping order and cut into N contiguous slices, one per rank (one process per GPU, CSR
+library's grouping order, cut into chunks of 256 (whole kernel groups) and dealt round-robin to the
+N ranks (one process per GPU, CSR
 replicated); every rank runs forward BFS + sigma
 and the dependency sweep for its share and accumulates a partial centrality vector in HBM; ONE
 in-place ``ncclReduce`` over NVLink combines the partial vectors and rank 0 reads the result back
@@ -295,12 +296,12 @@ def run_b200(args):
     T = args.sources_per_step
 
     def my_sources(step, handle=None):
-        """This rank's share of the step: a contiguous slice of the library's grouping order of the
-        step's sources (every rank computes the same order), so sibling clusters stay on one rank."""
-        from rustworkx_b200.distributed import contiguous_shard
+        """This rank's share of the step: chunks of the library's grouping order of the step's
+        sources (every rank computes the same order), so sibling clusters stay on one rank."""
+        from rustworkx_b200.distributed import group_shard
 
         ordered = (handle or dg).betweenness_source_order(step_sources(plan, step, T))
-        return contiguous_shard(ordered, rank, world)
+        return group_shard(ordered, rank, world)
 
     # Host inputs live in page-locked memory (rxc_host_alloc), as a binding that assembles the edge
     # arrays itself would hold them: the snapshot's H2D is then one DMA per array.  A graph from which
@@ -406,12 +407,12 @@ def run_b200(args):
     # ---- the whole job (every vertex a source), N = 8 or --full-run ------------------------------
     full = None
     if args.full_run or world == 8:
-        from rustworkx_b200.distributed import contiguous_shard
+        from rustworkx_b200.distributed import group_shard
 
         barrier()
         t0 = time.perf_counter()
         g3 = make_device_graph()
-        mine = contiguous_shard(g3.betweenness_source_order(np.arange(n, dtype=np.uint32)), rank, world)
+        mine = group_shard(g3.betweenness_source_order(np.arange(n, dtype=np.uint32)), rank, world)
         vec = g3.betweenness_partial_reduce(mine, False, root=0, out=host_out)
         barrier()
         full_s = time.perf_counter() - t0
@@ -523,8 +524,8 @@ def run_b200(args):
             "batches": agg["batches"], "wall_ms": wall_ms_max, "reduce_ms_per_step": agg["ms_reduce"] / max(args.steps, 1),
             "sources_per_step": T, "sources_per_step_per_gpu": int(src_all / max(args.steps, 1) / world),
             "host_gap_ms_per_step": (wall_ms_max - device_ms_max) / max(args.steps, 1),
-            "sharding": f"each step's {T} sources in the library's grouping order, cut into {world} contiguous "
-                        "slice(s), CSR replicated, one in-HBM ncclReduce per step",
+            "sharding": f"each step's {T} sources in the library's grouping order, chunks of 256 dealt round-robin "
+                        f"to {world} rank(s), CSR replicated, one in-HBM ncclReduce per step",
             "l2": "inputs larger than L2 (per-batch state >= 2 GB vs 126 MB L2)",
             "timing": "CUDA events on the library stream (rxc_stats.ms_total + ms_reduce), max over ranks"}
     if full:

@@ -288,7 +288,7 @@ def test_source_order_is_a_permutation_and_stable_on_slices(rx, oracle):
     permutation of the slice (the per-rank call does that), and the sliced sums must add up to the
     single-call result."""
     from rustworkx_b200 import device_snapshot
-    from rustworkx_b200.distributed import contiguous_shard
+    from rustworkx_b200.distributed import group_shard
 
     g = rx.barabasi_albert_graph(9000, 4, seed=21)
     for node in (5, 77, 4000):
@@ -300,7 +300,7 @@ def test_source_order_is_a_permutation_and_stable_on_slices(rx, oracle):
     assert not np.array_equal(order, live)  # it does reorder
     total = np.zeros(dg.n_bound)
     for rank in range(3):
-        mine = contiguous_shard(order, rank, 3)
+        mine = group_shard(order, rank, 3)
         assert sorted(dg.betweenness_source_order(mine).tolist()) == sorted(mine.tolist())
         total += dg.betweenness_partial(mine, False)
     assert_close(total, dg.betweenness_partial(live, False))

@@ -531,3 +531,22 @@ def test_generator_library_is_separate(rx):
         assert not hasattr(L, name), f"{name} must not be exported by librxcuda.so"
     g = rx.barabasi_albert_graph(500, 3, seed=5)
     assert g.num_nodes() == 500 and g.num_edges() == 2 + 3 * 497
+
+
+def test_group_shard_partitions_an_ordered_list(rx):
+    """Multi-process sharding of the ORDERED source list: whole chunks of 256 dealt round-robin -- a
+    partition of the list, clusters (consecutive runs) kept together, ranks balanced."""
+    from rustworkx_b200.distributed import SHARD_CHUNK, group_shard
+
+    order = np.random.default_rng(0).permutation(70000).astype(np.uint32)
+    for world in (1, 2, 4, 8):
+        parts = [group_shard(order, r, world) for r in range(world)]
+        assert sorted(np.concatenate(parts).tolist()) == sorted(order.tolist())
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= SHARD_CHUNK
+        for r, p in enumerate(parts):  # every chunk is a run of the ordered list
+            first = p[:SHARD_CHUNK]
+            start = r * SHARD_CHUNK
+            assert np.array_equal(first, order[start:start + SHARD_CHUNK])
+    with pytest.raises(ValueError):
+        group_shard(order, 3, 3)
+    assert group_shard(order[:100], 1, 2).shape == (0,)
