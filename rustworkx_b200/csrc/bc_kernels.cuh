@@ -291,12 +291,23 @@ __device__ __forceinline__ RowK row_load(const double *rows, uint32_t v, int lan
 #define RXC_FWD32_MINBLOCKS (BK == 4 ? 5 : 3)  // BK = 4: 46 registers, no spills: 28.0 -> 25.9 ms per 1024 sources
 #endif
 #ifndef RXC_FWD32_SLOTS
-#define RXC_FWD32_SLOTS (BK == 4 ? 8 : 6)
+#define RXC_FWD32_SLOTS 6  // BK = 4: 6 slots + the arc table keep the narrow forward kernel at 5 CTAs per SM
 #endif
+// Arc table (RXC_ARCTAB, default on): the arcs a look-up found on the frontier are compacted into a
+// small per-warp table in shared memory -- (vertex, sector-need) and the source mask per arc -- and
+// the staging loops walk that dense list with broadcast LDS reads.  ncu on the shuffle form (arc a
+// of the look-up lives in lane a: find-first-set on the ballot, clear the bit, 2 shuffles to stage
+// the row, 4 more to fetch its mask when the row is consumed) counted 78 issued instructions per
+// gathered row with the issue slots 80 % busy in the big forward launches; the table removes the
+// bit scans and 6 of the 6.2 shuffles per row.
+#ifndef RXC_ARCTAB
+#define RXC_ARCTAB 1
+#endif
+constexpr int ARCTAB_BYTES = RXC_ARCTAB ? 32 * 8 + (BK == 8 ? 32 * 4 : 0) + 32 * 16 * MQ : 0;  // per warp
 constexpr int STAGE = RXC_STAGE;  // f64 row slots per warp in the forward / edge / weighted kernels
-constexpr int BC_SMEM_BYTES = WARPS * STAGE * BG * 8;  // BK = 4: 32 KB per CTA
+constexpr int BC_SMEM_BYTES = WARPS * (STAGE * BG * 8 + ARCTAB_BYTES);  // BK = 4: 32 KB + tables per CTA
 constexpr int FWD32_SLOTS = RXC_FWD32_SLOTS;  // uint32 row slots per warp in the narrow forward kernels
-constexpr int BC_FWD32_SMEM_BYTES = WARPS * FWD32_SLOTS * BG * 4;
+constexpr int BC_FWD32_SMEM_BYTES = WARPS * (FWD32_SLOTS * BG * 4 + ARCTAB_BYTES);
 // The dependency kernels have no static shared memory, so 6 row slots per warp still fit 4 CTAs per
 // SM (4 x 48 KB) with groups of 128: measured 45.3 -> 43.3 ms per 1024 sources; the forward kernels
 // (10 KB static) would drop to 3 CTAs per SM with 6 slots and lose 3 ms.
@@ -304,7 +315,7 @@ constexpr int BC_FWD32_SMEM_BYTES = WARPS * FWD32_SLOTS * BG * 4;
 #define RXC_BSTAGE (BK == 4 ? 6 : 5)
 #endif
 constexpr int BSTAGE = RXC_BSTAGE;
-constexpr int BC_BWD_SMEM_BYTES = WARPS * BSTAGE * BG * 8;
+constexpr int BC_BWD_SMEM_BYTES = WARPS * (BSTAGE * BG * 8 + ARCTAB_BYTES);
 // edge mode: rows in flight per warp, and arcs per pass of the cross-lane exchange network
 #ifndef RXC_ESTAGE
 #define RXC_ESTAGE BSTAGE
@@ -349,10 +360,14 @@ __device__ __forceinline__ void row_need(const SrcMask &m, uint32_t (&need)[SPL]
     }
 }
 
+// lane_rows = (const char *)rows + 16 * lane: this lane's chunk of row 0, formed once by the caller,
+// so that a row's address is one multiply-add on it (ncu: the base used to be re-assembled from two
+// partial 64-bit sums for every row)
 template <class Elem>
-__device__ __forceinline__ void cp_async_row(uint32_t slot_smem, int lane, const Elem *grow,
+__device__ __forceinline__ void cp_async_row(uint32_t slot_smem, int lane, const char *lane_rows, uint32_t v,
                                              const uint32_t (&need)[RowGeom<Elem>::SPL]) {
     constexpr int CPL = RowGeom<Elem>::CPL;
+    const char *grow = lane_rows + (size_t)v * RowGeom<Elem>::ROW_BYTES;
 #pragma unroll
     for (int j = 0; j < CPL; j++) {
         const int c = 32 * j + lane;
@@ -373,7 +388,7 @@ __device__ __forceinline__ void cp_async_row(uint32_t slot_smem, int lane, const
             "setp.ne.u32 p1, %2, 0;\n"
             "@p1 cp.async.cg.shared.global [%0], [%1], 16;\n"
             "}\n" ::"r"(dst),
-            "l"(reinterpret_cast<const char *>(grow) + 16 * c), "r"(on)
+            "l"(grow + 512 * j), "r"(on)
             : "memory");
     }
 }
@@ -417,8 +432,54 @@ __device__ __forceinline__ void bc_gather(const Elem *rows, uint32_t v_lane, con
                                           uint32_t nz, int lane, char *stage, Acc (&acc)[BK]) {
     using G = RowGeom<Elem>;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage);
+    const char *lane_rows = reinterpret_cast<const char *>(rows) + 16 * lane;
+    asm("" : "+l"(lane_rows));  // keep it one 64-bit value (else the compiler re-adds a uniform part per row)
     uint32_t need_lane[G::SPL];
     row_need<G::SPL>(m_lane, need_lane);
+#if RXC_ARCTAB
+    // the table sits behind this warp's NS row slots: vn[32] = (vertex, need[0]), [need1[32]], m[32]
+    char *tab = stage + NS * G::ROW_BYTES;
+    uint2 *t_vn = reinterpret_cast<uint2 *>(tab);
+    uint32_t *t_need1 = reinterpret_cast<uint32_t *>(tab + 32 * 8);
+    SrcMask *t_m = reinterpret_cast<SrcMask *>(tab + 32 * 8 + (BK == 8 ? 32 * 4 : 0));
+    if (nz == 0) return;  // warp-uniform
+    const int total = __popc(nz);
+    if ((nz >> lane) & 1u) {
+        const int pos = __popc(nz & lanemask_lt());
+        t_vn[pos] = make_uint2(v_lane, need_lane[0]);
+        if (G::SPL == 2) t_need1[pos] = need_lane[G::SPL - 1];
+        mask_store(&t_m[pos], m_lane);
+    }
+    __syncwarp();
+    for (int j0 = 0; j0 < total; j0 += NS) {
+        const int cnt = min(NS, total - j0);
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+            if (i < cnt) {  // warp-uniform
+                const uint2 e = t_vn[j0 + i];  // broadcast read
+                uint32_t need[G::SPL];
+                need[0] = e.y;
+                if (G::SPL == 2) need[G::SPL - 1] = t_need1[j0 + i];
+                cp_async_row<Elem>(sbase + i * G::ROW_BYTES, lane, lane_rows, e.x, need);
+            }
+        }
+        cp_async_wait_all();
+        if (G::CPL > 1) __syncwarp();  // the chunks a lane reads were copied by other lanes
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+            if (i < cnt) {
+                const SrcMask mj = mask_load(&t_m[j0 + i]);  // broadcast read
+                Elem x[BK];
+                stage_read<Elem>(stage + i * G::ROW_BYTES, lane, x);
+#pragma unroll
+                for (int k = 0; k < BK; k++)
+                    if ((mj.w[k] >> lane) & 1u) acc[k] += x[k];
+            }
+        }
+        if (G::CPL > 1) __syncwarp();  // the slots may be refilled by other lanes from here on
+    }
+    __syncwarp();  // every lane is done with the table before the next look-up rewrites it
+#else
     while (nz) {
         uint32_t todo = nz;
         int cnt = 0;
@@ -431,7 +492,7 @@ __device__ __forceinline__ void bc_gather(const Elem *rows, uint32_t v_lane, con
                 uint32_t need[G::SPL];
 #pragma unroll
                 for (int h = 0; h < G::SPL; h++) need[h] = __shfl_sync(FULL, need_lane[h], a);
-                cp_async_row<Elem>(sbase + i * G::ROW_BYTES, lane, rows + (size_t)vj * BG, need);
+                cp_async_row<Elem>(sbase + i * G::ROW_BYTES, lane, lane_rows, vj, need);
                 cnt = i + 1;
             }
         }
@@ -452,6 +513,7 @@ __device__ __forceinline__ void bc_gather(const Elem *rows, uint32_t v_lane, con
         }
         if (G::CPL > 1) __syncwarp();  // the slots may be refilled by other lanes from here on
     }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -803,6 +865,8 @@ __device__ __forceinline__ void bc_bwd_scan(const BcParams &p, const double *row
         } else {
             using G = RowGeom<double>;
             const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage);
+            const char *lane_rows = reinterpret_cast<const char *>(rows) + 16 * lane;
+            asm("" : "+l"(lane_rows));
             uint32_t need_lane[G::SPL];
             row_need<G::SPL>(m, need_lane);
             while (nz) {
@@ -819,7 +883,7 @@ __device__ __forceinline__ void bc_bwd_scan(const BcParams &p, const double *row
                         uint32_t need[G::SPL];
 #pragma unroll
                         for (int h = 0; h < G::SPL; h++) need[h] = __shfl_sync(FULL, need_lane[h], a);
-                        cp_async_row<double>(sbase + i * G::ROW_BYTES, lane, rows + (size_t)wj * BG, need);
+                        cp_async_row<double>(sbase + i * G::ROW_BYTES, lane, lane_rows, wj, need);
                         cnt = i + 1;
                     }
                 }

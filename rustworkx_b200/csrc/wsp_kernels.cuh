@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) wsp_relax_kernel(WspPara
     char *stage = s_dyn_stage + (size_t)(threadIdx.x >> 5) * (BC_SMEM_BYTES / WARPS);
     using G = RowGeom<double>;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage);
+    const char *lane_rows = reinterpret_cast<const char *>(p.dist + (size_t)blockIdx.y * p.n * BG) + 16 * lane_id();
     const int tid = threadIdx.x, lane = lane_id();
     if (tid == 0) {
         s_ncand = 0;
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) wsp_relax_kernel(WspPara
                         uint32_t need[G::SPL];
 #pragma unroll
                         for (int h = 0; h < G::SPL; h++) need[h] = __shfl_sync(FULL, need_lane[h], a);
-                        cp_async_row<double>(sbase + j * G::ROW_BYTES, lane, rows + (size_t)vj * BG, need);
+                        cp_async_row<double>(sbase + j * G::ROW_BYTES, lane, lane_rows, vj, need);
                         cnt = j + 1;
                     }
                 }
