@@ -6,7 +6,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import rustworkx_b200 as rx
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
-g = rx.barabasi_albert_graph(1_000_000, 8, seed=1)
+g = (rx.directed_gnm_random_graph(2**20, 2**24, seed=7) if os.environ.get("GRAPH") == "gnm"
+     else rx.barabasi_albert_graph(1_000_000, 8, seed=1))
 dg = rx.device_snapshot(g)
 plan = np.random.default_rng(12345).permutation(g.num_nodes()).astype(np.uint32)
 mode = sys.argv[2] if len(sys.argv) > 2 else "node"
