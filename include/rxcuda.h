@@ -222,6 +222,10 @@ int rxc_get_stats(const rxc_graph *g, rxc_stats *out);
  *                      order; 1: sorted by two-hop neighbourhood size (similar level structure);
  *                      2 (default): sources that hang off the same hub (at least 2 lanes' worth of
  *                      them in the call) form clusters that come first, the rest in order 1
+ *   bc_siblings N      bc_order 2: a hub named by at least N sources of the call forms a cluster (2)
+ *   bc_bwd_ctas N      dependency sweep: CTAs of one launch, all groups together (32768; 0: a warp per
+ *                      1..8 queue entries)
+ *   snapshot_cache_entries N  handles rxc_graph_snapshot_cached keeps alive (2)
  *   bfs_threads N      regime 2: threads per CTA (0: 1024 for n >= 2^18, else 256)
  *   bfs_groups N       regime 1: groups of 32 sources per batch (0: up to 4096)
  *   device_csr 0|1     build the CSR on the device (1) or with the host counting sort (0)

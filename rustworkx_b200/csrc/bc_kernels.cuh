@@ -1021,9 +1021,9 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) bc_backward_kernel(BcPar
     }
     dag = warp_sum_u64(dag);
     if (lane == 0 && (te | vv | dag)) {
-        atomicAdd(&p.stats[ST_TE], te);
-        atomicAdd(&p.stats[ST_V], vv);
-        atomicAdd(&p.stats[ST_DAG], dag);
+        stat_add(p.stats, ST_TE, te);
+        stat_add(p.stats, ST_V, vv);
+        stat_add(p.stats, ST_DAG, dag);
     }
 }
 
@@ -1072,7 +1072,7 @@ __global__ void __launch_bounds__(BLOCK) bc_backward_hub_kernel(BcParams p, uint
                 d += s_dag[q];
             }
             bc_bwd_finish<EDGE, ENDPOINTS>(p, v, fm, sg.x, tot, rows, Pcur, tag_cur, level, lane);
-            if (lane == 0 && d) atomicAdd(&p.stats[ST_DAG], d);
+            if (lane == 0 && d) stat_add(p.stats, ST_DAG, d);
         }
         __syncthreads();
     }
@@ -1243,8 +1243,8 @@ __global__ void __launch_bounds__(BLOCK) bc_group_finalize_kernel(BcParams p, ui
     if (lane == 0) {
         if (sum != 0.0) atomicAdd(&p.acc[0], sum);
         if (te | vv) {
-            atomicAdd(&p.stats[ST_TE], te);
-            atomicAdd(&p.stats[ST_V], vv);
+            stat_add(p.stats, ST_TE, te);
+            stat_add(p.stats, ST_V, vv);
         }
     }
 }
@@ -1382,7 +1382,7 @@ __global__ void __launch_bounds__(BLOCK, (BK == 4 ? 5 : 3)) bfs128_level_kernel(
             atomicAdd(&p.lvl_total[level + 1], nout);
         }
         s_base = base + pos;
-        if (s_te) atomicAdd(&p.stats[ST_TE], s_te);
+        if (s_te) stat_add(p.stats, ST_TE, s_te);
     }
     __syncthreads();
     if ((uint32_t)tid < nout) {
@@ -1393,7 +1393,7 @@ __global__ void __launch_bounds__(BLOCK, (BK == 4 ? 5 : 3)) bfs128_level_kernel(
     if (tid < BG && s_cnt[tid]) {
         atomicAdd(&p.reach[(size_t)g * BG + tid], (unsigned long long)s_cnt[tid]);
         atomicAdd(&p.dsum[(size_t)g * BG + tid], (unsigned long long)s_cnt[tid] * (level + 1));
-        atomicAdd(&p.stats[ST_V], (unsigned long long)s_cnt[tid]);
+        stat_add(p.stats, ST_V, (unsigned long long)s_cnt[tid]);
     }
 }
 
@@ -1406,8 +1406,8 @@ __global__ void __launch_bounds__(BLOCK) bfs128_sources_kernel(BcParams p, uint3
     p.reach[i] = s != NO_SOURCE ? 1ull : 0ull;
     if (s == NO_SOURCE) return;
     if (rows) p.drows[(size_t)i * p.n_cols + s] = 0.0;
-    atomicAdd(&p.stats[ST_TE], (unsigned long long)(p.srow[s + 1] - p.srow[s]));
-    atomicAdd(&p.stats[ST_V], 1ull);
+    stat_add(p.stats, ST_TE, (unsigned long long)(p.srow[s + 1] - p.srow[s]));
+    stat_add(p.stats, ST_V, 1ull);
 }
 
 }  // namespace rxc

@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(BLOCK) bfs_level_kernel(BfsParams p, uint32_t 
     }
     if (threadIdx.x == 0) {
         if (s_enq) atomicAdd(&p.lvl_total[level + 1], s_enq);
-        if (s_te) atomicAdd(&p.stats[ST_TE], s_te);
-        if (s_v) atomicAdd(&p.stats[ST_V], s_v);
+        if (s_te) stat_add(p.stats, ST_TE, s_te);
+        if (s_v) stat_add(p.stats, ST_V, s_v);
     }
 }
 
@@ -359,8 +359,8 @@ __global__ void __launch_bounds__(1024, 1) bfs_smem_kernel(SmemBfsParams p) {
             p.reach[si] = reach;
             p.dsum[si] = dsum;
             if (p.depth) p.depth[si] = level;
-            atomicAdd(&p.stats[ST_TE], s_te);
-            atomicAdd(&p.stats[ST_V], reach);
+            stat_add(p.stats, ST_TE, s_te);
+            stat_add(p.stats, ST_V, reach);
         }
     }
 }

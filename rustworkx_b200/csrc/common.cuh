@@ -16,6 +16,11 @@ constexpr uint32_t NO_SOURCE = 0xFFFFFFFFu;
 
 // Device-side work counters (one array per graph handle).
 enum StatSlot { ST_TE = 0, ST_DAG = 1, ST_V = 2, ST_COUNT = 4 };
+// The counters are striped: a launch of the dependency sweep has up to 2 million warps, and three
+// atomics per warp on the SAME three addresses serialise in one L2 slice (and slow every other
+// access that hashes to it).  A warp adds to the stripe its CTA index picks -- one 32-byte sector per
+// stripe -- and the host sums the stripes (fetch_stats).
+constexpr int ST_STRIPES = 256;
 
 void set_error(const std::string &msg);
 
@@ -37,6 +42,11 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
+}
+
+__device__ __forceinline__ void stat_add(unsigned long long *stats, int slot, unsigned long long v) {
+    const unsigned stripe = (blockIdx.x + blockIdx.y * 37u + (threadIdx.x >> 5) * 11u) & (ST_STRIPES - 1);
+    atomicAdd(&stats[stripe * ST_COUNT + slot], v);
 }
 
 __device__ __forceinline__ double warp_sum(double x) {

@@ -132,6 +132,9 @@ struct Options {
     int64_t bc_sigma = 0;           // betweenness sigma rows: 0 auto (uint32, f64 on overflow), 1 f64, 2 uint32
     int64_t bfs_threads = 0;        // CTA-per-source BFS: threads per CTA (0: 1024 for n >= 2^18, else 256)
     int64_t bfs_ell = 1;            // CTA-per-source BFS: ELL adjacency when every vertex has <= 4 arcs
+    int64_t bc_bwd_ctas = 32768;    // dependency sweep: CTAs of one launch, all groups together (0: one warp per 1..8 entries).
+                                    // Measured on BA(10^6,8), 16384 sources: 8192 -> 920 ms, 32768 -> 900, 131072 -> 907, 0 -> 915;
+                                    // BA(125k,8), 8192 sources: 53.0 / 49.9 / 50.2 / 57.3 ms
     int64_t bc_siblings = 2;        // bc_order 2: a hub named by at least this many sources of the call forms a cluster
     int64_t bc_order = 2;           // betweenness source grouping: 0 off, 1 two-hop key, 2 key + hub siblings for >= 4096 sources
 };
@@ -607,12 +610,15 @@ static void end_call(rxc_graph *g) {
 }
 
 static void fetch_stats(rxc_graph *g) {
-    unsigned long long h[ST_COUNT];
+    unsigned long long h[ST_STRIPES * ST_COUNT];
     RXC_CUDA(cudaMemcpyAsync(h, g->d_stats.p, sizeof(h), cudaMemcpyDeviceToHost, g->stream));
     RXC_CUDA(cudaStreamSynchronize(g->stream));
-    g->stats.te = h[ST_TE];
-    g->stats.te_dag = h[ST_DAG];
-    g->stats.v = h[ST_V];
+    unsigned long long sum[ST_COUNT] = {0, 0, 0, 0};
+    for (int s = 0; s < ST_STRIPES; s++)
+        for (int c = 0; c < ST_COUNT; c++) sum[c] += h[s * ST_COUNT + c];
+    g->stats.te = sum[ST_TE];
+    g->stats.te_dag = sum[ST_DAG];
+    g->stats.v = sum[ST_V];
 }
 
 // Split a source list into rounds of pairwise-distinct compact ids (a vertex listed twice must
@@ -1002,7 +1008,9 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources_in, bool e
             for (uint32_t gi = 0; gi < bg; gi++)
                 maxcnt = std::max(maxcnt, h_lvlcnt[(size_t)gi * L + l]);
             if (maxcnt == 0) continue;
-            const uint32_t gx = std::min<uint32_t>((maxcnt + WARPS - 1) / WARPS, 16384);
+            uint32_t gx = std::min<uint32_t>((maxcnt + WARPS - 1) / WARPS, 16384);
+            if (g->opt.bc_bwd_ctas > 0)  // cap on the CTAs of one launch, all groups together
+                gx = std::min<uint32_t>(gx, (uint32_t)std::max<int64_t>(1, g->opt.bc_bwd_ctas / bg));
             const dim3 grid(gx, bg), hgrid(HUB_CTAS, bg);
 #define RXC_BWD(E, P, N)                                                                \
     do {                                                                                \
@@ -2105,7 +2113,7 @@ static rxc_graph *snapshot_on(int device, uint32_t n_bound, const uint32_t *live
         if (g->host.directed) g->in.upload(g->host.in, g->stream);
         g->n_arcs = g->host.out.col.size();
     }
-    g->d_stats.alloc(ST_COUNT);
+    g->d_stats.alloc(ST_STRIPES * ST_COUNT);
     RXC_CUDA(cudaMemsetAsync(g->d_stats.p, 0, g->d_stats.bytes(), g->stream));
     RXC_CUDA(cudaStreamSynchronize(g->stream));
     memset(&g->stats, 0, sizeof(g->stats));
@@ -2627,6 +2635,7 @@ int rxc_set_option(const char *name, int64_t value) {
     else if (k == "bfs_mode" && value >= 0 && value <= 3) g_opt.bfs_mode = value;
     else if (k == "bc_order" && value >= 0 && value <= 2) g_opt.bc_order = value;
     else if (k == "bc_siblings" && value >= 1) g_opt.bc_siblings = value;
+    else if (k == "bc_bwd_ctas" && value >= 0) g_opt.bc_bwd_ctas = value;
     else if (k == "bfs_depth_switch" && value >= 0) g_opt.bfs_depth_switch = value;
     else if (k == "bfs_threads" && (value == 0 || value == 128 || value == 256 || value == 512 || value == 1024)) g_opt.bfs_threads = value;
     else if (k == "bc_sigma" && value >= 0 && value <= 2) g_opt.bc_sigma = value;

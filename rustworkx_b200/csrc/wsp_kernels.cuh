@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) wsp_relax_kernel(WspPara
     if ((uint32_t)tid < nout)
         p.qv[(size_t)g * p.qstride + (size_t)((round + 1) & 1) * p.n + s_base + tid] = s_ov[tid];
     relaxed = warp_sum_u64(relaxed);
-    if (lane == 0 && relaxed) atomicAdd(&p.stats[ST_DAG], relaxed);
+    if (lane == 0 && relaxed) stat_add(p.stats, ST_DAG, relaxed);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -305,8 +305,8 @@ __global__ void __launch_bounds__(BG) wsp_sums_tile_kernel(WspParams p, double *
     te = warp_sum_u64(te);
     cnt = warp_sum_u64(cnt);
     if ((slot & 31) == 0 && (te | cnt)) {
-        atomicAdd(&p.stats[ST_TE], te);
-        atomicAdd(&p.stats[ST_V], cnt);
+        stat_add(p.stats, ST_TE, te);
+        stat_add(p.stats, ST_V, cnt);
     }
 }
 
