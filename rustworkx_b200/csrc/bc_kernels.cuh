@@ -444,6 +444,31 @@ __device__ __forceinline__ void bc_gather(const Elem *rows, uint32_t v_lane, con
     SrcMask *t_m = reinterpret_cast<SrcMask *>(tab + 32 * 8 + (BK == 8 ? 32 * 4 : 0));
     if (nz == 0) return;  // warp-uniform
     const int total = __popc(nz);
+#if RXC_PROBE
+    {
+        // 32-byte sectors and 128-byte lines this look-up's row gathers touch
+        const uint32_t nd = ((nz >> lane) & 1u) ? need_lane[0] : 0u;
+        uint32_t sectors, lines;
+        if (sizeof(Elem) == 8) {  // lane = one sector, 4 lanes = one line
+            sectors = __popc(nd);
+            lines = __popc((nd | nd >> 1 | nd >> 2 | nd >> 3) & 0x11111111u);
+        } else {  // lane = half a sector, 8 lanes = one line
+            sectors = __popc((nd | nd >> 1) & 0x55555555u);
+            uint32_t f = nd | nd >> 1;
+            f |= f >> 2;
+            f |= f >> 4;
+            lines = __popc(f & 0x01010101u);
+        }
+        sectors = __reduce_add_sync(FULL, sectors);
+        lines = __reduce_add_sync(FULL, lines);
+        if (lane == 0) {
+            const int o = sizeof(Elem) == 8 ? 4 : 0;
+            atomicAdd(&g_probe[PR_ROWS32 + o], (unsigned long long)total);
+            atomicAdd(&g_probe[PR_SECTORS32 + o], (unsigned long long)sectors);
+            atomicAdd(&g_probe[PR_LINES32 + o], (unsigned long long)lines);
+        }
+    }
+#endif
     if ((nz >> lane) & 1u) {
         const int pos = __popc(nz & lanemask_lt());
         t_vn[pos] = make_uint2(v_lane, need_lane[0]);
@@ -453,14 +478,31 @@ __device__ __forceinline__ void bc_gather(const Elem *rows, uint32_t v_lane, con
     __syncwarp();
     for (int j0 = 0; j0 < total; j0 += NS) {
         const int cnt = min(NS, total - j0);
+        // Straight-line blocks of 2 or 3 slots: the table reads of a block, then its predicated copies;
+        // a slot past the end of the list re-reads the last table entry with every lane switched
+        // off.  (ptxas puts three padding LDS in front of every LDGSTS that follows an LDS or opens a
+        // basic block; with a branch and a table read per slot that was 6 of the ~45 issue slots a
+        // gathered row costs.)
+        constexpr int NB = NS % 3 == 0 ? 3 : 2;  // slots per block
+        static_assert(NS % NB == 0, "row slots come in blocks of 2 or 3");
 #pragma unroll
-        for (int i = 0; i < NS; i++) {
-            if (i < cnt) {  // warp-uniform
-                const uint2 e = t_vn[j0 + i];  // broadcast read
-                uint32_t need[G::SPL];
-                need[0] = e.y;
-                if (G::SPL == 2) need[G::SPL - 1] = t_need1[j0 + i];
-                cp_async_row<Elem>(sbase + i * G::ROW_BYTES, lane, lane_rows, e.x, need);
+        for (int b = 0; b < NS; b += NB) {
+            if (b < cnt) {  // warp-uniform
+                uint2 e[NB];
+                uint32_t need1[NB];
+#pragma unroll
+                for (int i = 0; i < NB; i++) {
+                    const int j = min(j0 + b + i, total - 1);
+                    e[i] = t_vn[j];  // broadcast reads, all of them before the first copy (see above)
+                    if (G::SPL == 2) need1[i] = t_need1[j];
+                }
+#pragma unroll
+                for (int i = 0; i < NB; i++) {
+                    uint32_t need[G::SPL];
+                    need[0] = b + i < cnt ? e[i].y : 0u;
+                    if (G::SPL == 2) need[G::SPL - 1] = b + i < cnt ? need1[i] : 0u;
+                    cp_async_row<Elem>(sbase + (b + i) * G::ROW_BYTES, lane, lane_rows, e[i].x, need);
+                }
             }
         }
         cp_async_wait_all();
@@ -628,6 +670,9 @@ __device__ __forceinline__ void bc_fwd_scan(const BcParams &p, const Elem *rows,
             for (int k = 0; k < BK; k++) m.w[k] &= unv.w[k];
         }
         const uint32_t nz = __ballot_sync(FULL, mask_any(m));
+#if RXC_PROBE
+        if (lane == 0) atomicAdd(&g_probe[sizeof(Elem) == 8 ? PR_LOOKUPS64 : PR_LOOKUPS32], (unsigned long long)min(32u, e1 - e));
+#endif
         if (nz) {
 #pragma unroll
             for (int k = 0; k < BK; k++) newm.w[k] |= __reduce_or_sync(FULL, m.w[k]);
@@ -859,6 +904,9 @@ __device__ __forceinline__ void bc_bwd_scan(const BcParams &p, const double *row
             if (EDGE && mask_any(m)) ed = p.eid[idx];
         }
         uint32_t nz = __ballot_sync(FULL, mask_any(m));
+#if RXC_PROBE
+        if (lane == 0) atomicAdd(&g_probe[PR_LOOKUPS64], (unsigned long long)min(32u, e1 - e));
+#endif
         dag += mask_popc(m);  // per lane: the sources of this lane's own arc (summed over the warp at the end)
         if (!EDGE) {
             bc_gather<BSTAGE>(rows, w, m, nz, lane, stage, acc);
@@ -874,17 +922,29 @@ __device__ __forceinline__ void bc_bwd_scan(const BcParams &p, const double *row
                 // group, ER arcs per pass of the exchange network
                 uint32_t todo = nz;
                 int cnt = 0;
+                // blocks of 2 or 3 slots: the shuffles of a block, then its predicated copies in one
+                // straight line (see bc_gather); a slot past the last arc copies nothing
+                constexpr int NB = ESTAGE % 3 == 0 ? 3 : (ESTAGE % 2 == 0 ? 2 : 1);
 #pragma unroll
-                for (int i = 0; i < ESTAGE; i++) {
+                for (int b = 0; b < ESTAGE; b += NB) {
                     if (nz) {  // warp-uniform
-                        const int a = __ffs(nz) - 1;
-                        nz &= nz - 1;
-                        const uint32_t wj = __shfl_sync(FULL, w, a);
-                        uint32_t need[G::SPL];
+                        uint32_t wj[NB], need[NB][G::SPL];
 #pragma unroll
-                        for (int h = 0; h < G::SPL; h++) need[h] = __shfl_sync(FULL, need_lane[h], a);
-                        cp_async_row<double>(sbase + i * G::ROW_BYTES, lane, lane_rows, wj, need);
-                        cnt = i + 1;
+                        for (int i = 0; i < NB; i++) {
+                            const bool live = nz != 0;
+                            const int a = (__ffs(nz) - 1) & 31;
+                            nz &= nz - 1;
+                            wj[i] = __shfl_sync(FULL, w, a);
+#pragma unroll
+                            for (int h = 0; h < G::SPL; h++) {
+                                const uint32_t nd = __shfl_sync(FULL, need_lane[h], a);
+                                need[i][h] = live ? nd : 0u;
+                            }
+                            cnt += live;
+                        }
+#pragma unroll
+                        for (int i = 0; i < NB; i++)
+                            cp_async_row<double>(sbase + (b + i) * G::ROW_BYTES, lane, lane_rows, wj[i], need[i]);
                     }
                 }
                 cp_async_wait_all();

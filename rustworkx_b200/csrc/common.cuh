@@ -22,6 +22,17 @@ enum StatSlot { ST_TE = 0, ST_DAG = 1, ST_V = 2, ST_COUNT = 4 };
 // stripe -- and the host sums the stripes (fetch_stats).
 constexpr int ST_STRIPES = 256;
 
+// RXC_PROBE builds (make variant VAR=probe DEFS=-DRXC_PROBE=1) count what the betweenness kernels ask of
+// the memory system -- level-mask look-ups, gathered rows, sectors and 128-byte lines of those rows --
+// and print the totals of every call to stderr; never timed, never shipped.
+#ifndef RXC_PROBE
+#define RXC_PROBE 0
+#endif
+#if RXC_PROBE
+enum ProbeSlot { PR_LOOKUPS32 = 0, PR_ROWS32, PR_SECTORS32, PR_LINES32, PR_LOOKUPS64, PR_ROWS64, PR_SECTORS64, PR_LINES64, PR_COUNT };
+__device__ unsigned long long g_probe[PR_COUNT];
+#endif
+
 void set_error(const std::string &msg);
 
 struct CudaError {

@@ -619,6 +619,15 @@ static void fetch_stats(rxc_graph *g) {
     g->stats.te = sum[ST_TE];
     g->stats.te_dag = sum[ST_DAG];
     g->stats.v = sum[ST_V];
+#if RXC_PROBE
+    unsigned long long pr[PR_COUNT], zero[PR_COUNT] = {};
+    RXC_CUDA(cudaMemcpyFromSymbol(pr, g_probe, sizeof(pr)));
+    RXC_CUDA(cudaMemcpyToSymbol(g_probe, zero, sizeof(zero)));
+    fprintf(stderr,
+            "[rxc probe] uint32 rows (forward): lookups %llu rows %llu sectors %llu lines128 %llu | f64 rows "
+            "(dependency sweep; forward when wide): lookups %llu rows %llu sectors %llu lines128 %llu\n",
+            pr[0], pr[1], pr[2], pr[3], pr[4], pr[5], pr[6], pr[7]);
+#endif
 }
 
 // Split a source list into rounds of pairwise-distinct compact ids (a vertex listed twice must
