@@ -293,17 +293,14 @@ __device__ __forceinline__ RowK row_load(const double *rows, uint32_t v, int lan
 #ifndef RXC_FWD32_SLOTS
 #define RXC_FWD32_SLOTS 6  // BK = 4: 6 slots + the arc table keep the narrow forward kernel at 5 CTAs per SM
 #endif
-// Arc table (RXC_ARCTAB, default on): the arcs a look-up found on the frontier are compacted into a
-// small per-warp table in shared memory -- (vertex, sector-need) and the source mask per arc -- and
-// the staging loops walk that dense list with broadcast LDS reads.  ncu on the shuffle form (arc a
-// of the look-up lives in lane a: find-first-set on the ballot, clear the bit, 2 shuffles to stage
-// the row, 4 more to fetch its mask when the row is consumed) counted 78 issued instructions per
-// gathered row with the issue slots 80 % busy in the big forward launches; the table removes the
-// bit scans and 6 of the 6.2 shuffles per row.
-#ifndef RXC_ARCTAB
-#define RXC_ARCTAB 1
-#endif
-constexpr int ARCTAB_BYTES = RXC_ARCTAB ? 32 * 8 + (BK == 8 ? 32 * 4 : 0) + 32 * 16 * MQ : 0;  // per warp
+// Arc table: the arcs a look-up found on the frontier are compacted into a small per-warp table in
+// shared memory -- (vertex, sector-need) and the source mask per arc -- and the staging loops walk
+// that dense list with broadcast LDS reads.  ncu on the first form (arc a of the look-up lives in lane
+// a: find-first-set on the ballot, clear the bit, 2 shuffles to stage the row, 4 more to fetch its
+// mask when the row is consumed) counted 78 issued instructions per gathered row with the issue slots
+// 80 % busy in the big forward launches; the table removes the bit scans and 6 of the 6.2 shuffles
+// per row.
+constexpr int ARCTAB_BYTES = 32 * 8 + (BK == 8 ? 32 * 4 : 0) + 32 * 16 * MQ;  // per warp
 constexpr int STAGE = RXC_STAGE;  // f64 row slots per warp in the forward / edge / weighted kernels
 constexpr int BC_SMEM_BYTES = WARPS * (STAGE * BG * 8 + ARCTAB_BYTES);  // BK = 4: 32 KB + tables per CTA
 constexpr int FWD32_SLOTS = RXC_FWD32_SLOTS;  // uint32 row slots per warp in the narrow forward kernels
@@ -350,6 +347,11 @@ struct RowGeom {
 __device__ __forceinline__ int stage_pos(int c) { return (c & ~7) | ((c + (c >> 3)) & 7); }
 
 // Which lanes' sectors an arc with source mask m needs: need[h] bit l <-> sector h of lane l.
+// RXC_NEEDLINES = 4 or 8 (experiment): round the need up to whole groups of that many
+// lanes -- 4 lanes of an f64 row / 8 lanes of a uint32 row are one 128-byte line.
+#ifndef RXC_NEEDLINES
+#define RXC_NEEDLINES 0
+#endif
 template <int SPL>
 __device__ __forceinline__ void row_need(const SrcMask &m, uint32_t (&need)[SPL]) {
 #pragma unroll
@@ -357,6 +359,17 @@ __device__ __forceinline__ void row_need(const SrcMask &m, uint32_t (&need)[SPL]
         need[h] = 0;
 #pragma unroll
         for (int k = h * (BK / SPL); k < (h + 1) * (BK / SPL); k++) need[h] |= m.w[k];
+#if RXC_NEEDLINES == 4
+        uint32_t t = need[h] | need[h] >> 1 | need[h] >> 2 | need[h] >> 3;
+        need[h] = (t & 0x11111111u) * 15u;
+#elif RXC_NEEDLINES == 8
+        uint32_t t = need[h] | need[h] >> 1;
+        t |= t >> 2;
+        t |= t >> 4;
+        need[h] = (t & 0x01010101u) * 255u;
+#elif RXC_NEEDLINES == 32
+        need[h] = need[h] ? 0xFFFFFFFFu : 0u;
+#endif
     }
 }
 
@@ -427,21 +440,36 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // Batches of NS rows.  (A ring that tops itself up row by row, so that NS rows stay in flight for
 // the whole arc list, was measured: 80 -> 86 ms per 1024 sources -- its bookkeeping costs more issue
 // slots than the shorter waits give back.)
-template <int NS, class Elem, class Acc>
+// What a gathered value does to the running value of its source: betweenness sums (sigma, then
+// (1+delta)/sigma); the weighted shortest paths take min(dist + cost of the arc) -- the arc's cost is a
+// per-arc scalar that travels through the arc table.
+struct GatherSum {
+    static constexpr bool HAS_AUX = false;
+    template <class Acc, class Elem>
+    static __device__ __forceinline__ void apply(Acc &acc, Elem x, double) { acc += x; }
+};
+struct GatherMinPlus {
+    static constexpr bool HAS_AUX = true;
+    static __device__ __forceinline__ void apply(double &acc, double x, double c) { acc = fmin(acc, x + c); }
+};
+constexpr int ARCTAB_AUX_BYTES = 32 * 8;  // per warp, behind the arc table (GatherMinPlus only)
+
+template <int NS, class Elem, class Acc, class Op = GatherSum>
 __device__ __forceinline__ void bc_gather(const Elem *rows, uint32_t v_lane, const SrcMask &m_lane,
-                                          uint32_t nz, int lane, char *stage, Acc (&acc)[BK]) {
+                                          uint32_t nz, int lane, char *stage, Acc (&acc)[BK],
+                                          double aux_lane = 0.0) {
     using G = RowGeom<Elem>;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage);
     const char *lane_rows = reinterpret_cast<const char *>(rows) + 16 * lane;
     asm("" : "+l"(lane_rows));  // keep it one 64-bit value (else the compiler re-adds a uniform part per row)
     uint32_t need_lane[G::SPL];
     row_need<G::SPL>(m_lane, need_lane);
-#if RXC_ARCTAB
     // the table sits behind this warp's NS row slots: vn[32] = (vertex, need[0]), [need1[32]], m[32]
     char *tab = stage + NS * G::ROW_BYTES;
     uint2 *t_vn = reinterpret_cast<uint2 *>(tab);
     uint32_t *t_need1 = reinterpret_cast<uint32_t *>(tab + 32 * 8);
     SrcMask *t_m = reinterpret_cast<SrcMask *>(tab + 32 * 8 + (BK == 8 ? 32 * 4 : 0));
+    double *t_aux = reinterpret_cast<double *>(tab + ARCTAB_BYTES);
     if (nz == 0) return;  // warp-uniform
     const int total = __popc(nz);
 #if RXC_PROBE
@@ -474,6 +502,7 @@ __device__ __forceinline__ void bc_gather(const Elem *rows, uint32_t v_lane, con
         t_vn[pos] = make_uint2(v_lane, need_lane[0]);
         if (G::SPL == 2) t_need1[pos] = need_lane[G::SPL - 1];
         mask_store(&t_m[pos], m_lane);
+        if (Op::HAS_AUX) t_aux[pos] = aux_lane;
     }
     __syncwarp();
     for (int j0 = 0; j0 < total; j0 += NS) {
@@ -511,51 +540,17 @@ __device__ __forceinline__ void bc_gather(const Elem *rows, uint32_t v_lane, con
         for (int i = 0; i < NS; i++) {
             if (i < cnt) {
                 const SrcMask mj = mask_load(&t_m[j0 + i]);  // broadcast read
+                const double aux = Op::HAS_AUX ? t_aux[j0 + i] : 0.0;
                 Elem x[BK];
                 stage_read<Elem>(stage + i * G::ROW_BYTES, lane, x);
 #pragma unroll
                 for (int k = 0; k < BK; k++)
-                    if ((mj.w[k] >> lane) & 1u) acc[k] += x[k];
+                    if ((mj.w[k] >> lane) & 1u) Op::apply(acc[k], x[k], aux);
             }
         }
         if (G::CPL > 1) __syncwarp();  // the slots may be refilled by other lanes from here on
     }
     __syncwarp();  // every lane is done with the table before the next look-up rewrites it
-#else
-    while (nz) {
-        uint32_t todo = nz;
-        int cnt = 0;
-#pragma unroll
-        for (int i = 0; i < NS; i++) {
-            if (nz) {  // warp-uniform
-                const int a = __ffs(nz) - 1;
-                nz &= nz - 1;
-                const uint32_t vj = __shfl_sync(FULL, v_lane, a);
-                uint32_t need[G::SPL];
-#pragma unroll
-                for (int h = 0; h < G::SPL; h++) need[h] = __shfl_sync(FULL, need_lane[h], a);
-                cp_async_row<Elem>(sbase + i * G::ROW_BYTES, lane, lane_rows, vj, need);
-                cnt = i + 1;
-            }
-        }
-        cp_async_wait_all();
-        if (G::CPL > 1) __syncwarp();  // the chunks a lane reads were copied by other lanes
-#pragma unroll
-        for (int i = 0; i < NS; i++) {
-            if (i < cnt) {
-                const int a = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const SrcMask mj = mask_shfl(m_lane, a);
-                Elem x[BK];
-                stage_read<Elem>(stage + i * G::ROW_BYTES, lane, x);
-#pragma unroll
-                for (int k = 0; k < BK; k++)
-                    if ((mj.w[k] >> lane) & 1u) acc[k] += x[k];
-            }
-        }
-        if (G::CPL > 1) __syncwarp();  // the slots may be refilled by other lanes from here on
-    }
-#endif
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1801,7 +1801,7 @@ static void wsp_run(rxc_graph *g, bool reversed, const double *d_cost, const std
     if (sources.empty() || n == 0) return;
     static bool attr_done[64] = {false};
     if (!attr_done[g->device & 63]) {
-        RXC_CUDA(cudaFuncSetAttribute(wsp_relax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM_BYTES));
+        RXC_CUDA(cudaFuncSetAttribute(wsp_relax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WSP_SMEM_BYTES));
         attr_done[g->device & 63] = true;
     }
     const uint64_t total_groups = (sources.size() + BG - 1) / BG;
@@ -1875,7 +1875,7 @@ static void wsp_run(rxc_graph *g, bool reversed, const double *d_cost, const std
             g, ws.lvl_total.p, n + 1,
             [&](uint32_t round) {
                 wsp_mark_kernel<<<dim3(MARK_CTAS * 4, bg), BLOCK, 0, st>>>(p, round);
-                wsp_relax_kernel<<<dim3(vblocks, bg), BLOCK, BC_SMEM_BYTES, st>>>(p, round);
+                wsp_relax_kernel<<<dim3(vblocks, bg), BLOCK, WSP_SMEM_BYTES, st>>>(p, round);
                 launched++;
             },
             h_totals);

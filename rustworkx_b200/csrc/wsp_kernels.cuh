@@ -51,6 +51,9 @@ struct WspParams {
     uint32_t tagbase;
 };
 
+// row slots + arc table + the per-arc costs, per warp
+constexpr int WSP_SMEM_BYTES = BC_SMEM_BYTES + WARPS * ARCTAB_AUX_BYTES;
+
 __device__ __forceinline__ PEntry *wsp_C(const WspParams &p, uint32_t round) {
     return (round & 1) ? p.C1 : p.C0;
 }
@@ -118,10 +121,7 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) wsp_relax_kernel(WspPara
     __shared__ uint32_t s_w[BLOCK], s_e0[BLOCK], s_e1[BLOCK], s_ov[BLOCK];
     __shared__ uint32_t s_ncand, s_next, s_nout, s_base;
     extern __shared__ __align__(16) char s_dyn_stage[];
-    char *stage = s_dyn_stage + (size_t)(threadIdx.x >> 5) * (BC_SMEM_BYTES / WARPS);
-    using G = RowGeom<double>;
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage);
-    const char *lane_rows = reinterpret_cast<const char *>(p.dist + (size_t)blockIdx.y * p.n * BG) + 16 * lane_id();
+    char *stage = s_dyn_stage + (size_t)(threadIdx.x >> 5) * (WSP_SMEM_BYTES / WARPS);
     const int tid = threadIdx.x, lane = lane_id();
     if (tid == 0) {
         s_ncand = 0;
@@ -185,48 +185,14 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) wsp_relax_kernel(WspPara
                 c = p.cost[idx];
                 m = bc_level_mask(Ccur, v, tag_cur);
             }
-            uint32_t nz = __ballot_sync(FULL, mask_any(m));
+            const uint32_t nz = __ballot_sync(FULL, mask_any(m));
             if (nz) {  // once per look-up instead of once per row
 #pragma unroll
                 for (int k = 0; k < BK; k++) touched.w[k] |= __reduce_or_sync(FULL, m.w[k]);
                 relaxed += mask_popc(m);  // per lane; summed over the warp at the end
-            }
-            uint32_t need_lane[G::SPL];
-            row_need<G::SPL>(m, need_lane);
-            while (nz) {
-                uint32_t todo = nz;
-                int cnt = 0;
-#pragma unroll
-                for (int j = 0; j < STAGE; j++) {
-                    if (nz) {  // warp-uniform
-                        const int a = __ffs(nz) - 1;
-                        nz &= nz - 1;
-                        const uint32_t vj = __shfl_sync(FULL, v, a);
-                        uint32_t need[G::SPL];
-#pragma unroll
-                        for (int h = 0; h < G::SPL; h++) need[h] = __shfl_sync(FULL, need_lane[h], a);
-                        cp_async_row<double>(sbase + j * G::ROW_BYTES, lane, lane_rows, vj, need);
-                        cnt = j + 1;
-                    }
-                }
-                cp_async_wait_all();
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < STAGE; j++) {
-                    if (j < cnt) {
-                        const int a = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        const SrcMask mj = mask_shfl(m, a);
-                        const double cj = __shfl_sync(FULL, c, a);
-                        double xs[BK];
-                        stage_read<double>(stage + j * G::ROW_BYTES, lane, xs);
-                        // next_score = node_score + cost, dijkstra.rs:128
-#pragma unroll
-                        for (int k = 0; k < BK; k++)
-                            if ((mj.w[k] >> lane) & 1u) best[k] = fmin(best[k], xs[k] + cj);
-                    }
-                }
-                __syncwarp();
+                // next_score = node_score + cost, dijkstra.rs:128 -- through the arc table of the
+                // betweenness gathers, the arc's cost riding along as the per-arc scalar
+                bc_gather<STAGE, double, double, GatherMinPlus>(rows, v, m, nz, lane, stage, best, c);
             }
         }
         if (!mask_any(touched)) continue;
