@@ -137,6 +137,33 @@ def ncu_traffic():
     return {}, "no ncu capture committed"
 
 
+def probe_lines():
+    """128-byte line requests per SOURCE and kernel, counted by the RXC_PROBE build on this workload
+    (profiles/r02_probe_lines.json, scripts/probe_lines.py), and what the memory system delivers for
+    such requests (profiles/r02_sector_gather.txt, scripts/micro/sector_gather.cu: random 1 KB rows out of
+    24 GB, any 1-4 sectors of a 128-byte line cost the same line request)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_probe_lines.json")) as f:
+            rec = json.load(f)
+    except Exception:
+        return None
+    ceiling = None
+    try:
+        rates = []
+        with open(os.path.join(ROOT, "profiles", "r02_sector_gather.txt")) as f:
+            for ln in f:
+                if ln.startswith("24 GB") and "Gblocks/s" in ln:
+                    toks = ln.split()
+                    blocks = float(toks[toks.index("Gblocks/s") - 1])
+                    sectors = int(ln.split("sectors/block")[1].split(":")[0])
+                    rates.append(blocks * (2 if sectors == 8 else 1))  # 8 sectors = both lines of a block
+        ceiling = max(rates) if rates else None
+    except Exception:
+        pass
+    return {"per_source": {k: rec[k] for k in ("bc_forward_kernel", "bc_backward_kernel") if k in rec},
+            "probe_sources": rec.get("sources"), "ceiling_glines_s": ceiling}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
 
@@ -505,6 +532,22 @@ def run_b200(args):
                            "GBs_dram": gbs(kv["dram"], kv["ms"]), "GBs_useful": gbs(kv["useful"], kv["ms"])}
                        for k, kv in kernels.items()},
     }
+    pl = probe_lines()
+    if pl:  # the memory system counts 128-byte lines, not bytes
+        lines = {}
+        for k, kv in kernels.items():
+            ps = pl["per_source"].get(k)
+            if ps and kv["ms"]:
+                per_s = agg["sources"] / (kv["ms"] * 1e-3) / 1e9
+                lines[k] = {"row_lines_G_per_s": ps["lines128"] * per_s, "lookups_G_per_s": ps["lookups"] * per_s,
+                            "sectors_per_row_line": ps["sectors32"] / ps["lines128"]}
+        roofline["line_requests"] = {
+            "per_kernel": lines, "ceiling_G_per_s": pl["ceiling_glines_s"],
+            "source": f"profiles/r02_probe_lines.json (RXC_PROBE build, {pl['probe_sources']} sources of this workload) "
+                      "over this run's CUDA-event times; ceiling = profiles/r02_sector_gather.txt (random-row gather "
+                      "microbenchmark, 24 GB)",
+            "note": "128-byte lines requested by the row gathers and 32-byte level-mask look-ups (one line each) per "
+                    "second, averaged over all launches of the kernel; L2 hits are not subtracted"}
 
     cpu_baseline = None
     if not args.no_cpu_baseline:

@@ -59,9 +59,12 @@ def record(case, config, op, kind, dg, fn, cpu_fn, cpu_note, n, e2e_fn=None, sou
                         "note": "algorithmic bytes (SURVEY 8d) / device time of the whole call"}}
     if e2e_fn is not None:  # public API: snapshot from host arrays + call + result on the host
         e2e_fn()
-        t0 = time.perf_counter()
-        e2e_fn()
-        e2e = time.perf_counter() - t0
+        e2e = None
+        for _ in range(3):  # best of 3: a fresh handle takes its scratch from the pool, which varies
+            t0 = time.perf_counter()
+            e2e_fn()
+            dt = time.perf_counter() - t0
+            e2e = dt if e2e is None else min(e2e, dt)
         rec["e2e_ms"] = round(e2e * 1e3, 3)
         rec["gteps_e2e"] = round(te / e2e / 1e9, 2)
     t0 = time.perf_counter()
