@@ -60,7 +60,8 @@ typedef struct {
     double ms_snapshot;   /* host CSR build + H2D of the snapshot (wall clock)                   */
     double ms_d2h;        /* device-to-host result copies                                        */
     double ms_reduce;     /* rxc_*_partial_reduce: the in-place ncclReduce on the handle's stream
-                             (CUDA events; includes waiting for the slowest rank)                */
+                             (CUDA events), after a device-side rendezvous of the ranks          */
+    double ms_reduce_wait; /* that rendezvous: how long this rank waited for the slowest one     */
 } rxc_stats;
 
 /* ---- library / device ------------------------------------------------------------------------- */

@@ -43,6 +43,7 @@ class Stats(C.Structure):
         ("ms_snapshot", C.c_double),
         ("ms_d2h", C.c_double),
         ("ms_reduce", C.c_double),
+        ("ms_reduce_wait", C.c_double),
     ]
 
     def as_dict(self):

@@ -17,6 +17,7 @@
 namespace rxc {
 void set_error(const std::string &msg);
 int comm_reduce_device(double *d_inout, uint64_t len, int root, cudaStream_t st);
+int comm_rendezvous_device(cudaStream_t st);
 int comm_rank();
 int comm_world();
 }
@@ -99,6 +100,23 @@ int comm_reduce_device(double *d_inout, uint64_t len, int root, cudaStream_t st)
     if (!g_comm || g_world == 1 || len == 0) return RXC_OK;
     nccl_result_t r = g_nccl.Reduce(d_inout, d_inout, len, NCCL_FLOAT64, NCCL_SUM, root, g_comm, st);
     if (r != 0) return nccl_fail("ncclReduce", r);
+    return RXC_OK;
+}
+// Device-side rendezvous queued on the caller's stream (an all-reduce of one int): events around it
+// time how long this rank waited for the slowest one, apart from the transfer of the real reduce.
+int comm_rendezvous_device(cudaStream_t st) {
+    if (!g_comm || g_world == 1) return RXC_OK;
+    static int *d_flag[64] = {nullptr};  // one scratch word per device, kept for the process
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int *&d = d_flag[dev & 63];
+    if (!d) {
+        cudaError_t e = cudaMalloc((void **)&d, sizeof(int));
+        if (e != cudaSuccess) return cuda_fail("cudaMalloc", e);
+        cudaMemsetAsync(d, 0, sizeof(int), st);
+    }
+    nccl_result_t r = g_nccl.AllReduce(d, d, 1, NCCL_INT32, NCCL_SUM, g_comm, st);
+    if (r != 0) return nccl_fail("ncclAllReduce", r);
     return RXC_OK;
 }
 int comm_rank() { return g_rank; }
