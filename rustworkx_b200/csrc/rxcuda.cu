@@ -19,6 +19,7 @@
 #include <memory>
 #include <mutex>
 #include <thread>
+#include <type_traits>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -62,6 +63,84 @@ static void pool_setup(int device) {
     done[device] = true;
 }
 
+// The betweenness scratch is tens of GB.  Fresh memory from the stream-ordered pool costs ~50 ms per
+// GB the first time (measured: 1.7 s for the 30 GB of a 2048-source batch at n = 10^6, 0.4 s for four
+// bare cudaMallocAsync calls of that size), one cudaMalloc of the same size 10-35 ms
+// (scripts/micro/alloc_time.cu).  So the scratch is ONE cudaMalloc slab, carved into the arrays; a
+// released slab is parked per device (cudaFree synchronises the device and the next handle usually
+// wants the same size) and only freed when a larger one is needed or rxc_snapshot_cache_clear runs.
+struct Slab {
+    char *base = nullptr;
+    size_t bytes = 0;
+    int dev = -1;
+};
+static std::mutex g_slab_mu;
+static Slab g_slab_parked[64];
+
+static size_t slab_parked_bytes() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(g_slab_mu);
+    return g_slab_parked[dev & 63].bytes;
+}
+
+static Slab slab_acquire(size_t bytes) {
+    Slab out;
+    cudaGetDevice(&out.dev);
+    {
+        std::lock_guard<std::mutex> lock(g_slab_mu);
+        Slab &parked = g_slab_parked[out.dev & 63];
+        if (parked.base && parked.bytes >= bytes) {
+            out = parked;
+            parked = Slab{};
+            return out;
+        }
+        if (parked.base) {
+            cudaFree(parked.base);
+            parked = Slab{};
+        }
+    }
+    cudaError_t e = cudaMalloc((void **)&out.base, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        throw OomError("device allocation of " + std::to_string(bytes) + " bytes failed");
+    }
+    RXC_CUDA(e);
+    out.bytes = bytes;
+    return out;
+}
+
+// the caller has synchronised the stream that used the slab
+static void slab_release(Slab &sl) {
+    if (!sl.base) return;
+    std::lock_guard<std::mutex> lock(g_slab_mu);
+    Slab &parked = g_slab_parked[sl.dev & 63];
+    int cur = sl.dev;
+    cudaGetDevice(&cur);
+    if (cur != sl.dev) cudaSetDevice(sl.dev);
+    if (parked.base && parked.bytes >= sl.bytes) {
+        cudaFree(sl.base);  // keep the larger one
+    } else {
+        if (parked.base) cudaFree(parked.base);
+        parked = sl;
+    }
+    if (cur != sl.dev) cudaSetDevice(cur);
+    sl = Slab{};
+}
+
+static void slab_free_parked() {
+    std::lock_guard<std::mutex> lock(g_slab_mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (Slab &parked : g_slab_parked) {
+        if (!parked.base) continue;
+        cudaSetDevice(parked.dev);
+        cudaFree(parked.base);
+        parked = Slab{};
+    }
+    cudaSetDevice(cur);
+}
+
 template <class T>
 struct DevBuf {
     T *p = nullptr;
@@ -70,12 +149,25 @@ struct DevBuf {
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
+    bool owned = true;  // false: a view into a Slab (the slab's owner frees it)
+    void view(void *at, size_t count) {
+        release();
+        p = reinterpret_cast<T *>(at);
+        n = count;
+        owned = false;
+    }
     void alloc(size_t count) {
         release();
         if (count) {
             cudaGetDevice(&dev);
             cudaError_t e = cudaMallocAsync((void **)&p, count * sizeof(T), 0);
             if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+            if (e == cudaErrorMemoryAllocation && slab_parked_bytes()) {  // a parked scratch slab is in the way
+                cudaGetLastError();
+                slab_free_parked();
+                e = cudaMallocAsync((void **)&p, count * sizeof(T), 0);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+            }
             if (e == cudaErrorMemoryAllocation) {
                 cudaGetLastError();
                 p = nullptr;
@@ -88,7 +180,7 @@ struct DevBuf {
     // Callers release buffers whose consumer stream has been synchronised; on an exception the
     // C-ABI wrapper (`guarded`) synchronises the device before anything can be allocated again.
     void release() {
-        if (p) {
+        if (p && owned) {
             int cur = dev;
             cudaGetDevice(&cur);
             if (cur != dev) cudaSetDevice(dev);
@@ -97,10 +189,12 @@ struct DevBuf {
         }
         p = nullptr;
         n = 0;
+        owned = true;
     }
     size_t bytes() const { return n * sizeof(T); }
     ~DevBuf() { release(); }
 };
+
 
 struct DeviceCSR {
     DevBuf<uint32_t> row, col, eid;
@@ -171,10 +265,12 @@ struct BcWorkspace {
     uint64_t wanted = 0;    // groups asked for when `ng` was sized (may have been clamped by memory)
     uint32_t tagbase = 0;   // tags already used in P0/P1
     uint32_t dirty_levels = 0;  // prefix of the level tables the last batch wrote
+    Slab slab;              // every array above is a view into this one allocation
     void release() {
         sc.release(); sig32.release(); overflow.release(); P0.release(); P1.release(); visited.release(); qv.release(); qm.release(); qe.release();
         loff.release(); lvlcnt.release(); lvl_total.release(); src.release(); reach.release();
         hubv.release(); hubm.release(); hubcnt.release(); maybe.release();
+        slab_release(slab);
         ng = 0;
         qper = 0;
         wanted = 0;
@@ -751,25 +847,42 @@ static uint64_t bc_ws_ensure(rxc_graph *g, uint64_t total_groups) {
         ws.release();
         g->bfs_ws.release();  // one scratch set at a time keeps the footprint predictable
         ws.wanted = ng;
-        ng = std::min<uint64_t>(ng, std::max<uint64_t>(1, (uint64_t)((double)device_budget(g->opt.mem_fraction_pct) / per_group)));
-        ws.sc.alloc((size_t)ng * n * BG);
-        ws.sig32.alloc((size_t)ng * n * BG);
-        ws.overflow.alloc(1);
-        ws.P0.alloc((size_t)ng * n);
-        ws.P1.alloc((size_t)ng * n);
-        ws.visited.alloc((size_t)ng * n);
-        ws.qv.alloc((size_t)ng * qcap);
-        ws.qm.alloc((size_t)ng * qcap);
-        ws.qe.alloc((size_t)ng * qcap);
-        ws.loff.alloc((size_t)ng * lcap);
-        ws.lvlcnt.alloc((size_t)ng * lcap);
-        ws.lvl_total.alloc(lcap);
-        ws.src.alloc((size_t)ng * BG);
-        ws.reach.alloc((size_t)ng * BG);
-        ws.hubv.alloc((size_t)ng * HUB_CAP);
-        ws.hubm.alloc((size_t)ng * HUB_CAP);
-        ws.hubcnt.alloc((size_t)2 * ng);
-        ws.maybe.alloc((size_t)ng * ((n + 31) / 32));
+        // (a parked slab is ours to re-use or to free: it counts as available)
+        ng = std::min<uint64_t>(ng, std::max<uint64_t>(1, (uint64_t)(((double)device_budget(g->opt.mem_fraction_pct) +
+                                                                       (double)slab_parked_bytes()) / per_group)));
+        // one slab, carved into 256-byte aligned arrays (two passes: measure, then place)
+        size_t off = 0;
+        char *base = nullptr;
+        auto carve = [&](auto &buf, size_t count) {
+            using Elem = std::remove_pointer_t<decltype(buf.p)>;
+            if (base) buf.view(base + off, count);
+            off = (off + count * sizeof(Elem) + 255) & ~(size_t)255;
+        };
+        auto carve_all = [&]() {
+            off = 0;
+            carve(ws.sc, (size_t)ng * n * BG);
+            carve(ws.sig32, (size_t)ng * n * BG);
+            carve(ws.overflow, 1);
+            carve(ws.P0, (size_t)ng * n);
+            carve(ws.P1, (size_t)ng * n);
+            carve(ws.visited, (size_t)ng * n);
+            carve(ws.qv, (size_t)ng * qcap);
+            carve(ws.qm, (size_t)ng * qcap);
+            carve(ws.qe, (size_t)ng * qcap);
+            carve(ws.loff, (size_t)ng * lcap);
+            carve(ws.lvlcnt, (size_t)ng * lcap);
+            carve(ws.lvl_total, lcap);
+            carve(ws.src, (size_t)ng * BG);
+            carve(ws.reach, (size_t)ng * BG);
+            carve(ws.hubv, (size_t)ng * HUB_CAP);
+            carve(ws.hubm, (size_t)ng * HUB_CAP);
+            carve(ws.hubcnt, (size_t)2 * ng);
+            carve(ws.maybe, (size_t)ng * ((n + 31) / 32));
+        };
+        carve_all();
+        ws.slab = slab_acquire(off);
+        base = ws.slab.base;
+        carve_all();
         RXC_CUDA(cudaMemsetAsync(ws.maybe.p, 0, ws.maybe.bytes(), st));
         ws.ng = ng;
         ws.qper = qper;
@@ -2300,6 +2413,7 @@ int rxc_snapshot_cache_clear(void) {
     const int n = (int)g_cache.size();
     for (rxc_graph *c : g_cache) graph_unref_locked(c);
     g_cache.clear();
+    slab_free_parked();
     return n;
 }
 

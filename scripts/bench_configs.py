@@ -10,6 +10,9 @@ import os
 import sys
 import time
 
+# the oracle's OpenMP workers spin after a parallel region: left active they steal the host thread of
+# the next case's end-to-end call (seen as 10-70 ms outliers on the 4 ms calls of config 1)
+os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
