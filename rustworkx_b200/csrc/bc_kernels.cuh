@@ -512,8 +512,7 @@ __device__ __forceinline__ void bc_gather(const Elem *rows, uint32_t v_lane, con
         // off.  (ptxas puts three padding LDS in front of every LDGSTS that follows an LDS or opens a
         // basic block; with a branch and a table read per slot that was 6 of the ~45 issue slots a
         // gathered row costs.)
-        constexpr int NB = NS % 3 == 0 ? 3 : 2;  // slots per block
-        static_assert(NS % NB == 0, "row slots come in blocks of 2 or 3");
+        constexpr int NB = NS % 3 == 0 ? 3 : (NS % 2 == 0 ? 2 : 1);  // slots per block
 #pragma unroll
         for (int b = 0; b < NS; b += NB) {
             if (b < cnt) {  // warp-uniform
