@@ -437,6 +437,7 @@ struct rxc_graph {
     std::mutex mu;
     Options opt;    // the tunables this call runs with: copied from the process defaults by begin_call()
     int sms = 148;  // cudaDevAttrMultiProcessorCount of `device`
+    std::vector<uint32_t> order_cnt;  // bc_order_sources: children per hub, all zero between calls
     uint64_t cache_key[2] = {0, 0};  // rxc_graph_snapshot_cached: content hash (0,0: not cached)
     int refs = 1;                    // rxc_graph_snapshot_cached / rxc_graph_free
 
@@ -936,22 +937,55 @@ static std::vector<uint32_t> bc_order_sources(rxc_graph *g, const std::vector<ui
     }
     RXC_CUDA(cudaStreamSynchronize(st));  // also: before the device buffers go back to the pool
     const uint32_t SIBLINGS = (uint32_t)std::max<int64_t>(1, g->opt.bc_siblings);
+    // Host side of the ordering, written for k = 10^6 (a full run orders every vertex): children per
+    // hub are counted in a table kept in the handle (zeroed again below: O(k), not O(n)), the sort
+    // runs on packed 16-byte records -- (cluster, inverted key, source), plain lexicographic order --
+    // and on up to 8 threads with pairwise merges.  The first version (a binary search per source
+    // for its cluster size, an index sort through three arrays) took 0.85 s for 10^6 sources on one
+    // core -- 5 % of the whole job's wall clock on 8 GPUs; this one 0.1 s.
+    struct Rec {
+        uint32_t hub, src;
+        unsigned long long invkey;
+    };
+    auto less = [](const Rec &a, const Rec &b) {
+        if (a.hub != b.hub) return a.hub < b.hub;  // 0xFFFFFFFF (no cluster) last
+        if (a.invkey != b.invkey) return a.invkey < b.invkey;  // larger key first
+        return a.src < b.src;
+    };
+    std::vector<Rec> rec(k);
     if (!hubs.empty()) {  // hubs with too few children in this call do not form a cluster
-        std::vector<uint32_t> by_hub(hubs);
-        std::sort(by_hub.begin(), by_hub.end());
-        for (size_t i = 0; i < k; i++) {
-            const auto range = std::equal_range(by_hub.begin(), by_hub.end(), hubs[i]);
-            if ((size_t)(range.second - range.first) < SIBLINGS) hubs[i] = 0xFFFFFFFFu;
+        std::vector<uint32_t> &cnt = g->order_cnt;
+        if (cnt.size() < g->host.n_live) cnt.assign(g->host.n_live, 0);
+        for (size_t i = 0; i < k; i++) cnt[hubs[i]]++;
+        for (size_t i = 0; i < k; i++)
+            rec[i] = Rec{cnt[hubs[i]] < SIBLINGS ? 0xFFFFFFFFu : hubs[i], sources[i], ~keys[i]};
+        for (size_t i = 0; i < k; i++) cnt[hubs[i]] = 0;
+    } else {
+        for (size_t i = 0; i < k; i++) rec[i] = Rec{0xFFFFFFFFu, sources[i], ~keys[i]};
+    }
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int T = k < 32768 ? 1 : (int)std::min<unsigned>(8, hw);
+    if (T == 1) {
+        std::sort(rec.begin(), rec.end(), less);
+    } else {
+        std::vector<size_t> cut(T + 1);
+        for (int t = 0; t <= T; t++) cut[t] = k * (size_t)t / T;
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; t++)
+            th.emplace_back([&, t] { std::sort(rec.begin() + cut[t], rec.begin() + cut[t + 1], less); });
+        for (auto &x : th) x.join();
+        for (int w = 1; w < T; w *= 2) {
+            th.clear();
+            for (int t = 0; t + w < T; t += 2 * w)
+                th.emplace_back([&, t, w] {
+                    std::inplace_merge(rec.begin() + cut[t], rec.begin() + cut[t + w],
+                                       rec.begin() + cut[std::min(T, t + 2 * w)], less);
+                });
+            for (auto &x : th) x.join();
         }
     }
-    std::vector<uint32_t> idx(k);
-    for (size_t i = 0; i < k; i++) idx[i] = (uint32_t)i;
-    std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {
-        if (!hubs.empty() && hubs[a] != hubs[b]) return hubs[a] < hubs[b];  // 0xFFFFFFFF (no cluster) last
-        return keys[a] != keys[b] ? keys[a] > keys[b] : sources[a] < sources[b];
-    });
     std::vector<uint32_t> out(k);
-    for (size_t i = 0; i < k; i++) out[i] = sources[idx[i]];
+    for (size_t i = 0; i < k; i++) out[i] = rec[i].src;
     return out;
 }
 
