@@ -437,6 +437,7 @@ struct rxc_graph {
     std::mutex mu;
     Options opt;    // the tunables this call runs with: copied from the process defaults by begin_call()
     int sms = 148;  // cudaDevAttrMultiProcessorCount of `device`
+    uint32_t last_levels = 0;         // run_levels: levels launched by the previous level loop
     std::vector<uint32_t> order_cnt;  // bc_order_sources: children per hub, all zero between calls
     uint64_t cache_key[2] = {0, 0};  // rxc_graph_snapshot_cached: content hash (0,0: not cached)
     int refs = 1;                    // rxc_graph_snapshot_cached / rxc_graph_free
@@ -754,10 +755,16 @@ static std::vector<std::vector<uint32_t>> distinct_rounds(const std::vector<uint
 // Launch `launch(level)` for level = 0, 1, ... in growing speculative chunks and return the number
 // of BFS levels (first level whose total frontier is empty).  lvl_total[l] is final once the launch
 // for level l-1 has completed; launches past the end find empty frontiers and return at once.
+// The first chunk is what the previous level loop on the handle needed, plus one: batches of one call
+// have the same depth give or take a level, so the usual batch costs one chunk, one read-back and
+// one launch past its last level.
 template <class F>
 static uint32_t run_levels(rxc_graph *g, uint32_t *d_lvl_total, uint32_t n, F &&launch,
                            std::vector<uint32_t> &h_totals) {
-    uint32_t level = 0, checked = 1, chunk = 4;
+    uint32_t level = 0, checked = 1;
+    const bool adaptive = g->last_levels != 0;
+    uint32_t chunk = adaptive ? std::min<uint32_t>(g->last_levels + 1, 64) : 4;
+    const uint32_t first = chunk;
     h_totals.assign(1, 0);
     for (;;) {
         uint32_t launched = 0;
@@ -771,11 +778,19 @@ static uint32_t run_levels(rxc_graph *g, uint32_t *d_lvl_total, uint32_t n, F &&
                                  (size_t)(level + 1 - checked) * 4, cudaMemcpyDeviceToHost,
                                  g->stream));
         RXC_CUDA(cudaStreamSynchronize(g->stream));
-        for (uint32_t l = checked; l <= level; l++)
-            if (h_totals[l] == 0) return l;
+        for (uint32_t l = checked; l <= level; l++) {
+            if (h_totals[l] == 0) {
+                g->last_levels = l;
+                return l;
+            }
+        }
         checked = level + 1;
-        if (level >= n) return level;
-        chunk = std::min<uint32_t>(chunk * 2, 64);
+        if (level >= n) {
+            g->last_levels = level;
+            return level;
+        }
+        // the guess was short: carry on in small chunks that double
+        chunk = (adaptive && checked == level + 1 && level == first) ? 4 : std::min<uint32_t>(chunk * 2, 64);
     }
 }
 
