@@ -241,3 +241,62 @@ def newman_weighted_closeness_centrality(graph, edge_weight, wf_improved=True, *
         dense[mine.astype(np.int64)] = compute_partial(edge_weight, mine)
     total = reduce_partial(dense)
     return total[: int(snap["n_bound"])] if rank == 0 else None
+
+
+def closeness_centrality(graph, wf_improved=True, *, rank=None, world=None, compute_partial=None):
+    """``closeness_centrality`` (``centrality.rs:1166-1224``) with the sources sharded: closeness is a
+    per-source value, so every rank fills the entries of its own sources in a zero vector and one
+    sum-reduce assembles them (x + 0 is exact: the result stays bit-identical to a single-GPU call).
+    ``compute_partial(sources, wf_improved) -> f64[len(sources)]`` defaults to
+    ``rxc_closeness_partial``.  Dense vector over original node indices on rank 0, ``None`` elsewhere."""
+    rank, world = _world(rank, world)
+    snap = graph._snapshot_arrays()
+    mine = shard_sources(snap["live_nodes"], rank, world)
+    if compute_partial is None:
+        from . import device_snapshot
+
+        dg = device_snapshot(graph)
+        compute_partial = lambda s, wf: dg.closeness_partial(s, wf)  # noqa: E731
+    dense = np.zeros(max(int(snap["n_bound"]), 1), dtype=np.float64)
+    if mine.size:
+        dense[mine.astype(np.int64)] = compute_partial(mine, bool(wf_improved))
+    total = reduce_partial(dense)
+    return total[: int(snap["n_bound"])] if rank == 0 else None
+
+
+def distance_matrix(graph, as_undirected=False, null_value=0.0, *, rank=None, world=None,
+                    compute_rows=None):
+    """Unweighted ``distance_matrix`` (``distance_matrix.rs:71-159``) with the ROWS sharded: rank r
+    computes the contiguous block of rows ``[r n / world, (r + 1) n / world)`` of the compacted matrix
+    (``rxc_distance_matrix_rows``) and rank 0 gathers the blocks -- outputs are disjoint, there is
+    nothing to reduce.  ``compute_rows(row_begin, row_end, as_undirected, null_value) ->
+    f64[rows][n]`` defaults to the CUDA path.  The n x n matrix on rank 0, ``None`` elsewhere."""
+    rank, world = _world(rank, world)
+    n = int(graph._snapshot_arrays()["live_nodes"].shape[0])
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    if compute_rows is None:
+        from . import device_snapshot
+
+        dg = device_snapshot(graph)
+        compute_rows = dg.distance_matrix_rows
+    block = np.ascontiguousarray(compute_rows(lo, hi, bool(as_undirected), float(null_value)),
+                                 dtype=np.float64).reshape(hi - lo, n)
+    dist = _dist()
+    if dist is None or world == 1:
+        return block
+    import torch
+
+    cuda = dist.get_backend() == "nccl"
+    mine = torch.from_numpy(block)
+    if cuda:
+        mine = mine.cuda()
+    if rank == 0:
+        parts = [torch.empty((n * (r + 1) // world - n * r // world, n), dtype=torch.float64,
+                             device=mine.device) for r in range(world)]
+        parts[0] = mine
+        ops = [dist.irecv(parts[r], src=r) for r in range(1, world)]
+        for op in ops:
+            op.wait()
+        return torch.cat(parts, 0).cpu().numpy()
+    dist.send(mine, dst=0)
+    return None

@@ -27,6 +27,9 @@ gb = rxd.group_betweenness_centrality(g, group, True)
 _, eb = g._bounds()
 w = np.random.default_rng(3).uniform(0.1, 2.0, size=eb)
 nw = rxd.newman_weighted_closeness_centrality(g, w, True)
+cc = rxd.closeness_centrality(g, True)
+h = rx.generators.heavy_hex_graph(7)
+dm = rxd.distance_matrix(h, False, -1.0)
 if rank == 0:
     import oracle
     og = oracle.OracleGraph.from_graph(g)
@@ -37,9 +40,12 @@ if rank == 0:
     assert abs(gb - og.group_betweenness_centrality(group, True, 50)) <= 1e-9 * abs(gb)
     want_nw, _ = og.newman_weighted_closeness_centrality(w, True, 50, as_arrays=True)
     assert np.allclose(nw, want_nw, rtol=1e-12, atol=0.0)
+    want_cc, _ = og.closeness_centrality(True, 50, as_arrays=True)
+    assert np.array_equal(cc, want_cc)  # per-source values: sharding keeps them bit-identical
+    assert np.array_equal(dm, oracle.OracleGraph.from_graph(h).distance_matrix(300, False, -1.0))
     print("NCCL_OK")
 else:
-    assert node is None and edge is None
+    assert node is None and edge is None and cc is None and dm is None
 dist.barrier()
 dist.destroy_process_group()
 """

@@ -302,7 +302,13 @@ _, eb = g._bounds()
 w = np.random.default_rng(3).uniform(0.1, 2.0, size=eb)
 nw = rxd.newman_weighted_closeness_centrality(g, w, True,
         compute_partial=lambda ww, s: og.weighted_closeness_partial(ww, s)[0][s])
+cc = rxd.closeness_centrality(g, True, compute_partial=lambda s, wf: og.closeness_partial(s, wf)[0][s])
+full_dm, _ = og.distance_matrix(1 << 30, False, -1.0, return_stats=True)
+dm = rxd.distance_matrix(g, False, -1.0, compute_rows=lambda lo, hi, und, nv: full_dm[lo:hi])
 if dist.get_rank() == 0:
+    want_cc, _ = og.closeness_centrality(True, 1 << 30, as_arrays=True)
+    assert np.array_equal(cc, want_cc)  # per-source values: the sharded result is bit-identical
+    assert np.array_equal(dm, full_dm) and dm.shape == (g.num_nodes(), g.num_nodes())
     assert abs(gb - og.group_betweenness_centrality(group, True, 1 << 30)) <= 1e-12 * abs(gb)
     want_nw, _ = og.newman_weighted_closeness_centrality(w, True, 1 << 30, as_arrays=True)
     assert np.array_equal(nw, want_nw)
@@ -312,7 +318,7 @@ if dist.get_rank() == 0:
     assert np.allclose(edge, want_e, rtol=1e-12, atol=1e-15)
     print("GLOO_OK")
 else:
-    assert node is None and edge is None and gb is None and nw is None
+    assert node is None and edge is None and gb is None and nw is None and cc is None and dm is None
 dist.destroy_process_group()
 """
 
