@@ -225,7 +225,7 @@ struct Options {
     int64_t device_csr = 1;      // build the CSR on the device (0: host counting sort)
     int64_t bfs_depth_switch = 48;  // auto: pilot BFS deeper than this many levels -> mode 2
     int64_t bc_sigma = 0;           // betweenness sigma rows: 0 auto (uint32, f64 on overflow), 1 f64, 2 uint32
-    int64_t bfs_threads = 0;        // CTA-per-source BFS: threads per CTA (0: 1024 for n >= 2^18, else 256)
+    int64_t bfs_threads = 0;        // CTA-per-source BFS: threads per CTA (0: 128 / 256 / 512 / 1024 by n)
     int64_t bfs_ell = 1;            // CTA-per-source BFS: ELL adjacency when every vertex has <= 4 arcs
     int64_t bc_bwd_ctas = 32768;    // dependency sweep: CTAs of one launch, all groups together (0: one warp per 1..8 entries).
                                     // Measured on BA(10^6,8), 16384 sources: 8192 -> 920 ms, 32768 -> 900, 131072 -> 907, 0 -> 915;
@@ -1659,7 +1659,10 @@ static void bfs128_run(rxc_graph *g, const DeviceCSR &push, const DeviceCSR &pul
 // fits next to the frontier queues, otherwise to a per-CTA slab in global memory.
 static bool smem_bfs_fits(uint32_t n, uint32_t *qs_out, size_t *bytes_out, bool *global_bitmap = nullptr) {
     const uint32_t words = (n + 31) / 32;
-    const uint32_t qs = std::min<uint32_t>(SB_QS, ((n + 31) / 32) * 32);
+    // Queue entries kept in shared memory (the rest spills to global memory).  Small graphs get a
+    // quarter of n (at least 1024): a frontier of a lattice is a thin ring, and at n = 6451
+    // (heavy-hex d = 51) full-size queues (52 KB) allowed 4 CTAs per SM where 14 KB allow 8.
+    const uint32_t qs = std::min<uint32_t>(SB_QS, std::max<uint32_t>(1024, ((n / 4 + 31) / 32) * 32));
     size_t bytes = ((size_t)words + 2 * (size_t)qs) * 4;
     bool global_bm = false;
     if (bytes > 200 * 1024) {
@@ -1712,7 +1715,11 @@ static void bfs_smem_run(rxc_graph *g, const DeviceCSR &csr, const uint32_t *sou
             RXC_CUDA(cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_done = true;
     }
-    const int threads = g->opt.bfs_threads > 0 ? (int)g->opt.bfs_threads : (n >= (1u << 18) ? 1024 : 256);
+    // threads per source: a level of a small lattice has a few dozen frontier vertices, and more
+    // sources per SM beat more threads per source (heavy-hex d = 51, n = 6451: 128 threads 0.88 ms,
+    // 256 1.20, 512 2.00; grid 300 x 300: 512 threads 121 ms, 256 134, 128 178, 1024 245)
+    const int auto_threads = n >= (1u << 18) ? 1024 : (n >= (1u << 16) ? 512 : (n >= (1u << 14) ? 256 : 128));
+    const int threads = g->opt.bfs_threads > 0 ? (int)g->opt.bfs_threads : auto_threads;
     int per_sm = 1;
     const int sms = g->sms;
     RXC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
