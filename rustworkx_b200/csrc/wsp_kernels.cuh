@@ -52,7 +52,13 @@ struct WspParams {
 };
 
 // row slots + arc table + the per-arc costs, per warp
-constexpr int WSP_SMEM_BYTES = BC_SMEM_BYTES + WARPS * ARCTAB_AUX_BYTES;
+// Newman closeness, BA(10^6,8), 1024 sources: 4 slots (4 CTAs/SM) 143.1 ms, 5 slots 143.0, 6 slots
+// (3 CTAs/SM) 138.6
+#ifndef RXC_WSTAGE
+#define RXC_WSTAGE 6
+#endif
+constexpr int WSTAGE = RXC_WSTAGE;  // f64 row slots per warp in wsp_relax_kernel
+constexpr int WSP_SMEM_BYTES = WARPS * (WSTAGE * BG * 8 + ARCTAB_BYTES + ARCTAB_AUX_BYTES);
 
 __device__ __forceinline__ PEntry *wsp_C(const WspParams &p, uint32_t round) {
     return (round & 1) ? p.C1 : p.C0;
@@ -192,7 +198,7 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) wsp_relax_kernel(WspPara
                 relaxed += mask_popc(m);  // per lane; summed over the warp at the end
                 // next_score = node_score + cost, dijkstra.rs:128 -- through the arc table of the
                 // betweenness gathers, the arc's cost riding along as the per-arc scalar
-                bc_gather<STAGE, double, double, GatherMinPlus>(rows, v, m, nz, lane, stage, best, c);
+                bc_gather<WSTAGE, double, double, GatherMinPlus>(rows, v, m, nz, lane, stage, best, c);
             }
         }
         if (!mask_any(touched)) continue;
