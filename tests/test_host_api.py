@@ -28,6 +28,20 @@ def rx():
 
 
 # --------------------------------------------------------------------------------- C-ABI surface
+def test_stats_struct_mirror_matches_the_header(rx):
+    """rxc_stats is filled by the library and read through ctypes: same fields, same order, 8 bytes each."""
+    from rustworkx_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "rxcuda.h")).read()
+    body = header[header.index("typedef struct {"):header.index("} rxc_stats;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    declared = re.findall(r"\b(uint64_t|double)\s+(\w+)\s*;", body)
+    assert [name for _, name in declared] == [name for name, _ in _lib.Stats._fields_]
+    for (ctype, name), (_, field) in zip(declared, _lib.Stats._fields_):
+        assert field is (ctypes.c_uint64 if ctype == "uint64_t" else ctypes.c_double), name
+    assert ctypes.sizeof(_lib.Stats) == 8 * len(declared)
+
+
 def test_header_symbols_are_exported(rx):
     from rustworkx_b200 import _lib
 
