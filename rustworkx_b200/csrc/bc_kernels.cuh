@@ -879,7 +879,7 @@ __global__ void __launch_bounds__(BLOCK) bc_forward_hub_kernel(BcParams p, uint3
 // Successor pull of one warp over chunks of 32 arcs starting at e0+first with stride `step`.
 // Node mode sums coef rows into acc; edge mode adds sigma[v][b]*coef[w][b], summed over b, to the
 // arc's edge and the same products into acc (centrality.rs:318-325).
-template <bool EDGE>
+template <bool EDGE, int NS = BSTAGE>
 __device__ __forceinline__ void bc_bwd_scan(const BcParams &p, const double *rows,
                                             const PEntry *Pnext, uint32_t tag_next, uint32_t e0,
                                             uint32_t e1, uint32_t first, uint32_t step,
@@ -903,8 +903,9 @@ __device__ __forceinline__ void bc_bwd_scan(const BcParams &p, const double *row
 #endif
         dag += mask_popc(m);  // per lane: the sources of this lane's own arc (summed over the warp at the end)
         if (!EDGE) {
-            bc_gather<BSTAGE>(rows, w, m, nz, lane, stage, acc);
+            bc_gather<NS>(rows, w, m, nz, lane, stage, acc);
         } else {
+            static_assert(!EDGE || NS == BSTAGE, "edge mode stages into the default slots");
             using G = RowGeom<double>;
             const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage);
             const char *lane_rows = reinterpret_cast<const char *>(rows) + 16 * lane;
@@ -1072,6 +1073,177 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) bc_backward_kernel(BcPar
 #pragma unroll
         for (int k = 0; k < BK; k++)
             if (reach[k]) atomicAdd(&p.reach[(size_t)g * BG + k * 32 + lane], reach[k]);
+    }
+    dag = warp_sum_u64(dag);
+    if (lane == 0 && (te | vv | dag)) {
+        stat_add(p.stats, ST_TE, te);
+        stat_add(p.stats, ST_V, vv);
+        stat_add(p.stats, ST_DAG, dag);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Look-ahead variant for LEAF-HEAVY levels (node mode).  On the deepest big level of a small-world
+// graph most entries have no successor on the next level: an entry is a header, 16 look-ups that find
+// nothing, four divisions and a row store -- ~370 instructions and FOUR dependent memory round trips
+// (header -> targets + own sigma -> level masks -> nothing to gather), and the launch runs at a third
+// of the DRAM rate with the issue slots 38 % busy.  Here a warp works on four entries at once: while
+// entry t is finished, the level masks of entry t+1's targets, the targets and the own sigma of entry
+// t+2 and the header of entry t+3 are on their way into lane-private shared-memory slots (cp.async),
+// so the round trips overlap across entries.  The buffers cost two row slots (4 instead of 6), which
+// is why the gather-heavy levels keep the plain kernel: applied to every level the look-ahead was
+// neutral (561.0 against 561.9 ms per 16384 sources, profiles/r02_ab_staging_variants.txt); the host
+// picks it per level (rxcuda.cu: the next level has less than a quarter of this level's entries).
+// ---------------------------------------------------------------------------------------------
+constexpr int LSTAGE = 4;                 // row slots per warp
+constexpr int LOOK_HDR = 16 * MQ + 16;    // mask, arc range, vertex of one queue entry
+constexpr int LOOK_BYTES = 4 * LOOK_HDR + 2 * 128 + 128 + 32 * 16 * MQ + 2 * 32 * 4 * BK;  // per warp
+constexpr int BC_BWD_LOOK_SMEM_BYTES = WARPS * (LSTAGE * BG * 8 + ARCTAB_BYTES + LOOK_BYTES);
+
+template <bool ENDPOINTS, bool NARROW>
+__global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) bc_backward_look_kernel(BcParams p, uint32_t level) {
+    const uint32_t g = blockIdx.y;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *bc_hubcnt(p, level + 1, g) = 0;  // for the next launch
+    const uint32_t cnt = p.lvlcnt[(size_t)g * p.lcap + level];
+    const uint32_t off = p.loff[(size_t)g * p.lcap + level];
+    const int lane = lane_id();
+    const size_t gn = (size_t)g * p.n;
+    const PEntry *Pnext = bc_P(p, level + 1) + gn;
+    PEntry *Pcur = bc_P(p, level) + gn;
+    double *rows = p.sc + gn * BG;
+    const uint32_t tag_cur = p.tagbase + level + 1, tag_next = tag_cur + 1;
+    const uint32_t *qv = p.qv + (size_t)g * p.qcap + off;
+    const SrcMask *qm = p.qm + (size_t)g * p.qcap + off;
+    const uint2 *qe = p.qe + (size_t)g * p.qcap + off;
+
+    extern __shared__ __align__(16) char s_dyn_stage[];
+    char *stage = s_dyn_stage + (size_t)(threadIdx.x >> 5) * (BC_BWD_LOOK_SMEM_BYTES / WARPS);
+    // look-ahead buffers of this warp, behind its row slots and arc table
+    char *look = stage + LSTAGE * BG * 8 + ARCTAB_BYTES;
+    char *l_hdr = look;                                                   // [4][LOOK_HDR]
+    uint32_t *l_col = reinterpret_cast<uint32_t *>(look + 4 * LOOK_HDR);  // [2][32]
+    uint32_t *l_tag = l_col + 64;                                         // [32]
+    SrcMask *l_mask = reinterpret_cast<SrcMask *>(l_tag + 32);            // [32]
+    uint32_t *l_sig = reinterpret_cast<uint32_t *>(l_mask + 32);          // [2][32][BK]: own uint32 counts
+    const uint32_t a_hdr = (uint32_t)__cvta_generic_to_shared(l_hdr);
+    const uint32_t a_col = (uint32_t)__cvta_generic_to_shared(l_col) + 4u * lane;
+    const uint32_t a_tag = (uint32_t)__cvta_generic_to_shared(l_tag) + 4u * lane;
+    const uint32_t a_mask = (uint32_t)__cvta_generic_to_shared(l_mask) + (uint32_t)sizeof(SrcMask) * lane;
+    const uint32_t a_sig = (uint32_t)__cvta_generic_to_shared(l_sig) + 4u * BK * lane;
+
+    unsigned long long te = 0, vv = 0, dag = 0;
+    unsigned long long reach[BK] = {};
+    const uint32_t warp = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    const uint32_t stride = gridDim.x * WARPS;
+    const uint32_t nw = cnt > warp ? (cnt - warp + stride - 1) / stride : 0;  // entries of this warp
+    // step k: header of entry k; targets and own sigma of entry k-1; level masks of entry k-2; entry
+    // k-3 is finished.  Every slot is written and read by the same lane, except the headers, which
+    // the __syncwarp below publishes.
+    for (uint32_t k = 0; k < nw + 3; k++) {
+        cp_async_wait_all();
+        __syncwarp();
+        uint32_t v = 0, e0 = 0, e1 = 0, w0 = 0;
+        SrcMask fm = mask_zero(), m0 = mask_zero();
+        RowK sg;
+#pragma unroll
+        for (int j = 0; j < BK; j++) sg.x[j] = 0.0;
+        if (k >= 3) {
+            const char *h = l_hdr + ((k - 3) & 3) * LOOK_HDR;
+            fm = mask_load(reinterpret_cast<const SrcMask *>(h));
+            const uint2 ee = *reinterpret_cast<const uint2 *>(h + 16 * MQ);
+            v = *reinterpret_cast<const uint32_t *>(h + 16 * MQ + 8);
+            e0 = ee.x;
+            e1 = ee.y;
+            if (e0 + lane < e1) {
+                w0 = l_col[((k - 3) & 1) * 32 + lane];
+                m0 = mask_load(&l_mask[lane]);
+                const bool ok = l_tag[lane] == tag_next;
+#pragma unroll
+                for (int j = 0; j < BK; j++) m0.w[j] = ok ? (m0.w[j] & fm.w[j]) : 0u;
+            }
+            if (NARROW && ((mask_or(fm) >> lane) & 1u)) {
+#pragma unroll
+                for (int q = 0; q < MQ; q++) {
+                    const uint4 t = reinterpret_cast<const uint4 *>(l_sig + ((k - 3) & 1) * 32 * BK + lane * BK)[q];
+                    sg.x[4 * q] = (double)t.x;
+                    sg.x[4 * q + 1] = (double)t.y;
+                    sg.x[4 * q + 2] = (double)t.z;
+                    sg.x[4 * q + 3] = (double)t.w;
+                }
+            }
+        }
+        if (k >= 2 && k - 2 < nw) {  // level masks of entry k-2's first 32 targets
+            const char *h = l_hdr + ((k - 2) & 3) * LOOK_HDR;
+            const uint2 ee = *reinterpret_cast<const uint2 *>(h + 16 * MQ);
+            if (ee.x + lane < ee.y) {
+                const PEntry *pe = Pnext + l_col[((k - 2) & 1) * 32 + lane];
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(a_tag), "l"(pe) : "memory");
+#pragma unroll
+                for (int q = 0; q < MQ; q++)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(a_mask + 16u * q),
+                                 "l"(reinterpret_cast<const uint4 *>(pe) + MQ + q)
+                                 : "memory");
+            }
+        }
+        if (k >= 1 && k - 1 < nw) {  // first 32 targets and own sigma of entry k-1
+            const char *h = l_hdr + ((k - 1) & 3) * LOOK_HDR;
+            const uint2 ee = *reinterpret_cast<const uint2 *>(h + 16 * MQ);
+            if (ee.x + lane < ee.y)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(a_col + 128u * ((k - 1) & 1)),
+                             "l"(p.col + ee.x + lane)
+                             : "memory");
+            if (NARROW) {
+                const SrcMask f1 = mask_load(reinterpret_cast<const SrcMask *>(h));
+                if ((mask_or(f1) >> lane) & 1u) {
+                    const uint32_t v1 = *reinterpret_cast<const uint32_t *>(h + 16 * MQ + 8);
+                    const uint4 *src = reinterpret_cast<const uint4 *>(p.sig32 + (gn + v1) * BG + lane * BK);
+#pragma unroll
+                    for (int q = 0; q < MQ; q++)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
+                                         a_sig + 4u * 32 * BK * ((k - 1) & 1) + 16u * q),
+                                     "l"(src + q)
+                                     : "memory");
+                }
+            }
+        }
+        if (k < nw) {  // header of entry k
+            const size_t i = (size_t)warp + (size_t)k * stride;
+            const uint32_t dst = a_hdr + (k & 3) * LOOK_HDR;
+            if (lane < MQ)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(dst + 16u * lane),
+                             "l"(reinterpret_cast<const uint4 *>(&qm[i]) + lane)
+                             : "memory");
+            else if (lane == MQ)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst + 16u * MQ), "l"(&qe[i]) : "memory");
+            else if (lane == MQ + 1)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst + 16u * MQ + 8u), "l"(&qv[i]) : "memory");
+        }
+        if (k < 3) continue;
+
+        if (lane == 0) {
+            te += (unsigned long long)mask_popc(fm) * (e1 - e0);
+            vv += mask_popc(fm);
+        }
+        if (ENDPOINTS && level > 0) {
+#pragma unroll
+            for (int j = 0; j < BK; j++) reach[j] += (fm.w[j] >> lane) & 1u;
+        }
+        if (e1 - e0 > p.hub_degree && bc_defer_hub(p, level, g, v, fm)) continue;
+        if (!NARROW) sg = bc_load_sigma<false>(p, gn, v, lane, (mask_or(fm) >> lane) & 1u);
+        double acc[BK];  // -0.0: "nothing added yet", see bc_bwd_finish
+#pragma unroll
+        for (int j = 0; j < BK; j++) acc[j] = -0.0;
+        const uint32_t nz = __ballot_sync(FULL, mask_any(m0));
+        dag += mask_popc(m0);
+        bc_gather<LSTAGE>(rows, w0, m0, nz, lane, stage, acc);
+        if (e1 - e0 > 32)  // warp-uniform: the remaining chunks the plain way
+            bc_bwd_scan<false, LSTAGE>(p, rows, Pnext, tag_next, e0, e1, 32, 32, fm, sg.x, lane, stage, acc, dag);
+        bc_bwd_finish<false, ENDPOINTS>(p, v, fm, sg.x, acc, rows, Pcur, tag_cur, level, lane);
+    }
+    if (ENDPOINTS) {
+#pragma unroll
+        for (int j = 0; j < BK; j++)
+            if (reach[j]) atomicAdd(&p.reach[(size_t)g * BG + j * 32 + lane], reach[j]);
     }
     dag = warp_sum_u64(dag);
     if (lane == 0 && (te | vv | dag)) {

@@ -227,6 +227,7 @@ struct Options {
     int64_t bc_sigma = 0;           // betweenness sigma rows: 0 auto (uint32, f64 on overflow), 1 f64, 2 uint32
     int64_t bfs_threads = 0;        // CTA-per-source BFS: threads per CTA (0: 128 / 256 / 512 / 1024 by n)
     int64_t bfs_ell = 1;            // CTA-per-source BFS: ELL adjacency when every vertex has <= 4 arcs
+    int64_t bc_look = 1;            // dependency sweep, look-ahead kernel: 0 never, 1 on leaf-heavy levels, 2 always (node mode)
     int64_t bc_bwd_ctas = 32768;    // dependency sweep: CTAs of one launch, all groups together (0: one warp per 1..8 entries).
                                     // Measured on BA(10^6,8), 16384 sources: 8192 -> 920 ms, 32768 -> 900, 131072 -> 907, 0 -> 915;
                                     // BA(125k,8), 8192 sources: 53.0 / 49.9 / 50.2 / 57.3 ms
@@ -805,7 +806,7 @@ static void bc_enable_smem() {
     if (done) return;
     auto attr = [&](const void *fn) {
         RXC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      std::max(std::max(BC_SMEM_BYTES, BC_FWD32_SMEM_BYTES), BC_BWD_SMEM_BYTES)));
+                                      std::max(std::max(BC_SMEM_BYTES, BC_FWD32_SMEM_BYTES), std::max(BC_BWD_SMEM_BYTES, BC_BWD_LOOK_SMEM_BYTES))));
     };
     attr((const void *)bc_forward_kernel<false>);
     attr((const void *)bc_forward_kernel<true>);
@@ -817,6 +818,10 @@ static void bc_enable_smem() {
     attr((const void *)bc_backward_kernel<true, false, true>);
     attr((const void *)bc_backward_kernel<false, true, true>);
     attr((const void *)bc_backward_kernel<false, false, true>);
+    attr((const void *)bc_backward_look_kernel<false, false>);
+    attr((const void *)bc_backward_look_kernel<false, true>);
+    attr((const void *)bc_backward_look_kernel<true, false>);
+    attr((const void *)bc_backward_look_kernel<true, true>);
     attr((const void *)bc_backward_hub_kernel<true, false, false>);
     attr((const void *)bc_backward_hub_kernel<false, true, false>);
     attr((const void *)bc_backward_hub_kernel<false, false, false>);
@@ -1184,9 +1189,19 @@ static void bc_run(rxc_graph *g, const std::vector<uint32_t> &sources_in, bool e
             if (g->opt.bc_bwd_ctas > 0)  // cap on the CTAs of one launch, all groups together
                 gx = std::min<uint32_t>(gx, (uint32_t)std::max<int64_t>(1, g->opt.bc_bwd_ctas / bg));
             const dim3 grid(gx, bg), hgrid(HUB_CTAS, bg);
+            // leaf-heavy level (the next level has less than a quarter of this one's entries): most
+            // entries gather nothing and are bound by their chain of round trips -> look-ahead kernel
+            uint64_t cnt_here = 0, cnt_next = 0;
+            for (uint32_t gi = 0; gi < bg; gi++) {
+                cnt_here += h_lvlcnt[(size_t)gi * L + l];
+                if (l + 1 < L) cnt_next += h_lvlcnt[(size_t)gi * L + l + 1];
+            }
+            const bool look = !edge_mode && (g->opt.bc_look == 2 || (g->opt.bc_look == 1 && cnt_next * 4 < cnt_here &&
+                                                                     cnt_here >= (uint64_t)g->sms * 256));
 #define RXC_BWD(E, P, N)                                                                \
     do {                                                                                \
-        bc_backward_kernel<E, P, N><<<grid, BLOCK, BC_BWD_SMEM_BYTES, st>>>(p, l);      \
+        if (look) bc_backward_look_kernel<P, N><<<grid, BLOCK, BC_BWD_LOOK_SMEM_BYTES, st>>>(p, l); \
+        else bc_backward_kernel<E, P, N><<<grid, BLOCK, BC_BWD_SMEM_BYTES, st>>>(p, l);      \
         bc_backward_hub_kernel<E, P, N><<<hgrid, BLOCK, BC_BWD_SMEM_BYTES, st>>>(p, l); \
     } while (0)
             if (edge_mode) {
@@ -2822,6 +2837,7 @@ int rxc_set_option(const char *name, int64_t value) {
     else if (k == "bc_order" && value >= 0 && value <= 2) g_opt.bc_order = value;
     else if (k == "bc_siblings" && value >= 1) g_opt.bc_siblings = value;
     else if (k == "bc_bwd_ctas" && value >= 0) g_opt.bc_bwd_ctas = value;
+    else if (k == "bc_look" && value >= 0 && value <= 2) g_opt.bc_look = value;
     else if (k == "bfs_depth_switch" && value >= 0) g_opt.bfs_depth_switch = value;
     else if (k == "bfs_threads" && (value == 0 || value == 128 || value == 256 || value == 512 || value == 1024)) g_opt.bfs_threads = value;
     else if (k == "bc_sigma" && value >= 0 && value <= 2) g_opt.bc_sigma = value;

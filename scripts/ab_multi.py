@@ -12,7 +12,7 @@ g = (rx.directed_gnm_random_graph(2**20, 2**24, seed=7) if os.environ.get("GRAPH
 n = g.num_nodes()
 dg = rx.device_snapshot(g)
 plan = np.random.default_rng(12345).permutation(n).astype(np.uint32)
-DEFAULTS = {"bc_order": 2, "bc_groups": 0, "bc_sigma": 0, "hub_degree": 512, "bc_sparse_div": 16, "bc_siblings": 2, "bc_bwd_ctas": 32768}
+DEFAULTS = {"bc_order": 2, "bc_groups": 0, "bc_sigma": 0, "hub_degree": 512, "bc_sparse_div": 16, "bc_siblings": 2, "bc_bwd_ctas": 32768, "bc_look": 1}
 ref = {}
 for spec in sys.argv[1:]:
     kv = dict(x.split("=") for x in spec.split(";") if x)
