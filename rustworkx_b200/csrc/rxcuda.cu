@@ -102,6 +102,17 @@ static Slab slab_acquire(size_t bytes) {
     }
     cudaError_t e = cudaMalloc((void **)&out.base, bytes);
     if (e == cudaErrorMemoryAllocation) {
+        // the budget counts memory the stream-ordered pool holds in reserve (released buffers of earlier
+        // calls) as available: hand it back to the driver and try once more
+        cudaGetLastError();
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, out.dev) == cudaSuccess) {
+            cudaDeviceSynchronize();
+            cudaMemPoolTrimTo(pool, 0);
+        }
+        e = cudaMalloc((void **)&out.base, bytes);
+    }
+    if (e == cudaErrorMemoryAllocation) {
         cudaGetLastError();
         throw OomError("device allocation of " + std::to_string(bytes) + " bytes failed");
     }
