@@ -1,5 +1,5 @@
 """One betweenness call on the bench graph for ncu (no warm-up: every launch of the call is captured):
-ncu --set full --clock-control none --import-source on -k regex:"bc_(forward|backward)_kernel" -c 40 \
+ncu --set full --clock-control none --import-source on -k regex:"bc_(forward|backward)(_look)?_kernel" -c 40 \
     -o gpurun_out/r02_step python scripts/ncu_step.py [sources]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
