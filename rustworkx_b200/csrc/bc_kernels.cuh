@@ -1016,7 +1016,9 @@ __device__ __forceinline__ void bc_bwd_finish(const BcParams &p, uint32_t v, con
             if (!EDGE && level > 0) contrib += ENDPOINTS ? delta + 1.0 : delta;
         }
     }
-    if (!EDGE && level > 0) {
+    // (an entry without a successor for any of its sources contributes nothing: no reduction, no atomic --
+    // most entries of the deepest levels)
+    if (!EDGE && level > 0 && __any_sync(FULL, contrib != 0.0)) {
         const double tot = warp_sum(contrib);
         if (lane == 0) atomicAdd(&p.acc[v], tot);
     }
