@@ -226,8 +226,11 @@ int rxc_get_stats(const rxc_graph *g, rxc_stats *out);
  *   bc_siblings N      bc_order 2: a hub named by at least N sources of the call forms a cluster (2)
  *   bc_bwd_ctas N      dependency sweep: CTAs of one launch, all groups together (32768; 0: a warp per
  *                      1..8 queue entries)
+ *   bc_look 0|1|2      dependency sweep, look-ahead kernel (a warp prefetches for its next three queue
+ *                      entries): 0 never, 1 (default) on leaf-heavy levels -- the next level has less
+ *                      than a quarter of this level's entries --, 2 on every level (node mode only)
  *   snapshot_cache_entries N  handles rxc_graph_snapshot_cached keeps alive (2)
- *   bfs_threads N      regime 2: threads per CTA (0: 1024 for n >= 2^18, else 256)
+ *   bfs_threads N      regime 2: threads per CTA (0: 128 / 256 / 512 / 1024 for n < 2^14 / 2^16 / 2^18 / above)
  *   bfs_groups N       regime 1: groups of 32 sources per batch (0: up to 4096)
  *   device_csr 0|1     build the CSR on the device (1) or with the host counting sort (0)
  *   mem_fraction_pct N share of free HBM the scratch may take (70)
