@@ -274,7 +274,9 @@ def run_reference(args):
         "work": {"sources_per_step": per_step, "timing": "wall clock around the oracle call, all host threads"},
         "note": "reference Rust crate cannot be built here (no cargo/rustc); this is oracle/ (C "
                 "restatement at -O3, OpenMP over sources with an explicit thread count, one global "
-                "lock as in centrality.rs:107,280)",
+                "lock as in centrality.rs:107,280).  A real rustworkx install, were one importable, has no "
+                "source-subset entry point: its betweenness_centrality always runs all 10^6 sources "
+                "(>= 17 h here), so a bounded sample of this workload can only be timed through the port",
     }
     emit(line)
 
