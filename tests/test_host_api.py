@@ -570,3 +570,43 @@ def test_group_shard_partitions_an_ordered_list(rx):
     with pytest.raises(ValueError):
         group_shard(order, 3, 3)
     assert group_shard(order[:100], 1, 2).shape == (0,)
+
+
+# ------------------------------------------------------------------------------ bench.py contract
+def test_bench_reference_arm_prints_one_contract_line(rx, oracle):
+    """`bench.py --impl reference` on a small instance of the workload: ONE JSON line on stdout with the
+    driver's keys, the CPU arm's own cpu_baseline / e2e blocks, and no GPU launches."""
+    import json
+
+    proc = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                           "--warmup", "1", "--nodes", "3000", "--m", "4", "--cpu-sample", "16"],
+                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = [ln for ln in proc.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, proc.stdout
+    line = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["metric"] == "all_sources_betweenness_gteps"
+    assert line["unit"] == "GTEPS" and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert line["value"] > 0 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "GTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and "model" not in line["config"]
+    assert line["gpu_launches"] == 0
+
+
+def test_bench_roofline_inputs_parse(rx):
+    """The committed evidence bench.py reads for `roofline.traffic` / `line_requests` is well formed."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    traffic, src = bench.ncu_traffic()
+    assert {"bc_forward_kernel", "bc_backward_kernel"} <= set(traffic) and "profiles/" in src
+    assert all(v["dram_bytes_per_source"] > 1e6 for v in traffic.values())
+    pl = bench.probe_lines()
+    assert pl and 40.0 < pl["ceiling_glines_s"] < 80.0
+    for k in ("bc_forward_kernel", "bc_backward_kernel"):
+        ps = pl["per_source"][k]
+        assert ps["lines128"] <= ps["sectors32"] <= 4 * ps["lines128"] and ps["rows"] < ps["lines128"]
