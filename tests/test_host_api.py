@@ -610,3 +610,27 @@ def test_bench_roofline_inputs_parse(rx):
     for k in ("bc_forward_kernel", "bc_backward_kernel"):
         ps = pl["per_source"][k]
         assert ps["lines128"] <= ps["sectors32"] <= 4 * ps["lines128"] and ps["rows"] < ps["lines128"]
+
+
+def test_bench_reference_arm_under_torchrun_prints_once(rx, oracle):
+    """N > 1: the driver launches the reference arm under torchrun too; rank 0 alone runs and prints,
+    the other rank exits 0 without work -- and OMP_NUM_THREADS=1 (torchrun's default) must not
+    shrink the CPU arm to one thread (round 1's 20x handicap)."""
+    import json
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"),
+           "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--nodes", "3000",
+           "--cpu-sample", "16"]  # (no --m: torchrun's own parser takes it for an abbreviation)
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = [ln for ln in proc.stdout.splitlines() if ln.strip().startswith("{")]
+    assert len(lines) == 1, proc.stdout
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2
+    assert line["cpu_baseline"]["cores"] == max(1, len(os.sched_getaffinity(0)))
