@@ -1236,6 +1236,9 @@ __global__ void __launch_bounds__(BLOCK, RXC_MINBLOCKS) bc_backward_look_kernel(
 #pragma unroll
         for (int j = 0; j < BK; j++) acc[j] = -0.0;
         const uint32_t nz = __ballot_sync(FULL, mask_any(m0));
+#if RXC_PROBE
+        if (lane == 0 && e1 > e0) atomicAdd(&g_probe[PR_LOOKUPS64], (unsigned long long)min(32u, e1 - e0));
+#endif
         dag += mask_popc(m0);
         bc_gather<LSTAGE>(rows, w0, m0, nz, lane, stage, acc);
         if (e1 - e0 > 32)  // warp-uniform: the remaining chunks the plain way
